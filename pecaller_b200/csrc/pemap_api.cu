@@ -1,0 +1,898 @@
+// pemap_api.cu - C-ABI (include/pemap.h) over the sm_100a kernels.  Host orchestration only: buffers, streams,
+// launches, copies.  There is no CPU implementation of any stage in this library.
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pemap.h"
+#include "pemap_common.cuh"
+#include "seed_chain.cuh"
+#include "select_finish.cuh"
+#include "sw_wavefront.cuh"
+
+#define PEMAP_VERSION "pemap-b200 0.1 (sm_100a)"
+
+namespace {
+
+constexpr int kSeedWarps = 4;
+constexpr uint64_t kInsCapDefault = 256ull << 20;
+
+struct Timer {
+  cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct pemap_ctx {
+  int device = 0;
+  int sm_count = 148;
+  pemap_params params;
+  pm::DevParams dp;
+  std::string err;
+  int keep = 0;
+
+  // index + genome in HBM
+  uint32_t* d_pos_index = nullptr;
+  uint32_t* d_mers = nullptr;
+  uint64_t n_mers = 0;
+  char* d_genome = nullptr;
+  uint64_t genome_size = 0;
+  uint32_t* d_cstart = nullptr;
+  int n_contigs = 0;
+  double* d_border = nullptr;
+  uint32_t* d_counts = nullptr;
+
+  unsigned char* d_ins = nullptr;
+  unsigned long long* d_ins_cursor = nullptr;
+  uint64_t ins_cap = kInsCapDefault;
+
+  // chunk buffers
+  int chunk = 0;       // reads (pairs) per chunk
+  int stride_cap = 0;  // bytes per read row in the device buffers
+  char* d_reads[2] = {nullptr, nullptr};
+  int* d_len[2] = {nullptr, nullptr};
+  pm::Task* d_tasks = nullptr;
+  pm::TaskResult* d_results = nullptr;
+  uint32_t task_cap = 0;
+  uint32_t* d_cursors = nullptr;  // [0] task cursor, [1] winner cursor
+  uint32_t* d_cand_base = nullptr;
+  uint32_t* d_cand_n = nullptr;
+  pm::Winner* d_winners = nullptr;
+  uint32_t* d_m1 = nullptr;
+  uint32_t* d_m2 = nullptr;
+  int* d_type = nullptr;
+  int32_t* d_det_best = nullptr;
+  int32_t* d_det_orient = nullptr;
+  double* d_det_score = nullptr;
+  uint32_t* d_seed_scratch = nullptr;
+  int seed_blocks = 0;
+  unsigned long long* d_dirs = nullptr;
+  char* d_pend = nullptr;
+  int sw_blocks = 0;
+  pm::SeedCounters* d_counters = nullptr;
+
+  // pinned staging
+  char* h_reads[2] = {nullptr, nullptr};
+  int* h_len[2] = {nullptr, nullptr};
+  uint32_t* h_m1 = nullptr;
+  uint32_t* h_m2 = nullptr;
+  int* h_type = nullptr;
+
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+
+  // retained from the last batch
+  std::vector<pemap_detail> detail;
+  std::vector<uint32_t> cand_base_h, cand_n_h;  // per read-mate, offsets into cand_spot_h
+  std::vector<uint32_t> cand_spot_h;
+  std::vector<int8_t> cand_orient_h;
+
+  // finish buffers
+  std::vector<pemap_record> records;
+  std::vector<pemap_insertion> ins;
+  std::vector<char> ins_pool;
+
+  pemap_stats stats;
+};
+
+namespace {
+
+int fail(pemap_ctx* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      return fail(h, e_ == cudaErrorMemoryAllocation ? PEMAP_ERR_NOMEM : PEMAP_ERR_CUDA,                  \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                                    \
+  } while (0)
+
+void fill_dev_params(pemap_ctx* h) {
+  const pemap_params& p = h->params;
+  pm::DevParams& d = h->dp;
+  const double mb = p.match_bonus;
+  d.match = mb;
+  d.mism = -1.0 / ((double)3.0 * mb);  // pemapper.c:2011
+  d.go = 2.0 * mb;                     // pemapper.c:2039
+  d.ge = mb / 36.0;                    // pemapper.c:2040
+  d.min_align = p.min_align;
+  d.match_bonus = mb;
+  d.idepth = p.idepth;
+  d.max_hits = p.max_hits;
+  d.too_many_spots = p.too_many_spots;
+  d.is_bisulfite = p.is_bisulfite;
+  d.pair_flag = p.pair_flag;
+  d.min_dist = p.min_dist;
+  d.max_dist = p.max_dist;
+  d.misalign_slop = p.misalign_slop;
+  d.n_contigs = h->n_contigs;
+  d.genome_size_lo = (uint32_t)h->genome_size;
+}
+
+int check_params(pemap_ctx* h, const pemap_params* p) {
+  if (!p) return fail(h, PEMAP_ERR_ARG, "params is NULL");
+  if (p->idepth != 16) return fail(h, PEMAP_ERR_UNSUPPORTED, "idepth must be 16 (index_genome_whole.c:149)");
+  if (p->max_hits < 1 || p->max_hits > PM_MAX_HITS) return fail(h, PEMAP_ERR_UNSUPPORTED, "max_hits must be 1..200");
+  if (p->too_many_spots < 1 || p->too_many_spots > 100)
+    return fail(h, PEMAP_ERR_UNSUPPORTED, "too_many_spots must be 1..100");
+  if (p->misalign_slop != 10) return fail(h, PEMAP_ERR_UNSUPPORTED, "misalign_slop must be 10 (MISALIGN_SLOP)");
+  if (!(p->match_bonus > 0)) return fail(h, PEMAP_ERR_ARG, "match_bonus must be > 0");
+  return PEMAP_OK;
+}
+
+int upload_border(pemap_ctx* h) {
+  // S*[0][j] = -(gap_open + (j-1)*gap_extend), init_penalty_matrices pemapper.c:2073-2081, computed on the host
+  // with the reference's own expression (no FMA: this file is built with -ffp-contract=off on the host side).
+  std::vector<double> b(PM_DP_MAX + 1);
+  const volatile double go = h->dp.go, ge = h->dp.ge;
+  b[0] = 0.0;
+  for (int j = 1; j <= PM_DP_MAX; j++) {
+    volatile double prod = (double)(j - 1) * ge;
+    volatile double sum = go + prod;
+    b[j] = -sum;
+  }
+  if (!h->d_border) CK(cudaMalloc(&h->d_border, sizeof(double) * (PM_DP_MAX + 1)));
+  CK(cudaMemcpy(h->d_border, b.data(), sizeof(double) * (PM_DP_MAX + 1), cudaMemcpyHostToDevice));
+  return PEMAP_OK;
+}
+
+int open_device(pemap_ctx* h, int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(h, PEMAP_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0"));
+  if (device < 0 || device >= n) return fail(h, PEMAP_ERR_ARG, "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(h, PEMAP_ERR_CUDA, "device is not sm_100 (this library has only sm_100a code)");
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
+  return PEMAP_OK;
+}
+
+int alloc_chunk_buffers(pemap_ctx* h) {
+  int chunk = 1 << 17;
+  if (const char* s = getenv("PEMAP_CHUNK")) chunk = std::max(1024, atoi(s));
+  h->chunk = chunk;
+  h->stride_cap = PM_DP_MAX;
+  const size_t n = (size_t)chunk;
+  for (int m = 0; m < 2; m++) {
+    CK(cudaMalloc(&h->d_reads[m], n * h->stride_cap));
+    CK(cudaMalloc(&h->d_len[m], n * sizeof(int)));
+    CK(cudaHostAlloc(&h->h_reads[m], n * h->stride_cap, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&h->h_len[m], n * sizeof(int), cudaHostAllocDefault));
+  }
+  CK(cudaHostAlloc(&h->h_m1, n * 4, cudaHostAllocDefault));
+  CK(cudaHostAlloc(&h->h_m2, n * 4, cudaHostAllocDefault));
+  CK(cudaHostAlloc(&h->h_type, n * 4, cudaHostAllocDefault));
+  h->task_cap = (uint32_t)std::min<size_t>(2 * n * PM_MAX_HITS, 0x7FFFFFFFull);
+  CK(cudaMalloc(&h->d_tasks, (size_t)h->task_cap * sizeof(pm::Task)));
+  CK(cudaMalloc(&h->d_results, (size_t)h->task_cap * sizeof(pm::TaskResult)));
+  CK(cudaMalloc(&h->d_cursors, 16));
+  CK(cudaMalloc(&h->d_cand_base, 2 * n * 4));
+  CK(cudaMalloc(&h->d_cand_n, 2 * n * 4));
+  CK(cudaMemset(h->d_cand_n, 0, 2 * n * 4));
+  CK(cudaMemset(h->d_cand_base, 0, 2 * n * 4));
+  CK(cudaMalloc(&h->d_winners, 2 * n * sizeof(pm::Winner)));
+  CK(cudaMalloc(&h->d_m1, n * 4));
+  CK(cudaMalloc(&h->d_m2, n * 4));
+  CK(cudaMalloc(&h->d_type, n * 4));
+  CK(cudaMalloc(&h->d_det_best, 2 * n * 4));
+  CK(cudaMalloc(&h->d_det_orient, 2 * n * 4));
+  CK(cudaMalloc(&h->d_det_score, 2 * n * 8));
+  h->seed_blocks = h->sm_count * 4;
+  CK(cudaMalloc(&h->d_seed_scratch, (size_t)h->seed_blocks * kSeedWarps * 2 * PM_MAX_SEG * PM_SEG_CAP * 4));
+  h->sw_blocks = h->sm_count * 4;
+  const size_t max_groups = (size_t)h->sw_blocks * (128 / 16);
+  // trace scratch: groups * G == sw_blocks * 128 lanes for every instantiation, PM_DP_MAX rows of one word per lane
+  CK(cudaMalloc(&h->d_dirs, (size_t)h->sw_blocks * 128 * PM_DP_MAX * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->d_pend, max_groups * PM_DP_MAX));
+  CK(cudaMalloc(&h->d_counters, sizeof(pm::SeedCounters)));
+  CK(cudaMemset(h->d_counters, 0, sizeof(pm::SeedCounters)));
+  if (const char* s = getenv("PEMAP_INS_MB")) h->ins_cap = (uint64_t)std::max(1, atoi(s)) << 20;
+  CK(cudaMalloc(&h->d_ins, h->ins_cap));
+  CK(cudaMalloc(&h->d_ins_cursor, 8));
+  CK(cudaMemset(h->d_ins_cursor, 0, 8));
+  return PEMAP_OK;
+}
+
+int finish_init(pemap_ctx* h) {
+  fill_dev_params(h);
+  int rc = upload_border(h);
+  if (rc) return rc;
+  CK(cudaMalloc(&h->d_counts, (size_t)h->genome_size * 6 * 4 + 64));
+  CK(cudaMemset(h->d_counts, 0, (size_t)h->genome_size * 6 * 4 + 64));
+  rc = alloc_chunk_buffers(h);
+  if (rc) return rc;
+  memset(&h->stats, 0, sizeof(h->stats));
+  CK(cudaDeviceSynchronize());
+  return PEMAP_OK;
+}
+
+int upload_cstart(pemap_ctx* h, const uint32_t* cs, int n_contigs) {
+  std::vector<uint32_t> pad((size_t)std::max(n_contigs + 1, 16), 0u);
+  for (int i = 0; i <= n_contigs; i++) pad[i] = cs[i];
+  CK(cudaMalloc(&h->d_cstart, pad.size() * 4));
+  CK(cudaMemcpy(h->d_cstart, pad.data(), pad.size() * 4, cudaMemcpyHostToDevice));
+  return PEMAP_OK;
+}
+
+int check_contigs(pemap_ctx* h, int n) {
+  if (n < 1) return fail(h, PEMAP_ERR_ARG, "no contigs");
+  if (n >= 2 && n <= 7)
+    return fail(h, PEMAP_ERR_UNSUPPORTED,
+                "2..7 contigs: the reference's find_chrom (pemapper.c:2168-2186) starts its bisection at index 7 and "
+                "reads past contig_starts; its result is undefined there (SURVEY.md section 7-C). Use 1 or >= 8 contigs.");
+  return PEMAP_OK;
+}
+
+template <int G, int WD, bool TRACE>
+void launch_sw(pemap_ctx* h, const pm::SwArgs& a) {
+  pm::k_sw_fp64<G, WD, TRACE><<<h->sw_blocks, 128, 0, h->stream>>>(a);
+}
+
+template <bool TRACE>
+void dispatch_sw(pemap_ctx* h, const pm::SwArgs& a, int max_len) {
+  if (max_len <= 112) launch_sw<16, 7, TRACE>(h, a);
+  else if (max_len <= 160) launch_sw<16, 10, TRACE>(h, a);
+  else if (max_len <= 256) launch_sw<32, 8, TRACE>(h, a);
+  else launch_sw<32, 10, TRACE>(h, a);
+  h->stats.launches++;
+}
+
+// map one chunk whose reads are already in d_r1/d_r2 (device); results go to d_m1/d_m2/d_type (device)
+int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char* d_r2, const int* d_l2, int stride,
+              int max_len, uint32_t* d_m1, uint32_t* d_m2, int* d_type) {
+  const bool paired = h->params.pair_flag && d_r2;
+  CK(cudaMemsetAsync(h->d_cursors, 0, 16, h->stream));
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  pm::SeedArgs sa;
+  sa.pos_index = h->d_pos_index;
+  sa.mers = h->d_mers;
+  sa.cstart = h->d_cstart;
+  sa.reads[0] = d_r1;
+  sa.reads[1] = d_r2;
+  sa.len[0] = d_l1;
+  sa.len[1] = d_l2;
+  sa.stride = stride;
+  sa.n_reads = n;
+  sa.paired = paired ? 1 : 0;
+  sa.scratch = h->d_seed_scratch;
+  sa.tasks = h->d_tasks;
+  sa.task_cursor = h->d_cursors;
+  sa.task_cap = h->task_cap;
+  sa.cand_base = h->d_cand_base;
+  sa.cand_n = h->d_cand_n;
+  sa.counters = h->d_counters;
+  sa.p = h->dp;
+  sa.p.pair_flag = paired ? 1 : 0;
+  const int work = paired ? 2 * n : n;
+  const int seed_grid = std::min(h->seed_blocks, (work + kSeedWarps - 1) / kSeedWarps);
+  pm::k_seed_chain<kSeedWarps><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
+  h->stats.launches++;
+  CK(cudaEventRecord(h->ev[1], h->stream));
+
+  pm::SwArgs wa;
+  wa.tasks = h->d_tasks;
+  wa.results = h->d_results;
+  wa.winners = h->d_winners;
+  wa.n_items = h->d_cursors;
+  wa.reads[0] = d_r1;
+  wa.reads[1] = d_r2;
+  wa.len[0] = d_l1;
+  wa.len[1] = d_l2;
+  wa.stride = stride;
+  wa.genome = h->d_genome;
+  wa.border = h->d_border;
+  wa.counts = h->d_counts;
+  wa.dirs = h->d_dirs;
+  wa.pend = h->d_pend;
+  wa.ins_buf = h->d_ins;
+  wa.ins_cursor = h->d_ins_cursor;
+  wa.ins_cap = h->ins_cap;
+  wa.counters = h->d_counters;
+  wa.p = sa.p;
+  dispatch_sw<false>(h, wa, max_len);
+  CK(cudaEventRecord(h->ev[2], h->stream));
+
+  pm::SelectArgs se;
+  se.tasks = h->d_tasks;
+  se.results = h->d_results;
+  se.cand_base = h->d_cand_base;
+  se.cand_n = h->d_cand_n;
+  se.len[0] = d_l1;
+  se.len[1] = d_l2;
+  se.n_reads = n;
+  se.m1 = d_m1;
+  se.m2 = d_m2;
+  se.mapping_type = d_type;
+  const bool keep_det = (h->keep & PEMAP_KEEP_DETAIL) != 0;
+  se.det_best = keep_det ? h->d_det_best : nullptr;
+  se.det_orient = keep_det ? h->d_det_orient : nullptr;
+  se.det_score = keep_det ? h->d_det_score : nullptr;
+  se.winners = h->d_winners;
+  se.winner_cursor = h->d_cursors + 1;
+  se.p = sa.p;
+  pm::k_select<<<(n + 127) / 128, 128, 0, h->stream>>>(se);
+  h->stats.launches++;
+  CK(cudaEventRecord(h->ev[3], h->stream));
+
+  wa.n_items = h->d_cursors + 1;
+  dispatch_sw<true>(h, wa, max_len);
+  CK(cudaEventRecord(h->ev[4], h->stream));
+  CK(cudaGetLastError());
+  return PEMAP_OK;
+}
+
+int account_chunk(pemap_ctx* h, int n, bool paired) {
+  float ms;
+  CK(cudaEventSynchronize(h->ev[4]));
+  CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+  h->stats.ms_seed += ms;
+  CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]));
+  h->stats.ms_sw += ms;
+  CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+  h->stats.ms_select += ms;
+  CK(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]));
+  h->stats.ms_traceback += ms;
+  CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4]));
+  h->stats.ms_total += ms;
+  h->stats.reads += (uint64_t)n * (paired ? 2 : 1);
+  return PEMAP_OK;
+}
+
+int retain_chunk(pemap_ctx* h, int n, int first, bool paired) {
+  if (h->keep & PEMAP_KEEP_DETAIL) {
+    std::vector<int32_t> best(2 * (size_t)n), orient(2 * (size_t)n);
+    std::vector<double> score(2 * (size_t)n);
+    std::vector<uint32_t> cn(2 * (size_t)n);
+    CK(cudaMemcpyAsync(best.data(), h->d_det_best, best.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(orient.data(), h->d_det_orient, orient.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(score.data(), h->d_det_score, score.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(cn.data(), h->d_cand_n, cn.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; i++) {
+      pemap_detail& d = h->detail[(size_t)first + i];
+      d.hits1 = (int32_t)cn[2 * i];
+      d.hits2 = paired ? (int32_t)cn[2 * i + 1] : 0;
+      d.best1 = best[2 * i];
+      d.best2 = best[2 * i + 1];
+      d.orient1 = orient[2 * i];
+      d.orient2 = orient[2 * i + 1];
+      d.score1 = score[2 * i];
+      d.score2 = score[2 * i + 1];
+    }
+  }
+  if (h->keep & PEMAP_KEEP_CANDIDATES) {
+    uint32_t cur[2];
+    CK(cudaMemcpyAsync(cur, h->d_cursors, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<pm::Task> tasks(cur[0]);
+    std::vector<uint32_t> cb(2 * (size_t)n), cn(2 * (size_t)n);
+    if (cur[0]) CK(cudaMemcpy(tasks.data(), h->d_tasks, tasks.size() * sizeof(pm::Task), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cb.data(), h->d_cand_base, cb.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cn.data(), h->d_cand_n, cn.size() * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++)
+      for (int m = 0; m < (paired ? 2 : 1); m++) {
+        const size_t rm = 2 * ((size_t)first + i) + m;
+        h->cand_base_h[rm] = (uint32_t)h->cand_spot_h.size();
+        h->cand_n_h[rm] = cn[2 * i + m];
+        for (uint32_t q = 0; q < cn[2 * i + m]; q++) {
+          const pm::Task& t = tasks[cb[2 * i + m] + q];
+          h->cand_spot_h.push_back(t.spot);
+          h->cand_orient_h.push_back((int8_t)(t.rm >> 31));
+        }
+      }
+  }
+  return PEMAP_OK;
+}
+
+int fetch_counters(pemap_ctx* h) {
+  pm::SeedCounters c;
+  CK(cudaMemcpy(&c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+  h->stats.lookups = c.lookups;
+  h->stats.mer_positions = c.mer_positions;
+  h->stats.candidates = c.candidates;
+  h->stats.sw_cells = c.sw_cells;
+  h->stats.tb_cells = c.tb_cells;
+  h->stats.replayed = c.replayed;
+  return PEMAP_OK;
+}
+
+void begin_batch(pemap_ctx* h, int n) {
+  if (h->keep & PEMAP_KEEP_DETAIL) h->detail.assign((size_t)n, pemap_detail{});
+  if (h->keep & PEMAP_KEEP_CANDIDATES) {
+    h->cand_base_h.assign(2 * (size_t)n, 0);
+    h->cand_n_h.assign(2 * (size_t)n, 0);
+    h->cand_spot_h.clear();
+    h->cand_orient_h.clear();
+  }
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// rows: reads as (n x stride) matrices on the host, or, when ptrs != nullptr, as arrays of pointers
+int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, const int* len1, const char* rows2,
+             const char* const* ptr2, const int* len2, int stride, uint32_t* m1, uint32_t* m2, int* mapping_type) {
+  if (!h) return PEMAP_ERR_ARG;
+  if (n < 0 || (!rows1 && !ptr1) || !len1 || !m1 || !m2 || !mapping_type) return fail(h, PEMAP_ERR_ARG, "NULL argument");
+  const bool paired = h->params.pair_flag != 0;
+  if (paired && ((!rows2 && !ptr2) || !len2)) return fail(h, PEMAP_ERR_ARG, "pair_flag set but read2/len2 is NULL");
+  CK(cudaSetDevice(h->device));
+  begin_batch(h, n);
+  const bool direct = rows1 && is_pinned(rows1) && is_pinned(len1) && (!paired || (is_pinned(rows2) && is_pinned(len2))) &&
+                      is_pinned(m1) && is_pinned(m2) && is_pinned(mapping_type);
+  for (int first = 0; first < n; first += h->chunk) {
+    const int cn = std::min(h->chunk, n - first);
+    int max_len = 0;
+    for (int m = 0; m < (paired ? 2 : 1); m++) {
+      const int* len = (m ? len2 : len1) + first;
+      for (int i = 0; i < cn; i++) {
+        if (len[i] < 0 || len[i] > PM_DP_MAX - 22)
+          return fail(h, PEMAP_ERR_ARG, "read longer than 298 bases (reference DP buffers are 300x300)");
+        max_len = std::max(max_len, len[i]);
+      }
+    }
+    int dstride = stride;
+    const char* src_rows[2] = {rows1 ? rows1 + (size_t)first * stride : nullptr, rows2 ? rows2 + (size_t)first * stride : nullptr};
+    if (!direct || ptr1) {  // stage through the library's pinned buffers, packed at a 16-byte multiple
+      dstride = (max_len + 15) & ~15;
+      if (dstride < 16) dstride = 16;
+      for (int m = 0; m < (paired ? 2 : 1); m++) {
+        const int* len = (m ? len2 : len1) + first;
+        char* dst = h->h_reads[m];
+        if (m ? ptr2 != nullptr : ptr1 != nullptr) {
+          const char* const* pp = (m ? ptr2 : ptr1) + first;
+          for (int i = 0; i < cn; i++) memcpy(dst + (size_t)i * dstride, pp[i], (size_t)len[i]);
+        } else {
+          const char* rows = src_rows[m];
+          for (int i = 0; i < cn; i++) memcpy(dst + (size_t)i * dstride, rows + (size_t)i * stride, (size_t)len[i]);
+        }
+        memcpy(h->h_len[m], len, (size_t)cn * sizeof(int));
+        src_rows[m] = dst;
+      }
+    }
+    if (dstride > h->stride_cap) return fail(h, PEMAP_ERR_ARG, "row stride larger than 320 bytes");
+    for (int m = 0; m < (paired ? 2 : 1); m++) {
+      const int* lsrc = (!direct || ptr1) ? h->h_len[m] : (m ? len2 : len1) + first;
+      CK(cudaMemcpyAsync(h->d_reads[m], src_rows[m], (size_t)cn * dstride, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(h->d_len[m], lsrc, (size_t)cn * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    int rc = run_chunk(h, cn, h->d_reads[0], h->d_len[0], paired ? h->d_reads[1] : nullptr, paired ? h->d_len[1] : nullptr,
+                       dstride, max_len, h->d_m1, h->d_m2, h->d_type);
+    if (rc) return rc;
+    uint32_t* o1 = direct ? m1 + first : h->h_m1;
+    uint32_t* o2 = direct ? m2 + first : h->h_m2;
+    int* ot = direct ? mapping_type + first : h->h_type;
+    CK(cudaMemcpyAsync(o1, h->d_m1, (size_t)cn * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(o2, h->d_m2, (size_t)cn * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(ot, h->d_type, (size_t)cn * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (!direct) {
+      memcpy(m1 + first, h->h_m1, (size_t)cn * 4);
+      memcpy(m2 + first, h->h_m2, (size_t)cn * 4);
+      memcpy(mapping_type + first, h->h_type, (size_t)cn * 4);
+    }
+    rc = account_chunk(h, cn, paired);
+    if (rc) return rc;
+    rc = retain_chunk(h, cn, first, paired);
+    if (rc) return rc;
+  }
+  return PEMAP_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------- C-ABI
+
+extern "C" {
+
+const char* pemap_version(void) { return PEMAP_VERSION; }
+
+void pemap_default_params(pemap_params* p) {
+  if (!p) return;
+  p->idepth = 16;
+  p->max_hits = 200;
+  p->too_many_spots = 100;
+  p->min_align = 0.9;
+  p->match_bonus = 1.0;
+  p->is_bisulfite = 0;
+  p->pair_flag = 0;
+  p->min_dist = 0;
+  p->max_dist = 500;
+  p->misalign_slop = 10;
+}
+
+const char* pemap_last_error(pemap_t* h) { return h ? h->err.c_str() : "NULL handle"; }
+
+static pemap_ctx* g_failed = nullptr;  // keeps the message of a failed init readable through the returned handle
+
+int pemap_init(pemap_t** out, const pemap_index* ix, const pemap_params* p, int device) {
+  if (!out) return PEMAP_ERR_ARG;
+  pemap_ctx* h = new pemap_ctx();
+  *out = h;
+  int rc = check_params(h, p);
+  if (rc) return rc;
+  if (!ix || !ix->pos_index || !ix->mers || !ix->genome || !ix->contig_starts)
+    return fail(h, PEMAP_ERR_ARG, "index has NULL members");
+  rc = check_contigs(h, ix->no_contigs);
+  if (rc) return rc;
+  h->params = *p;
+  rc = open_device(h, device);
+  if (rc) return rc;
+  h->n_contigs = ix->no_contigs;
+  h->genome_size = ix->genome_size;
+  h->n_mers = ix->n_mers;
+  const size_t idx_words = ((size_t)1 << 32) + 1;
+  CK(cudaMalloc(&h->d_pos_index, idx_words * 4));
+  CK(cudaMemcpy(h->d_pos_index, ix->pos_index, idx_words * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->d_mers, (size_t)(h->n_mers + 4) * 4));
+  CK(cudaMemcpy(h->d_mers, ix->mers, (size_t)h->n_mers * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->d_genome, h->genome_size + 64));
+  CK(cudaMemset(h->d_genome, 'N', h->genome_size + 64));
+  CK(cudaMemcpy(h->d_genome, ix->genome, h->genome_size, cudaMemcpyHostToDevice));
+  rc = upload_cstart(h, ix->contig_starts, ix->no_contigs);
+  if (rc) return rc;
+  return finish_init(h);
+}
+
+int pemap_init_from_genome(pemap_t** out, const char* genome, const int64_t* contig_len, int n_contigs,
+                           const pemap_params* p, int device) {
+  if (!out) return PEMAP_ERR_ARG;
+  pemap_ctx* h = new pemap_ctx();
+  *out = h;
+  int rc = check_params(h, p);
+  if (rc) return rc;
+  if (!genome || !contig_len) return fail(h, PEMAP_ERR_ARG, "NULL genome");
+  rc = check_contigs(h, n_contigs);
+  if (rc) return rc;
+  h->params = *p;
+  rc = open_device(h, device);
+  if (rc) return rc;
+  h->n_contigs = n_contigs;
+  std::vector<uint64_t> real_start((size_t)n_contigs + 1, 0);
+  std::vector<uint32_t> cs((size_t)n_contigs + 1, 0);
+  for (int i = 0; i < n_contigs; i++) {
+    if (contig_len[i] < 16) return fail(h, PEMAP_ERR_ARG, "contig shorter than 16 bases");
+    real_start[i + 1] = real_start[i] + (uint64_t)contig_len[i];
+    cs[i + 1] = cs[i] + (uint32_t)(contig_len[i] - 15);  // .sdx stores len-15 (index_genome_whole.c:213-216, 316)
+  }
+  h->genome_size = real_start[n_contigs];
+  if (h->genome_size >= 0xFFFFFFFFull) return fail(h, PEMAP_ERR_UNSUPPORTED, "genome does not fit 32-bit coordinates");
+  const uint64_t gs = h->genome_size;
+  CK(cudaMalloc(&h->d_genome, gs + 64));
+  CK(cudaMemset(h->d_genome, 'N', gs + 64));
+  CK(cudaMemcpy(h->d_genome, genome, gs, cudaMemcpyHostToDevice));
+  rc = upload_cstart(h, cs.data(), n_contigs);
+  if (rc) return rc;
+
+  // ---- k-mers of every start position, compaction of the valid ones, stable sort by k-mer
+  uint64_t* d_real = nullptr;
+  uint32_t *d_key = nullptr, *d_val = nullptr, *d_key2 = nullptr, *d_val2 = nullptr;
+  unsigned char* d_flag = nullptr;
+  unsigned long long* d_nsel = nullptr;
+  CK(cudaMalloc(&d_real, real_start.size() * 8));
+  CK(cudaMemcpy(d_real, real_start.data(), real_start.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&d_key, gs * 4));
+  CK(cudaMalloc(&d_val, gs * 4));
+  CK(cudaMalloc(&d_key2, gs * 4));
+  CK(cudaMalloc(&d_val2, gs * 4));
+  CK(cudaMalloc(&d_flag, gs));
+  CK(cudaMalloc(&d_nsel, 8));
+  pm::k_index_kmers<<<(unsigned)((gs + 255) / 256), 256, 0, h->stream>>>(h->d_genome, gs, d_real, n_contigs,
+                                                                         p->is_bisulfite, d_key, d_val, d_flag);
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0, need = 0;
+  // chunked select/sort calls keep every CUB problem size below 2^31 items
+  if (gs >= 0x7FFFFFFFull) return fail(h, PEMAP_ERR_UNSUPPORTED, "device index build is limited to genomes < 2^31 bases; use pemap_init");
+  const int n_items = (int)gs;
+  cub::DeviceSelect::Flagged(nullptr, need, d_key, d_flag, d_key2, d_nsel, n_items, h->stream);
+  tmp_bytes = need;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, d_key2, d_key, d_val2, d_val, n_items, 0, 32, h->stream);
+  tmp_bytes = std::max(tmp_bytes, need);
+  CK(cudaMalloc(&tmp, tmp_bytes));
+  need = tmp_bytes;
+  CK(cub::DeviceSelect::Flagged(tmp, need, d_key, d_flag, d_key2, d_nsel, n_items, h->stream));
+  need = tmp_bytes;
+  CK(cub::DeviceSelect::Flagged(tmp, need, d_val, d_flag, d_val2, d_nsel, n_items, h->stream));
+  unsigned long long nsel = 0;
+  CK(cudaMemcpyAsync(&nsel, d_nsel, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_mers = nsel;
+  need = tmp_bytes;
+  CK(cub::DeviceRadixSort::SortPairs(tmp, need, d_key2, d_key, d_val2, d_val, (int)nsel, 0, 32, h->stream));
+  // d_key = sorted k-mers, d_val = positions grouped by k-mer (= .mdx)
+  const size_t idx_words = ((size_t)1 << 32) + 1;
+  CK(cudaMalloc(&h->d_pos_index, idx_words * 4));
+  const uint64_t step = 1ull << 30;
+  for (uint64_t first = 0; first < idx_words; first += step) {
+    const uint64_t cnt = std::min<uint64_t>(step, idx_words - first);
+    pm::k_index_prefix<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(d_key, nsel, h->d_pos_index, first, cnt);
+  }
+  CK(cudaMalloc(&h->d_mers, (size_t)(nsel + 4) * 4));
+  CK(cudaMemcpyAsync(h->d_mers, d_val, (size_t)nsel * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  cudaFree(tmp);
+  cudaFree(d_real);
+  cudaFree(d_key);
+  cudaFree(d_val);
+  cudaFree(d_key2);
+  cudaFree(d_val2);
+  cudaFree(d_flag);
+  cudaFree(d_nsel);
+  return finish_init(h);
+}
+
+int pemap_set_params(pemap_t* h, const pemap_params* p) {
+  if (!h) return PEMAP_ERR_ARG;
+  int rc = check_params(h, p);
+  if (rc) return rc;
+  if (p->is_bisulfite != h->params.is_bisulfite)
+    return fail(h, PEMAP_ERR_UNSUPPORTED, "is_bisulfite is baked into the index and cannot change");
+  const bool new_scores = p->match_bonus != h->params.match_bonus;
+  h->params = *p;
+  fill_dev_params(h);
+  if (new_scores) return upload_border(h);
+  return PEMAP_OK;
+}
+
+int pemap_keep(pemap_t* h, int flags) {
+  if (!h) return PEMAP_ERR_ARG;
+  h->keep = flags;
+  return PEMAP_OK;
+}
+
+int pemap_map_batch(pemap_t* h, int n, const char* const* read1, const int* len1, const char* const* read2,
+                    const int* len2, uint32_t* m1, uint32_t* m2, int* mapping_type) {
+  return map_host(h, n, nullptr, read1, len1, nullptr, read2, len2, 0, m1, m2, mapping_type);
+}
+
+int pemap_map_batch_rows(pemap_t* h, int n, const char* reads1, const int* len1, const char* reads2, const int* len2,
+                         int stride, uint32_t* m1, uint32_t* m2, int* mapping_type) {
+  return map_host(h, n, reads1, nullptr, len1, reads2, nullptr, len2, stride, m1, m2, mapping_type);
+}
+
+int pemap_map_batch_device(pemap_t* h, int n, const char* d_reads1, const int* d_len1, const char* d_reads2,
+                           const int* d_len2, int stride, int max_len, uint32_t* d_m1, uint32_t* d_m2,
+                           int* d_mapping_type) {
+  if (!h) return PEMAP_ERR_ARG;
+  if (n < 0 || !d_reads1 || !d_len1 || !d_m1 || !d_m2 || !d_mapping_type) return fail(h, PEMAP_ERR_ARG, "NULL argument");
+  if (max_len < 16 || max_len > PM_DP_MAX - 22) return fail(h, PEMAP_ERR_ARG, "max_len out of range");
+  const bool paired = h->params.pair_flag != 0;
+  if (paired && (!d_reads2 || !d_len2)) return fail(h, PEMAP_ERR_ARG, "pair_flag set but read2/len2 is NULL");
+  CK(cudaSetDevice(h->device));
+  begin_batch(h, n);
+  for (int first = 0; first < n; first += h->chunk) {
+    const int cn = std::min(h->chunk, n - first);
+    int rc = run_chunk(h, cn, d_reads1 + (size_t)first * stride, d_len1 + first,
+                       paired ? d_reads2 + (size_t)first * stride : nullptr, paired ? d_len2 + first : nullptr, stride,
+                       max_len, d_m1 + first, d_m2 + first, d_mapping_type + first);
+    if (rc) return rc;
+    rc = account_chunk(h, cn, paired);
+    if (rc) return rc;
+    rc = retain_chunk(h, cn, first, paired);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return PEMAP_OK;
+}
+
+int pemap_get_detail(pemap_t* h, pemap_detail* out, int n) {
+  if (!h || !out) return PEMAP_ERR_ARG;
+  if (!(h->keep & PEMAP_KEEP_DETAIL)) return fail(h, PEMAP_ERR_ARG, "PEMAP_KEEP_DETAIL not enabled");
+  if ((size_t)n > h->detail.size()) return fail(h, PEMAP_ERR_ARG, "n exceeds the last batch");
+  memcpy(out, h->detail.data(), (size_t)n * sizeof(pemap_detail));
+  return PEMAP_OK;
+}
+
+int pemap_get_candidates(pemap_t* h, int i, int mate, uint32_t* spots, int8_t* orients, int cap) {
+  if (!h || !spots || !orients) return PEMAP_ERR_ARG;
+  if (!(h->keep & PEMAP_KEEP_CANDIDATES)) return fail(h, PEMAP_ERR_ARG, "PEMAP_KEEP_CANDIDATES not enabled");
+  const size_t rm = 2 * (size_t)i + (size_t)mate;
+  if (i < 0 || rm >= h->cand_n_h.size()) return fail(h, PEMAP_ERR_ARG, "read index out of range");
+  const int n = (int)h->cand_n_h[rm];
+  for (int q = 0; q < n && q < cap; q++) {
+    spots[q] = h->cand_spot_h[h->cand_base_h[rm] + q];
+    orients[q] = h->cand_orient_h[h->cand_base_h[rm] + q];
+  }
+  return n;
+}
+
+int pemap_finish(pemap_t* h, const pemap_record** records, uint64_t* n_records, const pemap_insertion** ins,
+                 uint64_t* n_ins) {
+  if (!h || !records || !n_records) return PEMAP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  const uint64_t gs = h->genome_size;
+  const uint64_t tile = (uint64_t)PM_COMPACT_BLOCK * PM_COMPACT_ITEMS;
+  const unsigned n_tiles = (unsigned)((gs + tile - 1) / tile);
+  unsigned long long *d_cnt = nullptr, *d_off = nullptr;
+  CK(cudaMalloc(&d_cnt, ((size_t)n_tiles + 1) * 8));
+  CK(cudaMalloc(&d_off, ((size_t)n_tiles + 1) * 8));
+  CK(cudaMemsetAsync(d_cnt, 0, ((size_t)n_tiles + 1) * 8, h->stream));
+  pm::k_compact_count<<<n_tiles, PM_COMPACT_BLOCK, 0, h->stream>>>(h->d_counts, gs, d_cnt);
+  void* tmp = nullptr;
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, d_cnt, d_off, (int)n_tiles + 1, h->stream);
+  CK(cudaMalloc(&tmp, need));
+  CK(cub::DeviceScan::ExclusiveSum(tmp, need, d_cnt, d_off, (int)n_tiles + 1, h->stream));
+  unsigned long long total = 0;
+  CK(cudaMemcpyAsync(&total, d_off + n_tiles, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  pm::PileRecord* d_rec = nullptr;
+  CK(cudaMalloc(&d_rec, (size_t)(total + 1) * sizeof(pm::PileRecord)));
+  pm::k_compact_write<<<n_tiles, PM_COMPACT_BLOCK, 0, h->stream>>>(h->d_counts, gs, d_off, d_rec);
+  h->stats.launches += 2;
+  h->records.resize(total);
+  static_assert(sizeof(pm::PileRecord) == sizeof(pemap_record) && sizeof(pemap_record) == 16, "record layout");
+  if (total)
+    CK(cudaMemcpyAsync(h->records.data(), d_rec, (size_t)total * sizeof(pemap_record), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  cudaFree(tmp);
+  cudaFree(d_cnt);
+  cudaFree(d_off);
+  cudaFree(d_rec);
+  *records = h->records.data();
+  *n_records = total;
+
+  // insertion strings: {u32 pos, u32 len, chars padded to 4} records appended by the traceback kernel
+  unsigned long long used = 0;
+  CK(cudaMemcpy(&used, h->d_ins_cursor, 8, cudaMemcpyDeviceToHost));
+  if (used > h->ins_cap) return fail(h, PEMAP_ERR_NOMEM, "insertion buffer overflow (raise PEMAP_INS_MB)");
+  std::vector<unsigned char> raw(used);
+  if (used) CK(cudaMemcpy(raw.data(), h->d_ins, used, cudaMemcpyDeviceToHost));
+  h->ins.clear();
+  h->ins_pool.clear();
+  std::vector<size_t> offs;
+  for (size_t o = 0; o + 8 <= used;) {
+    uint32_t pos, len;
+    memcpy(&pos, raw.data() + o, 4);
+    memcpy(&len, raw.data() + o + 4, 4);
+    pemap_insertion r;
+    r.pos = pos;
+    r.len = len;
+    r.seq = nullptr;
+    offs.push_back(h->ins_pool.size());
+    h->ins_pool.insert(h->ins_pool.end(), raw.begin() + o + 8, raw.begin() + o + 8 + len);
+    h->ins_pool.push_back('\0');
+    h->ins.push_back(r);
+    o += 8 + ((len + 3) & ~3u);
+  }
+  for (size_t i = 0; i < h->ins.size(); i++) h->ins[i].seq = h->ins_pool.data() + offs[i];
+  // group by site (ascending position; order inside a site is not defined by the reference either)
+  std::stable_sort(h->ins.begin(), h->ins.end(), [](const pemap_insertion& x, const pemap_insertion& y) {
+    if (x.pos != y.pos) return x.pos < y.pos;
+    return strcmp(x.seq, y.seq) < 0;
+  });
+  if (ins) *ins = h->ins.data();
+  if (n_ins) *n_ins = h->ins.size();
+  return fetch_counters(h);
+}
+
+int pemap_reset_counts(pemap_t* h) {
+  if (!h) return PEMAP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemset(h->d_counts, 0, (size_t)h->genome_size * 6 * 4));
+  CK(cudaMemset(h->d_ins_cursor, 0, 8));
+  h->records.clear();
+  h->ins.clear();
+  h->ins_pool.clear();
+  return PEMAP_OK;
+}
+
+int pemap_counts_device(pemap_t* h, void** d_counts, uint64_t* n_words) {
+  if (!h || !d_counts || !n_words) return PEMAP_ERR_ARG;
+  *d_counts = h->d_counts;
+  *n_words = h->genome_size * 6;
+  return PEMAP_OK;
+}
+
+int pemap_get_stats(pemap_t* h, pemap_stats* out) {
+  if (!h || !out) return PEMAP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  int rc = fetch_counters(h);
+  if (rc) return rc;
+  *out = h->stats;
+  return PEMAP_OK;
+}
+
+int pemap_reset_stats(pemap_t* h) {
+  if (!h) return PEMAP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemset(h->d_counters, 0, sizeof(pm::SeedCounters)));
+  memset(&h->stats, 0, sizeof(h->stats));
+  return PEMAP_OK;
+}
+
+int pemap_index_device(pemap_t* h, const uint32_t** d_pos_index, const uint32_t** d_mers, uint64_t* n_mers) {
+  if (!h) return PEMAP_ERR_ARG;
+  if (d_pos_index) *d_pos_index = h->d_pos_index;
+  if (d_mers) *d_mers = h->d_mers;
+  if (n_mers) *n_mers = h->n_mers;
+  return PEMAP_OK;
+}
+
+int pemap_read_pos_index(pemap_t* h, uint64_t first, uint64_t n, uint32_t* out) {
+  if (!h || !out) return PEMAP_ERR_ARG;
+  if (first + n > ((uint64_t)1 << 32) + 1) return fail(h, PEMAP_ERR_ARG, "range beyond 2^32+1");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(out, h->d_pos_index + first, n * 4, cudaMemcpyDeviceToHost));
+  return PEMAP_OK;
+}
+
+int pemap_read_mers(pemap_t* h, uint64_t first, uint64_t n, uint32_t* out) {
+  if (!h || !out) return PEMAP_ERR_ARG;
+  if (first + n > h->n_mers) return fail(h, PEMAP_ERR_ARG, "range beyond n_mers");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(out, h->d_mers + first, n * 4, cudaMemcpyDeviceToHost));
+  return PEMAP_OK;
+}
+
+void pemap_destroy(pemap_t* h) {
+  if (!h) return;
+  if (h->stream) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    void* dev[] = {h->d_pos_index, h->d_mers, h->d_genome, h->d_cstart, h->d_border, h->d_counts, h->d_ins, h->d_ins_cursor,
+                   h->d_reads[0], h->d_reads[1], h->d_len[0], h->d_len[1], h->d_tasks, h->d_results, h->d_cursors,
+                   h->d_cand_base, h->d_cand_n, h->d_winners, h->d_m1, h->d_m2, h->d_type, h->d_det_best, h->d_det_orient,
+                   h->d_det_score, h->d_seed_scratch, h->d_dirs, h->d_pend, h->d_counters};
+    for (void* p : dev)
+      if (p) cudaFree(p);
+    void* host[] = {h->h_reads[0], h->h_reads[1], h->h_len[0], h->h_len[1], h->h_m1, h->h_m2, h->h_type};
+    for (void* p : host)
+      if (p) cudaFreeHost(p);
+    for (auto& ev : h->ev)
+      if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(h->stream);
+  }
+  delete h;
+  (void)g_failed;
+}
+
+}  // extern "C"
