@@ -159,6 +159,10 @@ int pemap_reset_counts(pemap_t *h);
    Insertions stay per shard: each rank's pemap_finish returns its own. */
 int pemap_counts_device(pemap_t *h, void **d_counts, uint64_t *n_words);
 
+/* The CUDA stream (cudaStream_t as void*) all of this handle's work is issued on, so that a caller can bracket
+   calls with its own events. */
+int pemap_stream(pemap_t *h, void **stream);
+
 int pemap_get_stats(pemap_t *h, pemap_stats *out);
 int pemap_reset_stats(pemap_t *h);
 

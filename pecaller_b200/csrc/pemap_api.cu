@@ -832,6 +832,12 @@ int pemap_counts_device(pemap_t* h, void** d_counts, uint64_t* n_words) {
   return PEMAP_OK;
 }
 
+int pemap_stream(pemap_t* h, void** stream) {
+  if (!h || !stream) return PEMAP_ERR_ARG;
+  *stream = (void*)h->stream;
+  return PEMAP_OK;
+}
+
 int pemap_get_stats(pemap_t* h, pemap_stats* out) {
   if (!h || !out) return PEMAP_ERR_ARG;
   CK(cudaSetDevice(h->device));

@@ -1,0 +1,434 @@
+/*
+ * pemapper_gpu.c - C host for the B200 hot path: same command line, input formats and output files as the
+ * reference pemapper (wingolab-org/pecaller src/pemapper.c main(), 178-904), with the per-batch worker
+ * (pthread_create(map_everything), 684/759) replaced by the C-ABI of include/pemap.h.
+ *
+ *   pemapper_gpu out sdx s|sa file1 is_bisulfite min_match max_threads max_reads
+ *   pemapper_gpu out sdx p|pa file1 file2 max_dist min_dist is_bisulfite min_match max_threads max_reads
+ *
+ * max_threads is accepted and ignored (one submitting thread, one GPU).  Environment:
+ *   PEMAP_DEVICE        GPU ordinal (default 0)
+ *   PEMAP_DEVICE_INDEX  1 = rebuild pos_index/mers on the GPU from .seq/.sdx instead of loading .idx/.mdx
+ *   PEMAP_BATCH         reads per pemap_map_batch_rows call (default 1,000,000; results do not depend on it)
+ * Written from scratch; what must be byte-compatible (file formats, summary text) cites the reference line.
+ */
+#include <ctype.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include "pemap.h"
+
+#define ROW 304 /* bytes per read row handed to the library */
+#define NAME_MAX_LEN 512
+#define MAX_FILES 2000
+
+static void die(const char *msg) { /* dump_error, pemapper.c:2808-2816 */
+  printf("\n%s\n", msg);
+  exit(1);
+}
+
+/* ---- line reader with my_gzgets semantics (2447-2483): '\n'-terminated lines only; a trailing
+   unterminated line is dropped; the returned pointer is valid until the next call. */
+typedef struct {
+  gzFile f;
+  char *buf;
+  size_t cap, beg, end;
+  int eof;
+} reader;
+
+static void reader_open(reader *r, const char *path) {
+  r->f = gzopen(path, "r");
+  if (!r->f) {
+    printf("\n Can not open file %s for reading\n", path);
+    exit(1);
+  }
+  gzbuffer(r->f, 1 << 25);
+  r->cap = (size_t)64 << 20;
+  r->buf = malloc(r->cap + 1);
+  r->beg = r->end = 0;
+  r->eof = 0;
+}
+
+static char *reader_line(reader *r) {
+  for (;;) {
+    char *nl = r->end > r->beg ? memchr(r->buf + r->beg, '\n', r->end - r->beg) : NULL;
+    if (nl) {
+      char *line = r->buf + r->beg;
+      *nl = '\0';
+      r->beg = (size_t)(nl - r->buf) + 1;
+      return line;
+    }
+    if (r->eof) return NULL;
+    memmove(r->buf, r->buf + r->beg, r->end - r->beg);
+    r->end -= r->beg;
+    r->beg = 0;
+    if (r->end == r->cap) die(" A fastq line is longer than 64 MB ");
+    int got = gzread(r->f, r->buf + r->end, (unsigned)(r->cap - r->end));
+    if (got <= 0) r->eof = 1; else r->end += (size_t)got;
+  }
+}
+
+static void reader_close(reader *r) {
+  gzclose(r->f);
+  free(r->buf);
+}
+
+/* skip '+', quality and look for the next '@' header, then return the sequence line (713-724) */
+static char *next_sequence(reader *r) {
+  char *s = reader_line(r);
+  s = reader_line(r);
+  s = reader_line(r);
+  int found = 0;
+  while (s && !found) {
+    if (s[0] == '@') found = 1;
+    s = reader_line(r);
+  }
+  return found ? s : NULL;
+}
+
+static int read_name_list(const char *path, char (*names)[NAME_MAX_LEN]) { /* 250-267 */
+  FILE *f = fopen(path, "r");
+  if (!f) {
+    printf("\n Can not open file %s for reading\n", path);
+    exit(1);
+  }
+  int n = 0;
+  char line[NAME_MAX_LEN];
+  while (n < MAX_FILES && fgets(line, NAME_MAX_LEN - 1, f)) {
+    char *tok = strtok(line, "\t \n");
+    if (!tok || strlen(tok) <= 2) break;
+    strcpy(names[n++], tok);
+  }
+  fclose(f);
+  return n;
+}
+
+typedef struct {
+  uint32_t *starts; /* n+1 unpadded prefix sums */
+  char (*names)[260];
+  int n, idepth;
+} sdx_t;
+
+static void load_sdx(const char *path, sdx_t *s) { /* 411-448 */
+  FILE *f = fopen(path, "r");
+  char line[1100];
+  if (!f) {
+    printf("\n Can not open file %s\n", path);
+    exit(1);
+  }
+  fgets(line, 256, f);
+  s->n = atoi(line);
+  s->starts = calloc((size_t)s->n + 2, 4);
+  s->names = calloc((size_t)s->n + 1, 260);
+  for (int i = 0; i < s->n; i++) {
+    fgets(line, 1024, f);
+    char *tok = strtok(line, "\t \n");
+    s->starts[i + 1] = s->starts[i] + (uint32_t)atoi(tok);
+    tok = strtok(NULL, "\t \n");
+    strncpy(s->names[i], tok ? tok : "", 259);
+  }
+  fgets(line, 1024, f);
+  s->idepth = atoi(line);
+  fclose(f);
+}
+
+static int find_contig(const uint32_t *pos, int n, uint32_t v) { /* find_chrom 2168-2186 */
+  int first = 0, last = n - 1, probe = 7;
+  for (;;) {
+    if (first == last) return first;
+    if (pos[probe] <= v && pos[probe + 1] >= v) return probe;
+    if (pos[probe] > v) last = probe - 1; else first = probe + 1;
+    probe = (last + first) / 2;
+  }
+}
+
+static void gz_read_all(gzFile f, void *dst, size_t n) {
+  size_t done = 0;
+  while (done < n) {
+    unsigned want = (unsigned)((n - done) > (1u << 30) ? (1u << 30) : (n - done));
+    int got = gzread(f, (char *)dst + done, want);
+    if (got <= 0) break;
+    done += (size_t)got;
+  }
+  if (done != n) die(" Short read on a compressed index file ");
+}
+
+int main(int argc, char **argv) {
+  if (argc < 4) die("Usage: pemapper_gpu out_file sdx_file [s,sa,p,pa] ... (same arguments as pemapper)");
+  const char mode = (char)toupper(argv[3][0]), arr = (char)toupper(argv[3][1]);
+  int paired, max_dist = 0, min_dist = 0, bisulfite;
+  double min_align;
+  long max_reads;
+  const char *in1, *in2 = NULL;
+  if (mode == 'S') { /* 233-280 */
+    if (argc != 9) die("Usage: pemapper_gpu out_file sdx_file [s,sa] file1 is_bisulfite[y,n] min_match_percentage max_threads max_reads");
+    paired = 0;
+    in1 = argv[4];
+    bisulfite = strchr(argv[5], 'Y') || strchr(argv[5], 'y');
+    min_align = atof(argv[6]);
+    max_reads = atoi(argv[8]);
+  } else if (mode == 'P') { /* 281-358 */
+    if (argc != 12)
+      die("Usage: pemapper_gpu out_file sdx_file [p,pa] file1 file2 max_dist min_dist is_bisulfite[y,n] min_match_percentage max_threads max_reads");
+    paired = 1;
+    in1 = argv[4];
+    in2 = argv[5];
+    max_dist = atoi(argv[6]);
+    min_dist = atoi(argv[7]);
+    bisulfite = strchr(argv[8], 'Y') || strchr(argv[8], 'y');
+    min_align = atof(argv[9]);
+    max_reads = atol(argv[11]);
+  } else {
+    die("Usage: pemapper_gpu out_file sdx_file paired_or_single_or_array[p,s,pa,ps] ...");
+    return 1;
+  }
+  static char files1[MAX_FILES][NAME_MAX_LEN], files2[MAX_FILES][NAME_MAX_LEN];
+  int n_files = 1;
+  if (arr == 'A') {
+    n_files = read_name_list(in1, files1);
+    if (paired && read_name_list(in2, files2) != n_files) die(" Mismatch in number of files in the two arrays ");
+  } else {
+    strcpy(files1[0], in1);
+    if (paired) strcpy(files2[0], in2);
+  }
+
+  char path[4300], base[1024], sdxbase[1024];
+  strcpy(base, argv[1]);
+  snprintf(path, sizeof path, "%s.pileup.gz", base);
+  gzFile pile = gzopen(path, "wb");
+  if (!pile) die(" Can not open the pileup file for writing ");
+  gzbuffer(pile, 33554432);
+  snprintf(path, sizeof path, "%s.indel.txt.gz", base);
+  gzFile indel = gzopen(path, "w");
+  if (!indel) die(" Can not open the indel file for writing ");
+  gzbuffer(indel, 33554432);
+  snprintf(path, sizeof path, "%s.summary.txt", base);
+  FILE *summary = fopen(path, "w");
+  if (!summary) die(" Can not open the summary file for writing ");
+
+  sdx_t sdx;
+  load_sdx(argv[2], &sdx);
+  strcpy(sdxbase, argv[2]);
+  if (strstr(sdxbase, ".sdx")) *strrchr(sdxbase, '.') = '\0'; /* 400-408 */
+  const uint64_t genome_size = (uint64_t)sdx.starts[sdx.n] + 15ull * (uint64_t)sdx.n; /* 453 */
+  printf("\n Genome size is %llu \n\n", (unsigned long long)genome_size);
+  char *genome = malloc(genome_size + 1);
+  snprintf(path, sizeof path, "%s.seq", sdxbase);
+  gzFile gf = gzopen(path, "r");
+  if (!gf) die(" Can not open the .seq file ");
+  gzbuffer(gf, 33554432);
+  gz_read_all(gf, genome, genome_size);
+  gzclose(gf);
+
+  pemap_params prm;
+  pemap_default_params(&prm);
+  prm.idepth = sdx.idepth;
+  prm.min_align = min_align;
+  prm.is_bisulfite = bisulfite;
+  prm.pair_flag = paired;
+  prm.min_dist = min_dist;
+  prm.max_dist = max_dist;
+  const int device = getenv("PEMAP_DEVICE") ? atoi(getenv("PEMAP_DEVICE")) : 0;
+  pemap_t *h = NULL;
+  int rc;
+  if (getenv("PEMAP_DEVICE_INDEX") && atoi(getenv("PEMAP_DEVICE_INDEX"))) {
+    int64_t *lens = malloc(sizeof(int64_t) * (size_t)sdx.n);
+    for (int i = 0; i < sdx.n; i++) lens[i] = (int64_t)(sdx.starts[i + 1] - sdx.starts[i]) + 15;
+    rc = pemap_init_from_genome(&h, genome, lens, sdx.n, &prm, device);
+    free(lens);
+  } else { /* init_index_buffer 2129-2155 */
+    const size_t words = ((size_t)1 << 32) + 1;
+    uint32_t *pos_index = malloc(words * 4);
+    if (!pos_index) die(" Can not allocate space for the position index ");
+    snprintf(path, sizeof path, "%s.idx", sdxbase);
+    gf = gzopen(path, "r");
+    if (!gf) die(" Could Not Open the .idx file ");
+    gzbuffer(gf, 33554432);
+    printf("\n About to read kmers index \n\n");
+    gz_read_all(gf, pos_index, words * 4);
+    gzclose(gf);
+    const uint64_t n_mers = pos_index[words - 1];
+    uint32_t *mers = malloc((n_mers + 1) * 4);
+    snprintf(path, sizeof path, "%s.mdx", sdxbase);
+    FILE *mf = fopen(path, "rb");
+    if (!mf || fread(mers, 4, n_mers, mf) != n_mers) die(" Could not read the .mdx file ");
+    fclose(mf);
+    pemap_index ix = {pos_index, mers, n_mers, genome, genome_size, sdx.starts, sdx.n};
+    rc = pemap_init(&h, &ix, &prm, device);
+    free(pos_index);
+    free(mers);
+  }
+  if (rc) {
+    printf("\n pemap_init failed: %s \n", pemap_last_error(h));
+    exit(1);
+  }
+
+  const long batch_cap = getenv("PEMAP_BATCH") ? atol(getenv("PEMAP_BATCH")) : 1000000;
+  char *rows1 = malloc((size_t)batch_cap * ROW), *rows2 = paired ? malloc((size_t)batch_cap * ROW) : NULL;
+  int *len1 = malloc(sizeof(int) * (size_t)batch_cap), *len2 = malloc(sizeof(int) * (size_t)batch_cap);
+  uint32_t *bm1 = malloc(4 * (size_t)batch_cap), *bm2 = malloc(4 * (size_t)batch_cap);
+  int *btype = malloc(sizeof(int) * (size_t)batch_cap);
+  uint32_t *maps1 = calloc((size_t)max_reads + 1, 4), *maps2 = calloc((size_t)max_reads + 1, 4);
+  if (!maps1 || !maps2) die(" Could not allocate space for mapping position of reads ");
+  long mate_counts[9] = {0}, total_reads = 0, total_bases = 0, total_dist = 0, no_dists = 0, tot_pairs = 0;
+
+  printf("\n About to start mapping everything \n\n");
+  for (int fi = 0; fi < n_files; fi++) {
+    reader r1, r2;
+    reader_open(&r1, files1[fi]);
+    if (paired) reader_open(&r2, files2[fi]);
+    char *s1 = reader_line(&r1), *s2 = NULL;
+    s1 = reader_line(&r1);
+    if (paired) {
+      s2 = reader_line(&r2);
+      s2 = reader_line(&r2);
+    }
+    long current = 0, filled = 0, batch_first = 0;
+    int go = s1 != NULL;
+    while (go || filled) {
+      const int have = go && s1 && (int)strlen(s1) > 12 && (!paired || s2); /* 663 */
+      if (have) {
+        const int l1 = (int)strlen(s1), l2 = paired ? (int)strlen(s2) : 0;
+        if (l1 > PEMAP_MAX_READ + 20 || l2 > PEMAP_MAX_READ + 20) die(" Read longer than the reference's DP buffers allow ");
+        memcpy(rows1 + (size_t)filled * ROW, s1, (size_t)l1);
+        len1[filled] = l1;
+        if (paired) {
+          memcpy(rows2 + (size_t)filled * ROW, s2, (size_t)l2);
+          len2[filled] = l2;
+        }
+        filled++;
+        current++;
+        if (current >= max_reads) go = 0;
+        else {
+          s1 = next_sequence(&r1);
+          if (!s1) go = 0;
+          if (paired && go) {
+            s2 = next_sequence(&r2);
+            if (!s2) go = 0;
+          }
+        }
+      } else
+        go = 0;
+      if (filled == batch_cap || (!go && filled)) {
+        rc = pemap_map_batch_rows(h, (int)filled, rows1, len1, rows2, paired ? len2 : NULL, ROW, bm1, bm2, btype);
+        if (rc) {
+          printf("\n pemap_map_batch failed: %s \n", pemap_last_error(h));
+          exit(1);
+        }
+        for (long j = 0; j < filled; j++) { /* batch epilogue, 1238-1265 */
+          mate_counts[btype[j]]++;
+          maps1[batch_first + j] = bm1[j];
+          if (bm1[j]) {
+            total_reads++;
+            total_bases += len1[j];
+            if (bm2[j]) {
+              total_reads++;
+              total_bases += len2[j];
+              long test = (long)(uint32_t)(bm1[j] - bm2[j]); /* labs() of an unsigned difference (1250) */
+              maps2[batch_first + j] = bm2[j];
+              if (test < (long)max_dist * 4) {
+                total_dist += test;
+                no_dists++;
+              }
+            }
+          } else if (bm2[j]) {
+            total_reads++;
+            total_bases += len2[j];
+            maps2[batch_first + j] = bm2[j];
+          }
+        }
+        batch_first += filled;
+        filled = 0;
+        printf("\n We have read %ld reads and %ld have come back from successful mapping\n\n", current, total_reads);
+      }
+    }
+    printf("\n Made it out alive, and have started cleanup \n\n");
+    snprintf(path, sizeof path, "%s.mfile", files1[fi]); /* 775-781 */
+    FILE *mf = fopen(path, "wb");
+    if (!mf) die(" Can not open the .mfile for writing ");
+    fwrite(maps1, 4, (size_t)current, mf);
+    fclose(mf);
+    if (paired) {
+      snprintf(path, sizeof path, "%s.mfile", files2[fi]);
+      mf = fopen(path, "wb");
+      if (!mf) die(" Can not open the .mfile for writing ");
+      fwrite(maps2, 4, (size_t)current, mf);
+      fclose(mf);
+      reader_close(&r2);
+    }
+    reader_close(&r1);
+    tot_pairs += current;
+  }
+
+  const char *pn[9] = {"Unique Mate-Paired", "Unique Mate-Paired with slip", "Unique Single End", "Unique Mis-size",
+                       "Non-Unique Mate-Paired", "Non-Unique Mis-size", "Fragment Mismatch", "Non-unique with no map",
+                       "Neither Map"}; /* 567-590 */
+  const char *sn[9] = {NULL, NULL, "Unique Mapping", NULL, NULL, NULL, NULL, "Non-Unique Mapping, discarded",
+                       "No mapping reaches threshold"};
+  const char **names = paired ? pn : sn;
+  const char *bars = "\n================================================================";
+  if (total_bases <= 0) { /* 790-808 */
+    fprintf(summary, "%s\n================= Summary ======================================%s%s", bars, bars, bars);
+    fprintf(summary, "\n\nTotal Number of Mapping reads of Any Kind\t0\tWith average Length\t0\tAverage Depth\t0\tAverage Insert Size\t0");
+    fprintf(summary, "\n\nMapping Type\tCount\tFraction");
+    fprintf(summary, "\nAll\t%ld\t1", tot_pairs);
+    for (int i = 0; i < 9; i++)
+      if (names[i]) fprintf(summary, "\n%s\t%ld\t%g", names[i], mate_counts[i], (double)mate_counts[i] / (double)tot_pairs);
+    fprintf(summary, "\n");
+    fclose(summary);
+    return 1;
+  }
+
+  const pemap_record *rec;
+  const pemap_insertion *ins;
+  uint64_t n_rec, n_ins;
+  rc = pemap_finish(h, &rec, &n_rec, &ins, &n_ins);
+  if (rc) {
+    printf("\n pemap_finish failed: %s \n", pemap_last_error(h));
+    exit(1);
+  }
+  gzprintf(indel, "Fragment\tPositions\tReference Base\tTotal Coverage\tReference Reads\tNo Deletions\tNo Insertions\tInsertion Sequence"); /* 819-820 */
+  uint32_t *padded = calloc((size_t)sdx.n + 16, 4);
+  for (int i = 0; i <= sdx.n; i++) padded[i] = sdx.starts[i] + 15u * (uint32_t)i; /* 821-822 */
+  uint64_t q = 0;
+  for (uint64_t k = 0; k < n_rec; k++) { /* 828-864 */
+    gzwrite(pile, &rec[k].pos, 4);
+    gzwrite(pile, rec[k].c, 12);
+    if (rec[k].c[5] > 0) {
+      const uint32_t pos = rec[k].pos;
+      const char ref = genome[pos];
+      const int tot = rec[k].c[0] + rec[k].c[1] + rec[k].c[2] + rec[k].c[3] + rec[k].c[4] + rec[k].c[5];
+      const int ref_reads = ref == 'A' ? rec[k].c[0] : ref == 'C' ? rec[k].c[1] : ref == 'G' ? rec[k].c[2] : rec[k].c[3];
+      const int which = find_contig(padded, sdx.n, pos);
+      gzprintf(indel, "\n%s\t%d\t%c\t%d\t%d\t%d\t%d", sdx.names[which], (int)(1 + pos - padded[which]), ref, tot, ref_reads,
+               rec[k].c[4], rec[k].c[5]);
+      while (q < n_ins && ins[q].pos < pos) q++;
+      for (; q < n_ins && ins[q].pos == pos; q++) gzprintf(indel, "\t%s", ins[q].seq);
+    }
+  }
+  gzclose(pile);
+  gzclose(indel);
+
+  double avg_len = (double)total_bases, avg_dist = (double)total_dist; /* 811-817, 868 */
+  if (total_reads > 0) avg_len /= (double)total_reads;
+  if (no_dists > 0) avg_dist /= (double)no_dists;
+  const double avg_depth = (double)total_bases / (double)genome_size;
+  FILE *outs[2] = {stdout, summary};
+  for (int o = 0; o < 2; o++) { /* 870-898 */
+    FILE *f = outs[o];
+    fprintf(f, "%s\n================= Summary ======================================%s%s", bars, bars, bars);
+    fprintf(f, "\n\nTotal Number of Mapping reads of Any Kind\t%ld\tWith average Length\t%g\tAverage Depth\t%g\tAverage Insert Size\t%g",
+            total_reads, avg_len, avg_depth, avg_dist);
+    fprintf(f, "\n\nMapping Type\tCount\tFraction");
+    fprintf(f, "\nAll\t%ld\t1", tot_pairs);
+    for (int i = 0; i < 9; i++)
+      if (names[i]) fprintf(f, "\n%s\t%ld\t%g", names[i], mate_counts[i], (double)mate_counts[i] / (double)tot_pairs);
+    fprintf(f, "\n");
+  }
+  fclose(summary);
+  pemap_destroy(h);
+  return 0;
+}

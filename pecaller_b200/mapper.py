@@ -54,7 +54,7 @@ class Stats(C.Structure):
 EXPORTS = ["pemap_version", "pemap_default_params", "pemap_init", "pemap_init_from_genome", "pemap_set_params",
            "pemap_map_batch", "pemap_map_batch_rows", "pemap_map_batch_device", "pemap_keep", "pemap_get_detail",
            "pemap_get_candidates", "pemap_finish", "pemap_reset_counts", "pemap_counts_device", "pemap_get_stats",
-           "pemap_reset_stats", "pemap_index_device", "pemap_read_pos_index", "pemap_read_mers", "pemap_last_error",
+           "pemap_reset_stats", "pemap_stream", "pemap_index_device", "pemap_read_pos_index", "pemap_read_mers", "pemap_last_error",
            "pemap_destroy"]
 
 _lib = None
@@ -91,6 +91,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.pemap_counts_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.pemap_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.pemap_reset_stats.argtypes = [vp]
+    L.pemap_stream.argtypes = [vp, C.POINTER(vp)]
     L.pemap_index_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.pemap_read_pos_index.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
     L.pemap_read_mers.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
@@ -268,6 +269,11 @@ class PEMapper:
         s = Stats()
         self._ck(self._L.pemap_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def stream_ptr(self) -> int:
+        p = C.c_void_p()
+        self._ck(self._L.pemap_stream(self._h, C.byref(p)))
+        return p.value or 0
 
     def reset_stats(self):
         self._ck(self._L.pemap_reset_stats(self._h))

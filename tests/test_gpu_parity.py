@@ -1,0 +1,160 @@
+"""GPU: the CUDA path, called through the C-ABI, against the oracle on the same seeded inputs (every stage:
+index, candidate lists, strand, score bits, m1/m2, mapping type, pileup records, insertion strings) and against
+the committed outputs of the reference binaries (tests/golden)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import golden_io as gio
+import oracle_lib as ol
+import pecaller_b200 as pb
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(mapper, oracle, run, n=None, threads=16):
+    r1 = run.reads1[:n]
+    r2 = run.reads2[:n] if run.paired else None
+    kw = dict(min_align=run.min_align, pair_flag=int(run.paired), min_dist=run.min_dist, max_dist=run.max_dist)
+    oracle.reset()
+    oracle.set_params(**kw)
+    mapper.reset_counts()
+    mapper.set_params(**kw)
+    mapper.keep(pb.KEEP_DETAIL | pb.KEEP_CANDIDATES)
+    o = oracle.map_batch(r1, r2, nthreads=threads, detail=True)
+    g = mapper.map_batch(r1, r2)
+    return r1, r2, o, g
+
+
+def _assert_parity(name, mapper, oracle, run, n=None, cand_step=37):
+    r1, r2, (om1, om2, oty, odet), (gm1, gm2, gty) = _run_both(mapper, oracle, run, n)
+    tag = "%s/%s" % (name, run.name)
+    assert np.array_equal(om1, gm1), tag + ": m1"
+    assert np.array_equal(om2, gm2), tag + ": m2"
+    assert np.array_equal(oty, gty), tag + ": mapping_type"
+    gdet = mapper.detail(r1.shape[0])
+    for f in ("hits1", "hits2", "best1", "best2", "orient1", "orient2"):
+        assert np.array_equal(odet[f], gdet[f]), tag + ": " + f
+    for f in ("score1", "score2"):  # bit pattern of the reference's double
+        assert np.array_equal(odet[f].view(np.uint64), gdet[f].view(np.uint64)), tag + ": " + f
+    for i in range(0, r1.shape[0], cand_step):
+        os_, oo = oracle.initial_map(r1[i].tobytes())
+        gs, go = mapper.candidates(i, 0)
+        assert np.array_equal(os_, gs) and np.array_equal(oo, go), tag + ": candidates of read %d" % i
+    orec = oracle.records()
+    grec, gins = mapper.finish()
+    assert orec.tobytes() == grec.tobytes(), tag + ": pileup records"
+    assert oracle.insertions() == sorted(gins), tag + ": insertion strings"
+    return gm1, gm2, gty, grec
+
+
+@pytest.fixture(scope="module")
+def ctx_cache():
+    cache = {}
+    yield cache
+    for m, o in cache.values():
+        m.close()
+        o.close()
+
+
+def _ctx(cache, fx):
+    if fx.name not in cache:
+        cache[fx.name] = (pb.PEMapper.from_genome(fx.genome), ol.Oracle(fx.genome))
+    return cache[fx.name]
+
+
+@pytest.mark.parametrize("name", ["tiny", "edge9", "cfg1", "pe150", "repeat"])
+def test_cuda_matches_oracle_and_reference(name, get_fixture, ctx_cache, oracle_built):
+    fx = get_fixture(name)
+    mapper, oracle = _ctx(ctx_cache, fx)
+    # index_genome_whole parity of the device index builder
+    assert np.array_equal(mapper.read_mers(), oracle.mers())
+    rng = np.random.default_rng(1)
+    for w in rng.integers(0, 1 << 32, size=200, dtype=np.uint64):
+        assert int(mapper.read_pos_index(int(w), 1)[0]) == oracle.pos_index(int(w))
+    assert int(mapper.read_pos_index(1 << 32, 1)[0]) == oracle.mers().shape[0]
+    for run in fx.runs:
+        gm1, gm2, gty, grec = _assert_parity(name, mapper, oracle, run)
+        if gio.have(name, run.name):  # the reference binary's own files
+            assert np.array_equal(gio.mfile(name, run.name, 1), gm1)
+            if run.paired:
+                assert np.array_equal(gio.mfile(name, run.name, 2), gm2)
+            pmeta = gio.pileup_meta(name, run.name)
+            assert hashlib.sha256(grec.tobytes()).hexdigest() == pmeta["sha256"]
+            counts, _ = gio.summary(name, run.name)
+            names = gio.PAIR_NAMES if run.paired else gio.SINGLE_NAMES
+            got = np.bincount(gty, minlength=9)
+            for code, nm in names.items():
+                assert counts[nm] == got[code]
+
+
+def test_pointer_entry_and_chunking(get_fixture, ctx_cache, oracle_built, monkeypatch):
+    """pemap_map_batch (char** form of PTHREAD_DATA_NODE) == pemap_map_batch_rows; results independent of batching."""
+    fx = get_fixture("tiny")
+    mapper, oracle = _ctx(ctx_cache, fx)
+    run = fx.runs[1]
+    kw = dict(min_align=run.min_align, pair_flag=1, min_dist=run.min_dist, max_dist=run.max_dist)
+    mapper.set_params(**kw)
+    mapper.reset_counts()
+    a = mapper.map_batch(run.reads1, run.reads2)
+    rec_a, ins_a = mapper.finish()
+    mapper.reset_counts()
+    l1 = [r.tobytes() for r in run.reads1]
+    l2 = [r.tobytes() for r in run.reads2]
+    parts = [mapper.map_pointers(l1[s:s + 333], l2[s:s + 333]) for s in range(0, len(l1), 333)]
+    b = [np.concatenate([p[k] for p in parts]) for k in range(3)]
+    rec_b, ins_b = mapper.finish()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert rec_a.tobytes() == rec_b.tobytes()
+    assert sorted(ins_a) == sorted(ins_b)
+
+
+def test_edge_inputs(get_fixture, ctx_cache, oracle_built):
+    """Empty batch, all-N reads, poly-T reads (k-mer 0xFFFFFFFF quirk), mixed lengths, lower-case, counter reset."""
+    fx = get_fixture("tiny")
+    mapper, oracle = _ctx(ctx_cache, fx)
+    mapper.set_params(min_align=0.9, pair_flag=0)
+    oracle.set_params(min_align=0.9, pair_flag=0)
+    m1, m2, ty = mapper.map_batch(np.zeros((0, 100), dtype=np.uint8))
+    assert m1.shape == (0,)
+    g = fx.genome[0]
+    rows = []
+    rows.append(np.full(100, ord("N"), np.uint8))
+    rows.append(np.full(100, ord("T"), np.uint8))
+    rows.append(np.full(100, ord("A"), np.uint8))
+    r = g[1000:1100].copy(); r[::9] = ord("N"); rows.append(r)            # 12 N >= 1+len/10 -> filtered
+    r = g[2000:2100].copy(); r[5] = ord("N"); r[50] = ord("n"); rows.append(r)
+    r = g[3000:3100].copy(); r[10:14] = np.frombuffer(b"acgt", np.uint8); rows.append(r)   # lower case
+    r = g[4000:4100].copy(); r[30] = ord("R"); r[31] = ord("Y"); rows.append(r)           # IUPAC codes
+    reads = np.stack(rows)
+    oracle.reset(); mapper.reset_counts()
+    o = oracle.map_batch(reads)
+    gq = mapper.map_batch(reads)
+    for x, y in zip(o, gq):
+        assert np.array_equal(x, y)
+    assert oracle.records().tobytes() == mapper.finish()[0].tobytes()
+    # ragged lengths in one batch through the rows entry
+    lens = np.array([100, 64, 17, 16, 150, 33, 250, 99], dtype=np.int32)
+    buf = np.zeros((8, 256), dtype=np.uint8)
+    for i, L in enumerate(lens):
+        buf[i, :L] = g[5000 + 300 * i: 5000 + 300 * i + L]
+    oracle.reset(); mapper.reset_counts()
+    om = np.zeros((3, 8), dtype=np.int64)
+    for i, L in enumerate(lens):
+        a, b, c = oracle.map_batch(buf[i:i + 1, :L])
+        om[:, i] = a[0], b[0], c[0]
+    gm1, gm2, gty = mapper.map_rows(buf, lens)
+    assert np.array_equal(om[0], gm1) and np.array_equal(om[2], gty)
+    assert oracle.records().tobytes() == mapper.finish()[0].tobytes()
+    mapper.reset_counts()
+    assert mapper.finish()[0].shape[0] == 0
+
+
+def test_contig_count_quirk_is_refused():
+    """2..7 contigs: find_chrom reads out of bounds in the reference; we refuse instead of guessing."""
+    from pecaller_b200 import synth
+    g = synth.random_genome(3, [5000, 5000, 5000])
+    with pytest.raises(pb.PemapError):
+        pb.PEMapper.from_genome(g)
