@@ -18,6 +18,7 @@
 #include "seed_chain.cuh"
 #include "select_finish.cuh"
 #include "sw_wavefront.cuh"
+#include "sw_int16.cuh"
 
 #define PEMAP_VERSION "pemap-b200 0.1 (sm_100a)"
 
@@ -63,7 +64,11 @@ struct pemap_ctx {
   pm::Task* d_tasks = nullptr;
   pm::TaskResult* d_results = nullptr;
   uint32_t task_cap = 0;
-  uint32_t* d_cursors = nullptr;  // [0] task cursor, [1] winner cursor
+  uint32_t* d_cursors = nullptr;  // [0] tasks, [1] winners, [2] replay reads, [3] replay tasks, [4]/[5] min/max len
+  pm::ITaskResult* d_ires = nullptr;
+  uint32_t* d_replay_reads = nullptr;
+  pm::Winner* d_replay_tasks = nullptr;
+  int exact = 0;  // 1: fp64 kernels for everything (PEMAP_EXACT=1, PEMAP_KEEP_DETAIL, match_bonus != 1)
   uint32_t* d_cand_base = nullptr;
   uint32_t* d_cand_n = nullptr;
   pm::Winner* d_winners = nullptr;
@@ -105,6 +110,26 @@ struct pemap_ctx {
 };
 
 namespace {
+
+__global__ void k_len_range(const int* l1, const int* l2, int n, unsigned* out) {
+  unsigned lo = 0xFFFFFFFFu, hi = 0u;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    unsigned a = (unsigned)l1[i];
+    lo = min(lo, a);
+    hi = max(hi, a);
+    if (l2) {
+      unsigned b = (unsigned)l2[i];
+      lo = min(lo, b);
+      hi = max(hi, b);
+    }
+  }
+  lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+  hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(out, lo);
+    atomicMax(out + 1, hi);
+  }
+}
 
 int fail(pemap_ctx* h, int code, const std::string& msg) {
   if (h) h->err = msg;
@@ -180,6 +205,9 @@ int open_device(pemap_ctx* h, int device) {
   if (prop.major < 10) return fail(h, PEMAP_ERR_CUDA, "device is not sm_100 (this library has only sm_100a code)");
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  // random 8-byte gathers into the 16 GiB table: ask for sector-sized (32 B) DRAM fetches instead of the default
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+  cudaGetLastError();
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
   return PEMAP_OK;
@@ -203,7 +231,11 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   h->task_cap = (uint32_t)std::min<size_t>(2 * n * PM_MAX_HITS, 0x7FFFFFFFull);
   CK(cudaMalloc(&h->d_tasks, (size_t)h->task_cap * sizeof(pm::Task)));
   CK(cudaMalloc(&h->d_results, (size_t)h->task_cap * sizeof(pm::TaskResult)));
-  CK(cudaMalloc(&h->d_cursors, 16));
+  CK(cudaMalloc(&h->d_cursors, 32));
+  CK(cudaMalloc(&h->d_ires, (size_t)h->task_cap * sizeof(pm::ITaskResult)));
+  CK(cudaMalloc(&h->d_replay_reads, n * 4));
+  CK(cudaMalloc(&h->d_replay_tasks, (size_t)h->task_cap * sizeof(pm::Winner)));
+  if (const char* s = getenv("PEMAP_EXACT")) h->exact = atoi(s) != 0;
   CK(cudaMalloc(&h->d_cand_base, 2 * n * 4));
   CK(cudaMalloc(&h->d_cand_n, 2 * n * 4));
   CK(cudaMemset(h->d_cand_n, 0, 2 * n * 4));
@@ -275,10 +307,35 @@ void dispatch_sw(pemap_ctx* h, const pm::SwArgs& a, int max_len) {
   h->stats.launches++;
 }
 
+template <int G, int WD, int CMM>
+struct CmmDispatch {
+  static void go(pemap_ctx* h, const pm::SwIntArgs& a, int cmm) {
+    if (cmm == CMM) pm::k_sw_i16<G, WD, CMM><<<h->sw_blocks, 128, 0, h->stream>>>(a);
+    else CmmDispatch<G, WD, CMM - 1>::go(h, a, cmm);
+  }
+};
+template <int G, int WD>
+struct CmmDispatch<G, WD, -1> {
+  static void go(pemap_ctx* h, const pm::SwIntArgs& a, int) { pm::k_sw_i16<G, WD, -1><<<h->sw_blocks, 128, 0, h->stream>>>(a); }
+};
+
+// uniform_len > 0: every read of the chunk has that length (lets the kernel fix the last read column at compile time)
+void dispatch_sw_int(pemap_ctx* h, pm::SwIntArgs& a, int max_len, int uniform_len) {
+  int wd = max_len <= 112 ? 7 : max_len <= 160 ? 10 : max_len <= 256 ? 8 : 10;
+  int cmm = uniform_len > 0 ? (uniform_len - 1) % wd : -1;
+  a.lane_mm = uniform_len > 0 ? (uniform_len - 1) / wd : -1;
+  if (max_len <= 112) CmmDispatch<16, 7, 6>::go(h, a, cmm);
+  else if (max_len <= 160) CmmDispatch<16, 10, 9>::go(h, a, cmm);
+  else if (max_len <= 256) CmmDispatch<32, 8, 7>::go(h, a, cmm);
+  else CmmDispatch<32, 10, 9>::go(h, a, cmm);
+  h->stats.launches++;
+}
+
 // map one chunk whose reads are already in d_r1/d_r2 (device); results go to d_m1/d_m2/d_type (device)
 int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char* d_r2, const int* d_l2, int stride,
-              int max_len, uint32_t* d_m1, uint32_t* d_m2, int* d_type) {
+              int max_len, int uniform_len, uint32_t* d_m1, uint32_t* d_m2, int* d_type) {
   const bool paired = h->params.pair_flag && d_r2;
+  const bool exact = h->exact || (h->keep & PEMAP_KEEP_DETAIL) || h->params.match_bonus != 1.0;
   CK(cudaMemsetAsync(h->d_cursors, 0, 16, h->stream));
   CK(cudaEventRecord(h->ev[0], h->stream));
   pm::SeedArgs sa;
@@ -311,6 +368,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   wa.tasks = h->d_tasks;
   wa.results = h->d_results;
   wa.winners = h->d_winners;
+  wa.list_mode = 0;
   wa.n_items = h->d_cursors;
   wa.reads[0] = d_r1;
   wa.reads[1] = d_r2;
@@ -327,8 +385,6 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   wa.ins_cap = h->ins_cap;
   wa.counters = h->d_counters;
   wa.p = sa.p;
-  dispatch_sw<false>(h, wa, max_len);
-  CK(cudaEventRecord(h->ev[2], h->stream));
 
   pm::SelectArgs se;
   se.tasks = h->d_tasks;
@@ -338,6 +394,8 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   se.len[0] = d_l1;
   se.len[1] = d_l2;
   se.n_reads = n;
+  se.read_list = nullptr;
+  se.n_list = nullptr;
   se.m1 = d_m1;
   se.m2 = d_m2;
   se.mapping_type = d_type;
@@ -348,8 +406,60 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   se.winners = h->d_winners;
   se.winner_cursor = h->d_cursors + 1;
   se.p = sa.p;
-  pm::k_select<<<(n + 127) / 128, 128, 0, h->stream>>>(se);
-  h->stats.launches++;
+
+  if (exact) {  // the reference's arithmetic for every candidate
+    dispatch_sw<false>(h, wa, max_len);
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    pm::k_select<<<(n + 127) / 128, 128, 0, h->stream>>>(se);
+    h->stats.launches++;
+  } else {
+    // integer DPX scoring of every candidate, integer selection, then fp64 replay of the reads with rational ties
+    pm::SwIntArgs ia;
+    ia.tasks = h->d_tasks;
+    ia.results = h->d_ires;
+    ia.n_items = h->d_cursors;
+    ia.reads[0] = d_r1;
+    ia.reads[1] = d_r2;
+    ia.len[0] = d_l1;
+    ia.len[1] = d_l2;
+    ia.stride = stride;
+    ia.genome = h->d_genome;
+    ia.lane_mm = -1;
+    ia.p = sa.p;
+    dispatch_sw_int(h, ia, max_len, uniform_len);
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    pm::SelectIntArgs si;
+    si.tasks = h->d_tasks;
+    si.ires = h->d_ires;
+    si.results64 = h->d_results;
+    si.cand_base = h->d_cand_base;
+    si.cand_n = h->d_cand_n;
+    si.len[0] = d_l1;
+    si.len[1] = d_l2;
+    si.n_reads = n;
+    si.m1 = d_m1;
+    si.m2 = d_m2;
+    si.mapping_type = d_type;
+    si.winners = h->d_winners;
+    si.winner_cursor = h->d_cursors + 1;
+    si.replay_reads = h->d_replay_reads;
+    si.replay_read_cursor = h->d_cursors + 2;
+    si.replay_tasks = h->d_replay_tasks;
+    si.replay_task_cursor = h->d_cursors + 3;
+    si.counters = h->d_counters;
+    si.p = sa.p;
+    pm::k_select_int<<<(n + 127) / 128, 128, 0, h->stream>>>(si);
+    // exact replay: fp64 scores of every candidate of the flagged reads, then the fp64 selection rules on them
+    pm::SwArgs ra = wa;
+    ra.winners = h->d_replay_tasks;
+    ra.list_mode = 1;
+    ra.n_items = h->d_cursors + 3;
+    dispatch_sw<false>(h, ra, max_len);
+    se.read_list = h->d_replay_reads;
+    se.n_list = h->d_cursors + 2;
+    pm::k_select<<<(n + 127) / 128, 128, 0, h->stream>>>(se);
+    h->stats.launches += 2;
+  }
   CK(cudaEventRecord(h->ev[3], h->stream));
 
   wa.n_items = h->d_cursors + 1;
@@ -466,13 +576,14 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
                       is_pinned(m1) && is_pinned(m2) && is_pinned(mapping_type);
   for (int first = 0; first < n; first += h->chunk) {
     const int cn = std::min(h->chunk, n - first);
-    int max_len = 0;
+    int max_len = 0, min_len = 1 << 30;
     for (int m = 0; m < (paired ? 2 : 1); m++) {
       const int* len = (m ? len2 : len1) + first;
       for (int i = 0; i < cn; i++) {
         if (len[i] < 0 || len[i] > PM_DP_MAX - 22)
           return fail(h, PEMAP_ERR_ARG, "read longer than 298 bases (reference DP buffers are 300x300)");
         max_len = std::max(max_len, len[i]);
+        min_len = std::min(min_len, len[i]);
       }
     }
     int dstride = stride;
@@ -501,7 +612,7 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
       CK(cudaMemcpyAsync(h->d_len[m], lsrc, (size_t)cn * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     }
     int rc = run_chunk(h, cn, h->d_reads[0], h->d_len[0], paired ? h->d_reads[1] : nullptr, paired ? h->d_len[1] : nullptr,
-                       dstride, max_len, h->d_m1, h->d_m2, h->d_type);
+                       dstride, max_len, min_len == max_len ? max_len : 0, h->d_m1, h->d_m2, h->d_type);
     if (rc) return rc;
     uint32_t* o1 = direct ? m1 + first : h->h_m1;
     uint32_t* o2 = direct ? m2 + first : h->h_m2;
@@ -705,11 +816,25 @@ int pemap_map_batch_device(pemap_t* h, int n, const char* d_reads1, const int* d
   if (paired && (!d_reads2 || !d_len2)) return fail(h, PEMAP_ERR_ARG, "pair_flag set but read2/len2 is NULL");
   CK(cudaSetDevice(h->device));
   begin_batch(h, n);
+  // one reduction over the lengths: uniform-length batches take the specialised integer kernel
+  int uniform_len = 0;
+  {
+    unsigned mm[2] = {0xFFFFFFFFu, 0u};
+    CK(cudaMemcpyAsync(h->d_cursors + 4, mm, 8, cudaMemcpyHostToDevice, h->stream));
+    if (n > 0) {
+      k_len_range<<<h->sm_count * 4, 256, 0, h->stream>>>(d_len1, paired ? d_len2 : nullptr, n, h->d_cursors + 4);
+      h->stats.launches++;
+    }
+    CK(cudaMemcpyAsync(mm, h->d_cursors + 4, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n > 0 && mm[0] == mm[1]) uniform_len = (int)mm[0];
+    if (n > 0 && (int)mm[1] > max_len) return fail(h, PEMAP_ERR_ARG, "a read is longer than max_len");
+  }
   for (int first = 0; first < n; first += h->chunk) {
     const int cn = std::min(h->chunk, n - first);
     int rc = run_chunk(h, cn, d_reads1 + (size_t)first * stride, d_len1 + first,
                        paired ? d_reads2 + (size_t)first * stride : nullptr, paired ? d_len2 + first : nullptr, stride,
-                       max_len, d_m1 + first, d_m2 + first, d_mapping_type + first);
+                       max_len, uniform_len, d_m1 + first, d_m2 + first, d_mapping_type + first);
     if (rc) return rc;
     rc = account_chunk(h, cn, paired);
     if (rc) return rc;
@@ -887,7 +1012,8 @@ void pemap_destroy(pemap_t* h) {
     void* dev[] = {h->d_pos_index, h->d_mers, h->d_genome, h->d_cstart, h->d_border, h->d_counts, h->d_ins, h->d_ins_cursor,
                    h->d_reads[0], h->d_reads[1], h->d_len[0], h->d_len[1], h->d_tasks, h->d_results, h->d_cursors,
                    h->d_cand_base, h->d_cand_n, h->d_winners, h->d_m1, h->d_m2, h->d_type, h->d_det_best, h->d_det_orient,
-                   h->d_det_score, h->d_seed_scratch, h->d_dirs, h->d_pend, h->d_counters};
+                   h->d_det_score, h->d_seed_scratch, h->d_dirs, h->d_pend, h->d_counters, h->d_ires, h->d_replay_reads,
+                   h->d_replay_tasks};
     for (void* p : dev)
       if (p) cudaFree(p);
     void* host[] = {h->h_reads[0], h->h_reads[1], h->h_len[0], h->h_len[1], h->h_m1, h->h_m2, h->h_type};

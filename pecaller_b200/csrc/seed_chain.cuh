@@ -173,8 +173,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_seed_chain(SeedArgs a) {
             int ss = q / PM_KV, v = q - ss * PM_KV;
             uint32_t code = kmer_variant(sm.kcode[ss], v);
             ssv[u] = ss;
-            lo[u] = __ldg(a.pos_index + code);
-            hi[u] = __ldg(a.pos_index + (uint32_t)(code + 1u));  // which+1 wraps in 32 bits (2163)
+            // L1-bypassing loads: a miss then costs one 32-byte sector instead of a 128-byte line fill
+            if ((code & 1u) == 0u) {
+              const uint2 v = __ldcg(reinterpret_cast<const uint2*>(a.pos_index + code));
+              lo[u] = v.x;
+              hi[u] = v.y;
+            } else {
+              lo[u] = __ldcg(a.pos_index + code);
+              hi[u] = __ldcg(a.pos_index + (uint32_t)(code + 1u));  // which+1 wraps in 32 bits (2163)
+            }
           }
         }
 #pragma unroll
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_seed_chain(SeedArgs a) {
               uint32_t off = atomicAdd(&sm.segcnt[ssv[u]], cnt);
               uint32_t* dst = lists + (size_t)ssv[u] * PM_SEG_CAP + off;
               const uint32_t* src = a.mers + lo[u];
-              for (uint32_t t = 0; t < cnt; t++) dst[t] = __ldg(src + t);
+              for (uint32_t t = 0; t < cnt; t++) dst[t] = __ldcg(src + t);
               st_pos += cnt;
             }
           }

@@ -17,6 +17,8 @@ struct SelectArgs {
   const uint32_t* cand_n;
   const int* len[2];
   int n_reads;
+  const uint32_t* read_list;   // optional: only these reads (replay of integer ties); count in *n_list
+  const uint32_t* n_list;
   uint32_t* m1;
   uint32_t* m2;
   int* mapping_type;
@@ -114,8 +116,12 @@ __device__ __forceinline__ int pair_rule(const Task* ta, const TaskResult* ra, i
 }
 
 __global__ void __launch_bounds__(128) k_select(SelectArgs a) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= a.n_reads) return;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = idx;
+  if (a.read_list) {
+    if ((uint32_t)idx >= *a.n_list) return;
+    r = (int)a.read_list[idx];
+  } else if (idx >= a.n_reads) return;
   const int n1 = (int)a.cand_n[2 * r], n2 = a.p.pair_flag ? (int)a.cand_n[2 * r + 1] : 0;
   const uint32_t b1 = a.cand_base[2 * r], b2 = a.p.pair_flag ? a.cand_base[2 * r + 1] : 0;
   const int l1 = a.len[0][r], l3 = a.p.pair_flag ? a.len[1][r] : 0;

@@ -1,0 +1,434 @@
+// sw_int16.cuh - integer Smith-Waterman scoring with packed s16x2 DPX instructions (sm_100a) and the integer
+// version of the selection rules, with tie flags that send a read to the exact fp64 path.
+//
+// All of the reference's scores are multiples of 1/36 (match +1, mismatch -1/3, gap open 2, gap extend 1/36;
+// pemapper.c:2011, 2039-2040), so the DP is rationally exact in integer units of 1/36: +36, -12, -72, -1.
+// Two alignment tasks are packed per 32-bit lane (low / high 16 bits) and advance with VIADDMNMX.S16x2,
+// VIMNMX3.S16x2 and VIMNMX.U16x2; values are stored biased by +1024 so that every half stays positive and the
+// constant subtractions can be plain 32-bit adds without borrows between halves.
+//
+// The reference compares IEEE doubles with strict '>' (1101, 1147, 1455, 1463, 1724-1741, 1805-1811), and
+// rationally equal scores need not be equal doubles.  Every comparison whose outcome
+// could depend on that is detected here (equal integers) and the read is replayed by the fp64 kernels; all
+// other comparisons have operands at least 1/36 apart and resolve identically in double.
+#pragma once
+#include "pemap_common.cuh"
+#include "select_finish.cuh"
+#include "sw_wavefront.cuh"
+
+#define PM_IBIAS 1024
+
+namespace pm {
+
+struct ITaskResult {
+  int32_t score36;  // score in units of 1/36
+  uint16_t maxi;    // start[1]
+  uint8_t maxk;     // start[0]
+  uint8_t flags;    // 1: the last-column argmax has a rational tie; 2: a base outside ACGTN (codes not valid)
+};
+
+struct SwIntArgs {
+  const Task* tasks;
+  ITaskResult* results;
+  const uint32_t* n_items;
+  const char* reads[2];
+  const int* len[2];
+  int stride;
+  const char* genome;
+  int lane_mm;  // CMM >= 0 only: lane that owns the last read column
+  DevParams p;
+};
+
+// 4-bit one-hot codes: two bases match iff their codes share a bit (N = all bits).  0 = not representable.
+__device__ __forceinline__ uint32_t ref_code(char ch, int bis) {
+  switch (ch) {
+    case 'A': return 1u;
+    case 'C': return bis ? 10u : 2u;  // bisulfite: reference C also matches read T (2026-2033)
+    case 'G': return 4u;
+    case 'T': return 8u;
+    case 'N': case 'n': return 15u;
+    default: return 0u;
+  }
+}
+__device__ __forceinline__ uint32_t read_code(char ch) {
+  switch (ch) {
+    case 'A': return 1u;
+    case 'C': return 2u;
+    case 'G': return 4u;
+    case 'T': return 8u;
+    case 'N': case 'n': return 15u;
+    default: return 0u;
+  }
+}
+
+__device__ __forceinline__ void track_best(int v0, int v1, int v2, int i, int& best, int& bk, int& bi, int& tie) {
+  // scan of the last column, states 0,1,2 in order with strict '>' (1724-1741); equal values are remembered
+  if (v0 > best) { best = v0; bk = 0; bi = i; tie = 0; } else if (v0 == best) tie = 1;
+  if (v1 > best) { best = v1; bk = 1; bi = i; tie = 0; } else if (v1 == best) tie = 1;
+  if (v2 > best) { best = v2; bk = 2; bi = i; tie = 0; } else if (v2 == best) tie = 1;
+}
+
+// CMM >= 0: every task of the launch has (len-1) % WD == CMM and (len-1) / WD == lane_mm (uniform read length);
+// CMM < 0: per-task lengths.
+template <int G, int WD, int CMM>
+__global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
+  constexpr int GPB = 128 / G;
+  __shared__ uint32_t s_win[GPB][PM_DP_MAX];
+  __shared__ uint32_t s_last[CMM >= 0 ? GPB : 1][CMM >= 0 ? 3 * PM_DP_MAX : 1];  // last read column of every row
+  const int tid = threadIdx.x, grp = tid / G, gl = tid % G;
+  const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) / G * G));
+  const uint32_t n_items = *a.n_items, n_pairs = (n_items + 1) >> 1;
+  const uint32_t ggid = blockIdx.x * GPB + grp, n_groups = gridDim.x * GPB;
+  uint32_t* win = s_win[grp];
+  uint32_t* last = s_last[CMM >= 0 ? grp : 0];
+  constexpr uint32_t K1 = 0x00010001u, K12 = 0x000C000Cu, NEG72 = 0xFFB8FFB8u;
+  constexpr uint32_t BIASP = (PM_IBIAS << 16) | PM_IBIAS;
+
+  for (uint32_t pair = ggid; pair < n_pairs; pair += n_groups) {
+    const uint32_t idA = 2 * pair, idB = (2 * pair + 1 < n_items) ? 2 * pair + 1 : 2 * pair;
+    const Task tA = a.tasks[idA], tB = a.tasks[idB];
+    const int orA = (int)(tA.rm >> 31), orB = (int)(tB.rm >> 31);
+    const uint32_t rmA = tA.rm & 0x7FFFFFFFu, rmB = tB.rm & 0x7FFFFFFFu;
+    const int mmA = a.len[rmA & 1][rmA >> 1], mmB = a.len[rmB & 1][rmB >> 1];
+    const char* readA = a.reads[rmA & 1] + (size_t)(rmA >> 1) * a.stride;
+    const char* readB = a.reads[rmB & 1] + (size_t)(rmB >> 1) * a.stride;
+    const int nnA = tA.blen > 0 ? tA.blen : 0, nnB = tB.blen > 0 ? tB.blen : 0;
+    const int nn = nnA > nnB ? nnA : nnB;
+
+    __syncwarp(gmask);
+    bool badA = false, badB = false;
+    for (int i = gl; i < nn; i += G) {
+      uint32_t cA = 0, cB = 0;
+      if (i < nnA) { cA = ref_code(a.genome[(size_t)tA.wstart + i], a.p.is_bisulfite); badA |= (cA == 0); }
+      if (i < nnB) { cB = ref_code(a.genome[(size_t)tB.wstart + i], a.p.is_bisulfite); badB |= (cB == 0); }
+      win[i] = cA | (cB << 16);
+    }
+    uint32_t q[WD], s0u[WD], s1u[WD], mu[WD];
+    const int jbase = gl * WD;
+#pragma unroll
+    for (int c = 0; c < WD; c++) {
+      const int j0 = jbase + c;
+      uint32_t cA = 0, cB = 0;
+      if (j0 < mmA) { cA = read_code(seq_char(readA, mmA, orA, j0)); badA |= (cA == 0); }
+      if (j0 < mmB) { cB = read_code(seq_char(readB, mmB, orB, j0)); badB |= (cB == 0); }
+      q[c] = cA | (cB << 16);
+      // row 0: S*[0][j] = -(72 + j - 1) (2073-2081); mu holds max(S0,S1,S2) - 12
+      const uint32_t b = (uint32_t)(PM_IBIAS - 72 - (j0 + 1 - 1));
+      s0u[c] = b | (b << 16);
+      s1u[c] = s0u[c];
+      mu[c] = s0u[c] - K12;
+    }
+    badA = __any_sync(gmask, badA);
+    badB = __any_sync(gmask, badB);
+
+    int colA, colB;
+    bool ownA, ownB;
+    if (CMM >= 0) {
+      colA = colB = CMM;
+      ownA = ownB = (gl == a.lane_mm);
+    } else {
+      ownA = ((mmA - 1) / WD == gl);
+      ownB = ((mmB - 1) / WD == gl);
+      colA = ownA ? (mmA - 1) % WD : -1;
+      colB = ownB ? (mmB - 1) % WD : -1;
+    }
+    int bestA = PM_IBIAS - 72 - (mmA - 1), bkA = 0, biA = 0, tieA = 0;  // S[0][0][mm] (1701-1703)
+    int bestB = PM_IBIAS - 72 - (mmB - 1), bkB = 0, biB = 0, tieB = 0;
+    uint32_t out_s0 = 0, out_s2 = 0, out_m = 0;
+    __syncwarp(gmask);
+
+    const int steps = nn > 0 ? nn + G - 1 : 0;
+    for (int s = 0; s < steps; s++) {
+      uint32_t l_s0 = __shfl_up_sync(gmask, out_s0, 1, G);
+      uint32_t l_s2 = __shfl_up_sync(gmask, out_s2, 1, G);
+      uint32_t diag = __shfl_up_sync(gmask, out_m, 1, G);
+      if (gl == 0) {  // column 0: S0 = 0, S2 = -72, M(row above) - 12 = -12 (2062-2081)
+        l_s0 = BIASP;
+        l_s2 = BIASP - 0x00480048u;
+        diag = BIASP - K12;
+      }
+      const int i = s - gl + 1;
+      if (i >= 1 && i <= nn) {
+        const uint32_t rc = win[i - 1];
+#pragma unroll
+        for (int c = 0; c < WD; c++) {
+          const uint32_t s2 = __viaddmax_s16x2(l_s0, NEG72, l_s2 - K1);      // 1710 / 1720
+          const uint32_t s1 = __viaddmax_s16x2(s0u[c], NEG72, s1u[c] - K1);  // 1711 / 1721
+          const uint32_t m01 = __vminu2(q[c] & rc, K1);                      // 1 where the bases match
+          const uint32_t s0 = m01 * 48u + diag;                              // (M - 12) + 48 or + 0 (1713 / 1723)
+          diag = mu[c];
+          const uint32_t m = __vimax3_s16x2(s0, s1, s2);
+          if (CMM >= 0) {
+            if (c == CMM && ownA) {  // uniform read length: park the last column, scan it after the sweep
+              last[3 * (i - 1)] = s0;
+              last[3 * (i - 1) + 1] = s1;
+              last[3 * (i - 1) + 2] = s2;
+            }
+          } else {
+            if (c == colA && ownA && i <= nnA)
+              track_best((int)(s0 & 0xFFFFu), (int)(s1 & 0xFFFFu), (int)(s2 & 0xFFFFu), i, bestA, bkA, biA, tieA);
+            if (c == colB && ownB && i <= nnB)
+              track_best((int)(s0 >> 16), (int)(s1 >> 16), (int)(s2 >> 16), i, bestB, bkB, biB, tieB);
+          }
+          s0u[c] = s0;
+          s1u[c] = s1;
+          mu[c] = m - K12;
+          l_s0 = s0;
+          l_s2 = s2;
+        }
+        out_s0 = l_s0;
+        out_s2 = l_s2;
+        out_m = diag;
+      }
+    }
+    if (CMM >= 0) {
+      // scan of the last column (1717-1742) by the whole group.  key = value<<10 | (1023 - order) keeps the FIRST
+      // row/state of the maximum (strict '>' in scan order); the mirrored key keeps the LAST one; they differ
+      // exactly when the maximum occurs more than once.  order = 3*i + k <= 3*320+2 < 1024.
+      __syncwarp(gmask);
+      uint32_t fA = 0, lA = 0, fB = 0, lB = 0;
+      if (gl == 0) {  // S[0][0][mm]: i = 0, k = 0
+        fA = ((uint32_t)bestA << 10) | 1023u;
+        lA = ((uint32_t)bestA << 10);
+        fB = ((uint32_t)bestB << 10) | 1023u;
+        lB = ((uint32_t)bestB << 10);
+      }
+      for (int r = gl; r < nn; r += G) {
+        const uint32_t w0 = last[3 * r], w1 = last[3 * r + 1], w2 = last[3 * r + 2];
+        const uint32_t o = 3u * (uint32_t)(r + 1);
+        if (r < nnA) {
+          const uint32_t v0 = (w0 & 0xFFFFu) << 10, v1 = (w1 & 0xFFFFu) << 10, v2 = (w2 & 0xFFFFu) << 10;
+          fA = max(fA, max(v0 | (1023u - o), max(v1 | (1022u - o), v2 | (1021u - o))));
+          lA = max(lA, max(v0 | o, max(v1 | (o + 1u), v2 | (o + 2u))));
+        }
+        if (r < nnB) {
+          const uint32_t v0 = (w0 >> 16) << 10, v1 = (w1 >> 16) << 10, v2 = (w2 >> 16) << 10;
+          fB = max(fB, max(v0 | (1023u - o), max(v1 | (1022u - o), v2 | (1021u - o))));
+          lB = max(lB, max(v0 | o, max(v1 | (o + 1u), v2 | (o + 2u))));
+        }
+      }
+#pragma unroll
+      for (int off = G / 2; off > 0; off >>= 1) {
+        fA = max(fA, __shfl_xor_sync(gmask, fA, off, G));
+        lA = max(lA, __shfl_xor_sync(gmask, lA, off, G));
+        fB = max(fB, __shfl_xor_sync(gmask, fB, off, G));
+        lB = max(lB, __shfl_xor_sync(gmask, lB, off, G));
+      }
+      const uint32_t oA = 1023u - (fA & 1023u), oB = 1023u - (fB & 1023u);
+      bestA = (int)(fA >> 10); biA = (int)(oA / 3u); bkA = (int)(oA % 3u); tieA = (lA & 1023u) != oA;
+      bestB = (int)(fB >> 10); biB = (int)(oB / 3u); bkB = (int)(oB % 3u); tieB = (lB & 1023u) != oB;
+    }
+    if (ownA) {
+      ITaskResult r;
+      r.score36 = bestA - PM_IBIAS;
+      r.maxi = (uint16_t)biA;
+      r.maxk = (uint8_t)bkA;
+      r.flags = (uint8_t)((tieA ? 1 : 0) | (badA ? 2 : 0));
+      a.results[idA] = r;
+    }
+    if (ownB && idB != idA) {
+      ITaskResult r;
+      r.score36 = bestB - PM_IBIAS;
+      r.maxi = (uint16_t)biB;
+      r.maxk = (uint8_t)bkB;
+      r.flags = (uint8_t)((tieB ? 1 : 0) | (badB ? 2 : 0));
+      a.results[idB] = r;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Integer selection: same control flow as select_finish.cuh (1084-1192, 1313-1536) on exact integers.
+// `amb` is raised whenever the double-precision outcome is not implied by the integers.
+// ---------------------------------------------------------------------------------------------------
+
+struct SelectIntArgs {
+  const Task* tasks;
+  const ITaskResult* ires;
+  TaskResult* results64;      // maxi / maxk of the winners are copied here for the traceback kernel
+  const uint32_t* cand_base;
+  const uint32_t* cand_n;
+  const int* len[2];
+  int n_reads;
+  uint32_t* m1;
+  uint32_t* m2;
+  int* mapping_type;
+  Winner* winners;
+  uint32_t* winner_cursor;
+  uint32_t* replay_reads;     // reads whose outcome needs the fp64 path
+  uint32_t* replay_read_cursor;
+  Winner* replay_tasks;       // every task of those reads
+  uint32_t* replay_task_cursor;
+  SeedCounters* counters;
+  DevParams p;
+};
+
+// s >= good_score ?  returns 1 / 0, or -1 when the rational score is (numerically) on the threshold
+__device__ __forceinline__ int ge_good(int s36, double good36) {
+  const double d = (double)s36 - good36;
+  if (d > 1e-6) return 1;
+  if (d < -1e-6) return 0;
+  return -1;
+}
+
+__device__ __forceinline__ int single_rule_int(const ITaskResult* res, int n, int len, const DevParams& p, int* best,
+                                               bool* amb) {
+  const double good36 = (double)len * p.min_align * p.match_bonus * 36.0;
+  int top = -72 * len, count = 0;
+  bool tie = false;
+  *best = -1;
+  for (int q = 0; q < n; q++) {
+    const int s = res[q].score36;
+    if (res[q].flags & 2) *amb = true;
+    const int ge = ge_good(s, good36);
+    if (ge < 0) *amb = true;
+    if (s > top && ge > 0) {
+      top = s;
+      count = 1;
+      *best = q;
+      tie = false;
+    } else if (s == top && count > 0) {  // double: either '>' by an ulp (new unique top) or counted as a tie
+      count++;
+      tie = true;
+    }
+  }
+  if (tie) *amb = true;
+  if (count == 0) { *best = -1; return T_NEITHER_MAP; }
+  if (count == 1) {
+    if (res[*best].flags & 1) *amb = true;
+    return T_UNIQUE_SINGLE;
+  }
+  *best = -1;
+  return T_NON_NO;
+}
+
+__device__ __forceinline__ int pair_rule_int(const Task* ta, const ITaskResult* ra, int n1, int l1, const Task* tb,
+                                             const ITaskResult* rb, int n2, int l3, const DevParams& p, int* keep1,
+                                             int* keep2, bool* amb) {
+  const double good1 = (double)l1 * p.min_align * p.match_bonus * 36.0, good2 = (double)l3 * p.min_align * p.match_bonus * 36.0;
+  for (int i = 0; i < n1; i++)
+    if ((ra[i].flags & 2) || ge_good(ra[i].score36, good1) < 0) *amb = true;
+  for (int i = 0; i < n2; i++)
+    if ((rb[i].flags & 2) || ge_good(rb[i].score36, good2) < 0) *amb = true;
+  long long tot_best = -100000LL * 36;
+  int perfect = 0, slip = 0, sm1 = -1, sm2 = -1;
+  *keep1 = *keep2 = -1;
+  for (int w1 = 0; w1 < n1; w1++) {
+    if (ge_good(ra[w1].score36, good1) <= 0) continue;
+    const long long p1 = (long long)ta[w1].spot;
+    const int or1 = (int)(ta[w1].rm >> 31);
+    for (int w2 = 0; w2 < n2; w2++) {
+      if (ge_good(rb[w2].score36, good2) <= 0) continue;
+      long long dist = p1 - (long long)tb[w2].spot;
+      if (dist < 0) dist = -dist;
+      if (!(dist >= p.min_dist && dist <= p.max_dist && or1 != (int)(tb[w2].rm >> 31))) continue;
+      const long long sum = (long long)ra[w1].score36 + rb[w2].score36;
+      if (sum > tot_best) {  // inc > 0.001: sums differ by at least 1/36
+        perfect = 1;
+        sm1 = w1;
+        sm2 = w2;
+        tot_best = sum;
+        slip = 1;
+      } else if (sum == tot_best) {  // inc > -0.001: equal sums differ by rounding only
+        if (sm1 == w1 || sm2 == w2) slip++;
+        perfect++;
+      }
+    }
+  }
+  if (perfect > 0) {
+    if (perfect == 1 || slip == perfect) {
+      *keep1 = sm1;
+      *keep2 = sm2;
+      if ((ra[sm1].flags | rb[sm2].flags) & 1) *amb = true;
+      return perfect == 1 ? T_UNIQUE_MATE : T_UNIQUE_SLIP;
+    }
+    return T_NON_MATE;
+  }
+  int best1 = 0, best2 = 0, c1 = 0, c2 = 0;
+  bool tie1 = false, tie2 = false;
+  for (int i = 1; i < n1; i++) {
+    if (ra[i].score36 > ra[best1].score36) { best1 = i; c1 = 1; tie1 = false; }
+    else if (ra[i].score36 == ra[best1].score36) { c1++; tie1 = true; }  // '>' on doubles is undecided here
+  }
+  for (int i = 1; i < n2; i++) {
+    if (rb[i].score36 > rb[best2].score36) { best2 = i; c2 = 1; tie2 = false; }
+    else {
+      if (rb[i].score36 == rb[best2].score36) tie2 = true;
+      const int other = best1 < n2 ? rb[best1].score36 : -36;  // smax2[best1] (sic, 1468); unset entries are -1.0
+      if (rb[i].score36 >= other) c2++;
+    }
+  }
+  if (tie1 || tie2) *amb = true;
+  const bool ok2 = ge_good(rb[best2].score36, good2) > 0 && c2 < 2;
+  if (ge_good(ra[best1].score36, good1) > 0 && c1 < 2) {
+    *keep1 = best1;
+    if (ra[best1].flags & 1) *amb = true;
+    if (ok2) {
+      *keep2 = best2;
+      if (rb[best2].flags & 1) *amb = true;
+      return T_UNIQUE_MIS;
+    }
+    return T_UNIQUE_SINGLE;
+  }
+  if (ok2) {
+    *keep2 = best2;
+    if (rb[best2].flags & 1) *amb = true;
+    return T_UNIQUE_SINGLE;
+  }
+  return T_NON_MIS;
+}
+
+__global__ void __launch_bounds__(128) k_select_int(SelectIntArgs a) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.n_reads) return;
+  const int n1 = (int)a.cand_n[2 * r], n2 = a.p.pair_flag ? (int)a.cand_n[2 * r + 1] : 0;
+  const uint32_t b1 = a.cand_base[2 * r], b2 = a.p.pair_flag ? a.cand_base[2 * r + 1] : 0;
+  const int l1 = a.len[0][r], l3 = a.p.pair_flag ? a.len[1][r] : 0;
+  int keep1 = -1, keep2 = -1, call;
+  bool amb = false;
+  if (n1 > 0 && n2 == 0) call = single_rule_int(a.ires + b1, n1, l1, a.p, &keep1, &amb);
+  else if (n2 > 0 && n1 == 0) call = single_rule_int(a.ires + b2, n2, l3, a.p, &keep2, &amb);
+  else if (n1 > 0 && n2 > 0)
+    call = pair_rule_int(a.tasks + b1, a.ires + b1, n1, l1, a.tasks + b2, a.ires + b2, n2, l3, a.p, &keep1, &keep2, &amb);
+  else call = T_NEITHER_MAP;
+  if (amb) {  // hand the whole read (pair) to the exact path
+    const uint32_t slot = atomicAdd(a.replay_read_cursor, 1u);
+    a.replay_reads[slot] = (uint32_t)r;
+    const uint32_t tot = (uint32_t)(n1 + n2);
+    const uint32_t at = atomicAdd(a.replay_task_cursor, tot);
+    for (int q = 0; q < n1; q++) { a.replay_tasks[at + q].task = b1 + q; a.replay_tasks[at + q].rm = 2u * r; }
+    for (int q = 0; q < n2; q++) { a.replay_tasks[at + n1 + q].task = b2 + q; a.replay_tasks[at + n1 + q].rm = 2u * r + 1u; }
+    atomicAdd(&a.counters->replayed, (unsigned long long)((n1 > 0) + (n2 > 0)));
+    return;
+  }
+  uint32_t m1 = 0, m2 = 0;
+  if (keep1 >= 0) {
+    const ITaskResult ir = a.ires[b1 + keep1];
+    m1 = a.tasks[b1 + keep1].wstart + (uint32_t)ir.maxi + 1u;
+    TaskResult t64;
+    t64.score = (double)ir.score36 / 36.0;
+    t64.maxi = ir.maxi;
+    t64.maxk = ir.maxk;
+    a.results64[b1 + keep1] = t64;
+    const uint32_t w = atomicAdd(a.winner_cursor, 1u);
+    a.winners[w].task = b1 + (uint32_t)keep1;
+    a.winners[w].rm = 2u * (uint32_t)r;
+  }
+  if (keep2 >= 0) {
+    const ITaskResult ir = a.ires[b2 + keep2];
+    m2 = a.tasks[b2 + keep2].wstart + (uint32_t)ir.maxi + 1u;
+    TaskResult t64;
+    t64.score = (double)ir.score36 / 36.0;
+    t64.maxi = ir.maxi;
+    t64.maxk = ir.maxk;
+    a.results64[b2 + keep2] = t64;
+    const uint32_t w = atomicAdd(a.winner_cursor, 1u);
+    a.winners[w].task = b2 + (uint32_t)keep2;
+    a.winners[w].rm = 2u * (uint32_t)r + 1u;
+  }
+  a.m1[r] = m1;
+  a.m2[r] = m2;
+  a.mapping_type[r] = call;
+}
+
+}  // namespace pm

@@ -20,7 +20,8 @@ namespace pm {
 struct SwArgs {
   const Task* tasks;
   TaskResult* results;         // score kernel: written; trace kernel: read (maxk/maxi of the winner)
-  const Winner* winners;       // trace kernel only
+  const Winner* winners;       // trace kernel: the winners; score kernel with list_mode: the tasks to (re)score
+  int list_mode;
   const uint32_t* n_items;     // device counter: number of tasks (score) or winners (trace)
   const char* reads[2];
   const int* len[2];
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
   char* win = s_win[grp];
 
   for (uint32_t item = ggid; item < n_items; item += n_groups) {
-    const uint32_t task_id = TRACE ? a.winners[item].task : item;
+    const uint32_t task_id = (TRACE || a.list_mode) ? a.winners[item].task : item;
     const Task tk = a.tasks[task_id];
     const int orient = (int)(tk.rm >> 31);
     const uint32_t rm = tk.rm & 0x7FFFFFFFu;

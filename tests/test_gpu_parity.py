@@ -45,7 +45,22 @@ def _assert_parity(name, mapper, oracle, run, n=None, cand_step=37):
     orec = oracle.records()
     grec, gins = mapper.finish()
     assert orec.tobytes() == grec.tobytes(), tag + ": pileup records"
-    assert oracle.insertions() == sorted(gins), tag + ": insertion strings"
+    oins = oracle.insertions()
+    assert oins == sorted(gins), tag + ": insertion strings"
+    # default mode: integer DPX scoring + fp64 replay of rational ties must give the same bytes
+    # (keep(DETAIL) above forced the all-fp64 path, whose scores are the reference's doubles bit for bit)
+    mapper.keep(0)
+    mapper.reset_counts()
+    mapper.reset_stats()
+    fm1, fm2, fty = mapper.map_batch(r1, r2)
+    assert np.array_equal(om1, fm1), tag + ": m1 (integer path)"
+    assert np.array_equal(om2, fm2), tag + ": m2 (integer path)"
+    assert np.array_equal(oty, fty), tag + ": mapping_type (integer path)"
+    frec, fins = mapper.finish()
+    assert orec.tobytes() == frec.tobytes(), tag + ": pileup records (integer path)"
+    assert oins == sorted(fins), tag + ": insertion strings (integer path)"
+    st = mapper.stats()
+    print("%s: %d read-mates, %d replayed in fp64 (%.2f%%)" % (tag, st["reads"], st["replayed"], 100.0 * st["replayed"] / max(1, st["reads"])))
     return gm1, gm2, gty, grec
 
 

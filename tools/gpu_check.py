@@ -80,6 +80,21 @@ def compare_run(mapper, oracle, run, max_reads, out):
         res["first_bad_records"] = [[orec[j].tolist(), grec[j].tolist()] for j in w[:5]]
     res["stats"] = mapper.stats()
     res["oracle_cells"] = int(oracle.cells())
+    # integer fast path (default mode)
+    mapper.keep(0)
+    mapper.reset_counts()
+    mapper.reset_stats()
+    fm1, fm2, fty = mapper.map_batch(r1, r2)
+    frec, fins = mapper.finish()
+    res["fast_m1_equal"] = bool(np.array_equal(om1, fm1))
+    res["fast_m2_equal"] = bool(np.array_equal(om2, fm2))
+    res["fast_type_equal"] = bool(np.array_equal(oty, fty))
+    res["fast_records_equal"] = bool(orec.shape == frec.shape and orec.tobytes() == frec.tobytes())
+    res["fast_insertions_equal"] = bool(oins == sorted(fins))
+    fst = mapper.stats()
+    res["fast_stats"] = {k: fst[k] for k in ("reads", "replayed", "ms_seed", "ms_sw", "ms_select", "ms_traceback", "ms_total")}
+    fbad = np.nonzero((om1 != fm1) | (om2 != fm2) | (oty != fty))[0]
+    res["fast_bad_reads"] = [[int(i), int(om1[i]), int(om2[i]), int(oty[i]), int(fm1[i]), int(fm2[i]), int(fty[i])] for i in fbad[:10]]
     out.append({"summary": res, "bad": dump})
     print(json.dumps(res), flush=True)
     return res
