@@ -95,6 +95,7 @@ typedef struct pemap_stats {
   uint64_t replayed;        /* read-mates whose integer result had a rational tie and was re-scored in fp64 */
   double ms_seed, ms_sw, ms_select, ms_traceback, ms_total; /* CUDA-event time per stage, accumulated */
   uint64_t launches;        /* kernels launched by this library */
+  uint64_t diag_traced;     /* winners whose traceback was a pure diagonal (no gap, no rational tie): no DP recompute */
 } pemap_stats;
 
 typedef struct pemap_ctx pemap_t;

@@ -64,7 +64,9 @@ struct pemap_ctx {
   pm::Task* d_tasks = nullptr;
   pm::TaskResult* d_results = nullptr;
   uint32_t task_cap = 0;
-  uint32_t* d_cursors = nullptr;  // [0] tasks, [1] winners, [2] replay reads, [3] replay tasks, [4]/[5] min/max len
+  uint32_t* d_cursors = nullptr;  // [0] tasks, [1] winners, [2] replay reads, [3] replay tasks, [4]/[5] min/max len,
+                                  // [6] pure-diagonal winners
+  pm::Winner* d_diag_winners = nullptr;
   pm::ITaskResult* d_ires = nullptr;
   uint32_t* d_replay_reads = nullptr;
   pm::Winner* d_replay_tasks = nullptr;
@@ -241,6 +243,7 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   CK(cudaMemset(h->d_cand_n, 0, 2 * n * 4));
   CK(cudaMemset(h->d_cand_base, 0, 2 * n * 4));
   CK(cudaMalloc(&h->d_winners, 2 * n * sizeof(pm::Winner)));
+  CK(cudaMalloc(&h->d_diag_winners, 2 * n * sizeof(pm::Winner)));
   CK(cudaMalloc(&h->d_m1, n * 4));
   CK(cudaMalloc(&h->d_m2, n * 4));
   CK(cudaMalloc(&h->d_type, n * 4));
@@ -337,6 +340,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   const bool paired = h->params.pair_flag && d_r2;
   const bool exact = h->exact || (h->keep & PEMAP_KEEP_DETAIL) || h->params.match_bonus != 1.0;
   CK(cudaMemsetAsync(h->d_cursors, 0, 16, h->stream));
+  CK(cudaMemsetAsync(h->d_cursors + 6, 0, 4, h->stream));
   CK(cudaEventRecord(h->ev[0], h->stream));
   pm::SeedArgs sa;
   sa.pos_index = h->d_pos_index;
@@ -442,6 +446,8 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     si.mapping_type = d_type;
     si.winners = h->d_winners;
     si.winner_cursor = h->d_cursors + 1;
+    si.diag_winners = h->d_diag_winners;
+    si.diag_cursor = h->d_cursors + 6;
     si.replay_reads = h->d_replay_reads;
     si.replay_read_cursor = h->d_cursors + 2;
     si.replay_tasks = h->d_replay_tasks;
@@ -462,6 +468,22 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   }
   CK(cudaEventRecord(h->ev[3], h->stream));
 
+  if (!exact) {  // winners whose walk is a pure diagonal need no DP recompute
+    pm::DiagArgs da;
+    da.tasks = h->d_tasks;
+    da.ires = h->d_ires;
+    da.winners = h->d_diag_winners;
+    da.n_items = h->d_cursors + 6;
+    da.reads[0] = d_r1;
+    da.reads[1] = d_r2;
+    da.len[0] = d_l1;
+    da.len[1] = d_l2;
+    da.stride = stride;
+    da.counts = h->d_counts;
+    da.counters = h->d_counters;
+    pm::k_apply_diag<<<h->sm_count * 8, 256, 0, h->stream>>>(da);
+    h->stats.launches++;
+  }
   wa.n_items = h->d_cursors + 1;
   dispatch_sw<true>(h, wa, max_len);
   CK(cudaEventRecord(h->ev[4], h->stream));
@@ -541,6 +563,7 @@ int fetch_counters(pemap_ctx* h) {
   h->stats.sw_cells = c.sw_cells;
   h->stats.tb_cells = c.tb_cells;
   h->stats.replayed = c.replayed;
+  h->stats.diag_traced = c.diag_traced;
   return PEMAP_OK;
 }
 
@@ -1013,7 +1036,7 @@ void pemap_destroy(pemap_t* h) {
                    h->d_reads[0], h->d_reads[1], h->d_len[0], h->d_len[1], h->d_tasks, h->d_results, h->d_cursors,
                    h->d_cand_base, h->d_cand_n, h->d_winners, h->d_m1, h->d_m2, h->d_type, h->d_det_best, h->d_det_orient,
                    h->d_det_score, h->d_seed_scratch, h->d_dirs, h->d_pend, h->d_counters, h->d_ires, h->d_replay_reads,
-                   h->d_replay_tasks};
+                   h->d_replay_tasks, h->d_diag_winners};
     for (void* p : dev)
       if (p) cudaFree(p);
     void* host[] = {h->h_reads[0], h->h_reads[1], h->h_len[0], h->h_len[1], h->h_m1, h->h_m2, h->h_type};

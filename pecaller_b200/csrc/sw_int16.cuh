@@ -24,7 +24,8 @@ struct ITaskResult {
   int32_t score36;  // score in units of 1/36
   uint16_t maxi;    // start[1]
   uint8_t maxk;     // start[0]
-  uint8_t flags;    // 1: the last-column argmax has a rational tie; 2: a base outside ACGTN (codes not valid)
+  uint8_t flags;    // 1: the last-column argmax has a rational tie; 2: a base outside ACGTN (codes not valid);
+                    // 4: the traceback from (0, maxi, mm) is a pure diagonal decided by strict integer inequalities
 };
 
 struct SwIntArgs {
@@ -61,9 +62,10 @@ __device__ __forceinline__ uint32_t read_code(char ch) {
   }
 }
 
-__device__ __forceinline__ void track_best(int v0, int v1, int v2, int i, int& best, int& bk, int& bi, int& tie) {
+__device__ __forceinline__ void track_best(int v0, int v1, int v2, int dq, int i, int& best, int& bk, int& bi, int& tie,
+                                           int& bdq) {
   // scan of the last column, states 0,1,2 in order with strict '>' (1724-1741); equal values are remembered
-  if (v0 > best) { best = v0; bk = 0; bi = i; tie = 0; } else if (v0 == best) tie = 1;
+  if (v0 > best) { best = v0; bk = 0; bi = i; tie = 0; bdq = dq; } else if (v0 == best) tie = 1;
   if (v1 > best) { best = v1; bk = 1; bi = i; tie = 0; } else if (v1 == best) tie = 1;
   if (v2 > best) { best = v2; bk = 2; bi = i; tie = 0; } else if (v2 == best) tie = 1;
 }
@@ -73,8 +75,9 @@ __device__ __forceinline__ void track_best(int v0, int v1, int v2, int i, int& b
 template <int G, int WD, int CMM>
 __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
   constexpr int GPB = 128 / G;
-  __shared__ uint32_t s_win[GPB][PM_DP_MAX];
-  __shared__ uint32_t s_last[CMM >= 0 ? GPB : 1][CMM >= 0 ? 3 * PM_DP_MAX : 1];  // last read column of every row
+  constexpr int ROWS = (G * WD + 24 < PM_DP_MAX) ? G * WD + 24 : PM_DP_MAX;  // window rows: nn <= len + 21
+  __shared__ uint32_t s_win[GPB][ROWS];
+  __shared__ __align__(16) uint32_t s_last[CMM >= 0 ? GPB : 1][CMM >= 0 ? 4 * ROWS : 4];  // last read column of every row
   const int tid = threadIdx.x, grp = tid / G, gl = tid % G;
   const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) / G * G));
   const uint32_t n_items = *a.n_items, n_pairs = (n_items + 1) >> 1;
@@ -103,7 +106,9 @@ __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
       if (i < nnB) { cB = ref_code(a.genome[(size_t)tB.wstart + i], a.p.is_bisulfite); badB |= (cB == 0); }
       win[i] = cA | (cB << 16);
     }
-    uint32_t q[WD], s0u[WD], s1u[WD], mu[WD];
+    // dvu: "diagonal quality" E[i][j] = min over the cells (i-t, j-t), t >= 0, of (S0 - max(S1, S2)) clipped at 0:
+    // >= 1 iff the traceback arriving there in state 0 keeps taking state 0 by strict inequalities (1804-1811)
+    uint32_t q[WD], s0u[WD], s1u[WD], mu[WD], dvu[WD];
     const int jbase = gl * WD;
 #pragma unroll
     for (int c = 0; c < WD; c++) {
@@ -117,6 +122,7 @@ __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
       s0u[c] = b | (b << 16);
       s1u[c] = s0u[c];
       mu[c] = s0u[c] - K12;
+      dvu[c] = 0xFFFFFFFFu;  // row 0 is never consulted by the walk (loop ends at i == 0)
     }
     badA = __any_sync(gmask, badA);
     badB = __any_sync(gmask, badB);
@@ -132,9 +138,9 @@ __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
       colA = ownA ? (mmA - 1) % WD : -1;
       colB = ownB ? (mmB - 1) % WD : -1;
     }
-    int bestA = PM_IBIAS - 72 - (mmA - 1), bkA = 0, biA = 0, tieA = 0;  // S[0][0][mm] (1701-1703)
-    int bestB = PM_IBIAS - 72 - (mmB - 1), bkB = 0, biB = 0, tieB = 0;
-    uint32_t out_s0 = 0, out_s2 = 0, out_m = 0;
+    int bestA = PM_IBIAS - 72 - (mmA - 1), bkA = 0, biA = 0, tieA = 0, dqA = 0;  // S[0][0][mm] (1701-1703)
+    int bestB = PM_IBIAS - 72 - (mmB - 1), bkB = 0, biB = 0, tieB = 0, dqB = 0;
+    uint32_t out_s0 = 0, out_s2 = 0, out_m = 0, out_dv = 0xFFFFFFFFu;
     __syncwarp(gmask);
 
     const int steps = nn > 0 ? nn + G - 1 : 0;
@@ -142,10 +148,12 @@ __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
       uint32_t l_s0 = __shfl_up_sync(gmask, out_s0, 1, G);
       uint32_t l_s2 = __shfl_up_sync(gmask, out_s2, 1, G);
       uint32_t diag = __shfl_up_sync(gmask, out_m, 1, G);
+      uint32_t dvd = __shfl_up_sync(gmask, out_dv, 1, G);
       if (gl == 0) {  // column 0: S0 = 0, S2 = -72, M(row above) - 12 = -12 (2062-2081)
         l_s0 = BIASP;
         l_s2 = BIASP - 0x00480048u;
         diag = BIASP - K12;
+        dvd = 0xFFFFFFFFu;  // the walk stops at j == 0
       }
       const int i = s - gl + 1;
       if (i >= 1 && i <= nn) {
@@ -157,19 +165,23 @@ __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
           const uint32_t m01 = __vminu2(q[c] & rc, K1);                      // 1 where the bases match
           const uint32_t s0 = m01 * 48u + diag;                              // (M - 12) + 48 or + 0 (1713 / 1723)
           diag = mu[c];
-          const uint32_t m = __vimax3_s16x2(s0, s1, s2);
+          const uint32_t m12 = __vmaxs2(s1, s2);
+          const uint32_t m = __vmaxs2(s0, m12);
           if (CMM >= 0) {
             if (c == CMM && ownA) {  // uniform read length: park the last column, scan it after the sweep
-              last[3 * (i - 1)] = s0;
-              last[3 * (i - 1) + 1] = s1;
-              last[3 * (i - 1) + 2] = s2;
+              *reinterpret_cast<uint4*>(&last[4 * (i - 1)]) = make_uint4(s0, s1, s2, dvd);
             }
           } else {
             if (c == colA && ownA && i <= nnA)
-              track_best((int)(s0 & 0xFFFFu), (int)(s1 & 0xFFFFu), (int)(s2 & 0xFFFFu), i, bestA, bkA, biA, tieA);
+              track_best((int)(s0 & 0xFFFFu), (int)(s1 & 0xFFFFu), (int)(s2 & 0xFFFFu), (int)(dvd & 0xFFFFu), i, bestA, bkA,
+                         biA, tieA, dqA);
             if (c == colB && ownB && i <= nnB)
-              track_best((int)(s0 >> 16), (int)(s1 >> 16), (int)(s2 >> 16), i, bestB, bkB, biB, tieB);
+              track_best((int)(s0 >> 16), (int)(s1 >> 16), (int)(s2 >> 16), (int)(dvd >> 16), i, bestB, bkB, biB, tieB, dqB);
           }
+          // both halves of m - m12 are >= 0, so the plain subtraction does not borrow across halves
+          const uint32_t e = __vminu2(dvd, m - m12);
+          dvd = dvu[c];
+          dvu[c] = e;
           s0u[c] = s0;
           s1u[c] = s1;
           mu[c] = m - K12;
@@ -179,6 +191,7 @@ __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
         out_s0 = l_s0;
         out_s2 = l_s2;
         out_m = diag;
+        out_dv = dvd;
       }
     }
     if (CMM >= 0) {
@@ -194,7 +207,7 @@ __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
         lB = ((uint32_t)bestB << 10);
       }
       for (int r = gl; r < nn; r += G) {
-        const uint32_t w0 = last[3 * r], w1 = last[3 * r + 1], w2 = last[3 * r + 2];
+        const uint32_t w0 = last[4 * r], w1 = last[4 * r + 1], w2 = last[4 * r + 2];
         const uint32_t o = 3u * (uint32_t)(r + 1);
         if (r < nnA) {
           const uint32_t v0 = (w0 & 0xFFFFu) << 10, v1 = (w1 & 0xFFFFu) << 10, v2 = (w2 & 0xFFFFu) << 10;
@@ -217,13 +230,15 @@ __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
       const uint32_t oA = 1023u - (fA & 1023u), oB = 1023u - (fB & 1023u);
       bestA = (int)(fA >> 10); biA = (int)(oA / 3u); bkA = (int)(oA % 3u); tieA = (lA & 1023u) != oA;
       bestB = (int)(fB >> 10); biB = (int)(oB / 3u); bkB = (int)(oB % 3u); tieB = (lB & 1023u) != oB;
+      dqA = biA > 0 ? (int)(last[4 * (biA - 1) + 3] & 0xFFFFu) : 0;
+      dqB = biB > 0 ? (int)(last[4 * (biB - 1) + 3] >> 16) : 0;
     }
     if (ownA) {
       ITaskResult r;
       r.score36 = bestA - PM_IBIAS;
       r.maxi = (uint16_t)biA;
       r.maxk = (uint8_t)bkA;
-      r.flags = (uint8_t)((tieA ? 1 : 0) | (badA ? 2 : 0));
+      r.flags = (uint8_t)((tieA ? 1 : 0) | (badA ? 2 : 0) | ((bkA == 0 && biA > 0 && dqA >= 1) ? 4 : 0));
       a.results[idA] = r;
     }
     if (ownB && idB != idA) {
@@ -231,7 +246,7 @@ __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
       r.score36 = bestB - PM_IBIAS;
       r.maxi = (uint16_t)biB;
       r.maxk = (uint8_t)bkB;
-      r.flags = (uint8_t)((tieB ? 1 : 0) | (badB ? 2 : 0));
+      r.flags = (uint8_t)((tieB ? 1 : 0) | (badB ? 2 : 0) | ((bkB == 0 && biB > 0 && dqB >= 1) ? 4 : 0));
       a.results[idB] = r;
     }
   }
@@ -253,8 +268,10 @@ struct SelectIntArgs {
   uint32_t* m1;
   uint32_t* m2;
   int* mapping_type;
-  Winner* winners;
+  Winner* winners;            // winners that need the full traceback (gaps, or a rational tie on the way)
   uint32_t* winner_cursor;
+  Winner* diag_winners;       // winners whose traceback is a pure diagonal (ITaskResult.flags & 4)
+  uint32_t* diag_cursor;
   uint32_t* replay_reads;     // reads whose outcome needs the fp64 path
   uint32_t* replay_read_cursor;
   Winner* replay_tasks;       // every task of those reads
@@ -410,9 +427,15 @@ __global__ void __launch_bounds__(128) k_select_int(SelectIntArgs a) {
     t64.maxi = ir.maxi;
     t64.maxk = ir.maxk;
     a.results64[b1 + keep1] = t64;
-    const uint32_t w = atomicAdd(a.winner_cursor, 1u);
-    a.winners[w].task = b1 + (uint32_t)keep1;
-    a.winners[w].rm = 2u * (uint32_t)r;
+    if (ir.flags & 4) {
+      const uint32_t w = atomicAdd(a.diag_cursor, 1u);
+      a.diag_winners[w].task = b1 + (uint32_t)keep1;
+      a.diag_winners[w].rm = 2u * (uint32_t)r;
+    } else {
+      const uint32_t w = atomicAdd(a.winner_cursor, 1u);
+      a.winners[w].task = b1 + (uint32_t)keep1;
+      a.winners[w].rm = 2u * (uint32_t)r;
+    }
   }
   if (keep2 >= 0) {
     const ITaskResult ir = a.ires[b2 + keep2];
@@ -422,13 +445,60 @@ __global__ void __launch_bounds__(128) k_select_int(SelectIntArgs a) {
     t64.maxi = ir.maxi;
     t64.maxk = ir.maxk;
     a.results64[b2 + keep2] = t64;
-    const uint32_t w = atomicAdd(a.winner_cursor, 1u);
-    a.winners[w].task = b2 + (uint32_t)keep2;
-    a.winners[w].rm = 2u * (uint32_t)r + 1u;
+    if (ir.flags & 4) {
+      const uint32_t w = atomicAdd(a.diag_cursor, 1u);
+      a.diag_winners[w].task = b2 + (uint32_t)keep2;
+      a.diag_winners[w].rm = 2u * (uint32_t)r + 1u;
+    } else {
+      const uint32_t w = atomicAdd(a.winner_cursor, 1u);
+      a.winners[w].task = b2 + (uint32_t)keep2;
+      a.winners[w].rm = 2u * (uint32_t)r + 1u;
+    }
   }
   a.m1[r] = m1;
   a.m2[r] = m2;
   a.mapping_type[r] = call;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pileup of the pure-diagonal winners: smith_waterman_backtrack (1752-1965) when every step is the state-0
+// diagonal step (1846-1858): read base j-1 is counted at window row i-1 for j = mm .. 1 while i >= 1.
+// One warp per winner, consecutive lanes hit consecutive sites (24-byte stride) with fire-and-forget atomics.
+// ---------------------------------------------------------------------------------------------------
+
+struct DiagArgs {
+  const Task* tasks;
+  const ITaskResult* ires;
+  const Winner* winners;
+  const uint32_t* n_items;
+  const char* reads[2];
+  const int* len[2];
+  int stride;
+  uint32_t* counts;
+  SeedCounters* counters;
+};
+
+__global__ void __launch_bounds__(256) k_apply_diag(DiagArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_items = *a.n_items;
+  for (uint32_t item = gw; item < n_items; item += nw) {
+    const uint32_t task_id = a.winners[item].task;
+    const Task tk = a.tasks[task_id];
+    const int orient = (int)(tk.rm >> 31);
+    const uint32_t rm = tk.rm & 0x7FFFFFFFu;
+    const int mm = ((rm & 1) ? a.len[1] : a.len[0])[rm >> 1];
+    const char* read = ((rm & 1) ? a.reads[1] : a.reads[0]) + (size_t)(rm >> 1) * a.stride;
+    const int maxi = (int)a.ires[task_id].maxi;
+    const int steps = maxi < mm ? maxi : mm;  // the walk ends at i == 0 or j == 0
+    for (int t = lane; t < steps; t += 32) {
+      const int j1 = mm - 1 - t, i1 = maxi - 1 - t;
+      const char ch = seq_char(read, mm, orient, j1);
+      const int col = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1;
+      if (col >= 0) atomicAdd(&a.counts[((size_t)tk.wstart + (size_t)i1) * 6 + col], 1u);
+    }
+  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&a.counters->diag_traced, (unsigned long long)n_items);
 }
 
 }  // namespace pm
