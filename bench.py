@@ -376,7 +376,10 @@ def main():
                 "sw_gcups": sw_gcups, "seed_gather_gbs": seed_gbs,
                 "stage_ms_per_step": {"seed": 1000 * seed_s, "sw": 1000 * sw_s, "select": stats["ms_select"] / a.steps,
                                       "traceback": 1000 * tb_s, "sum_of_chunks": stats["ms_total"] / a.steps},
-                "mapped_reads_per_step": mapped, "mapping_types": types}
+                "mapped_reads_per_step": mapped, "mapping_types": types,
+                "tracebacks_per_step": {"pure_diagonal": stats["diag_traced"] / a.steps,
+                                        "fp64_after_tie": stats["exact_traced"] / a.steps,
+                                        "replayed_read_mates": stats["replayed"] / a.steps}}
         if not a.no_cpu_baseline and world == 1:
             ns = a.cpu_sample_pairs
             r1 = h_r1[:ns, :READ_LEN].numpy()

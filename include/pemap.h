@@ -96,6 +96,7 @@ typedef struct pemap_stats {
   double ms_seed, ms_sw, ms_select, ms_traceback, ms_total; /* CUDA-event time per stage, accumulated */
   uint64_t launches;        /* kernels launched by this library */
   uint64_t diag_traced;     /* winners whose traceback was a pure diagonal (no gap, no rational tie): no DP recompute */
+  uint64_t exact_traced;    /* winners whose integer traceback met a rational tie and was redone in fp64 */
 } pemap_stats;
 
 typedef struct pemap_ctx pemap_t;

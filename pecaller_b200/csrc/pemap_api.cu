@@ -19,6 +19,7 @@
 #include "select_finish.cuh"
 #include "sw_wavefront.cuh"
 #include "sw_int16.cuh"
+#include "trace_int.cuh"
 
 #define PEMAP_VERSION "pemap-b200 0.1 (sm_100a)"
 
@@ -65,11 +66,14 @@ struct pemap_ctx {
   pm::TaskResult* d_results = nullptr;
   uint32_t task_cap = 0;
   uint32_t* d_cursors = nullptr;  // [0] tasks, [1] winners, [2] replay reads, [3] replay tasks, [4]/[5] min/max len,
-                                  // [6] pure-diagonal winners
+                                  // [6] pure-diagonal winners, [7] winners handed to the fp64 traceback
   pm::Winner* d_diag_winners = nullptr;
+  pm::Winner* d_exact_winners = nullptr;
+  pm::Winner* d_oob_winners = nullptr;  // [8] winners whose walk left the shared-memory band
   pm::ITaskResult* d_ires = nullptr;
   uint32_t* d_replay_reads = nullptr;
   pm::Winner* d_replay_tasks = nullptr;
+  int band_half = PM_BAND_LANES / 2;  // PEMAP_BAND_HALF=0/1 narrows the traceback band (tests of the hand-over path)
   int exact = 0;  // 1: fp64 kernels for everything (PEMAP_EXACT=1, PEMAP_KEEP_DETAIL, match_bonus != 1)
   uint32_t* d_cand_base = nullptr;
   uint32_t* d_cand_n = nullptr;
@@ -233,17 +237,20 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   h->task_cap = (uint32_t)std::min<size_t>(2 * n * PM_MAX_HITS, 0x7FFFFFFFull);
   CK(cudaMalloc(&h->d_tasks, (size_t)h->task_cap * sizeof(pm::Task)));
   CK(cudaMalloc(&h->d_results, (size_t)h->task_cap * sizeof(pm::TaskResult)));
-  CK(cudaMalloc(&h->d_cursors, 32));
+  CK(cudaMalloc(&h->d_cursors, 64));
   CK(cudaMalloc(&h->d_ires, (size_t)h->task_cap * sizeof(pm::ITaskResult)));
   CK(cudaMalloc(&h->d_replay_reads, n * 4));
   CK(cudaMalloc(&h->d_replay_tasks, (size_t)h->task_cap * sizeof(pm::Winner)));
   if (const char* s = getenv("PEMAP_EXACT")) h->exact = atoi(s) != 0;
+  if (const char* s = getenv("PEMAP_BAND_HALF")) h->band_half = std::min(PM_BAND_LANES / 2, std::max(0, atoi(s)));
   CK(cudaMalloc(&h->d_cand_base, 2 * n * 4));
   CK(cudaMalloc(&h->d_cand_n, 2 * n * 4));
   CK(cudaMemset(h->d_cand_n, 0, 2 * n * 4));
   CK(cudaMemset(h->d_cand_base, 0, 2 * n * 4));
   CK(cudaMalloc(&h->d_winners, 2 * n * sizeof(pm::Winner)));
   CK(cudaMalloc(&h->d_diag_winners, 2 * n * sizeof(pm::Winner)));
+  CK(cudaMalloc(&h->d_exact_winners, 2 * n * sizeof(pm::Winner)));
+  CK(cudaMalloc(&h->d_oob_winners, 2 * n * sizeof(pm::Winner)));
   CK(cudaMalloc(&h->d_m1, n * 4));
   CK(cudaMalloc(&h->d_m2, n * 4));
   CK(cudaMalloc(&h->d_type, n * 4));
@@ -296,17 +303,44 @@ int check_contigs(pemap_ctx* h, int n) {
   return PEMAP_OK;
 }
 
-template <int G, int WD, bool TRACE>
+template <int G, int WD, int MODE>
 void launch_sw(pemap_ctx* h, const pm::SwArgs& a) {
-  pm::k_sw_fp64<G, WD, TRACE><<<h->sw_blocks, 128, 0, h->stream>>>(a);
+  const size_t dyn = MODE == 2 ? pm::trace_band_bytes<G, WD>() : 0;
+  if (MODE == 2) {
+    static bool once = false;  // per instantiation
+    if (!once) {
+      cudaFuncSetAttribute(pm::k_sw_fp64<G, WD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      once = true;
+    }
+  }
+  pm::k_sw_fp64<G, WD, MODE><<<h->sw_blocks, 128, dyn, h->stream>>>(a);
 }
 
-template <bool TRACE>
+template <int MODE>
 void dispatch_sw(pemap_ctx* h, const pm::SwArgs& a, int max_len) {
-  if (max_len <= 112) launch_sw<16, 7, TRACE>(h, a);
-  else if (max_len <= 160) launch_sw<16, 10, TRACE>(h, a);
-  else if (max_len <= 256) launch_sw<32, 8, TRACE>(h, a);
-  else launch_sw<32, 10, TRACE>(h, a);
+  if (max_len <= 112) launch_sw<16, 7, MODE>(h, a);
+  else if (max_len <= 160) launch_sw<16, 10, MODE>(h, a);
+  else if (max_len <= 256) launch_sw<32, 8, MODE>(h, a);
+  else launch_sw<32, 10, MODE>(h, a);
+  h->stats.launches++;
+}
+
+template <int G, int WD>
+void launch_trace_int(pemap_ctx* h, const pm::TraceIntArgs& a) {
+  const size_t dyn = pm::trace_band_bytes<G, WD>();
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(pm::k_trace_i32<G, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    once = true;
+  }
+  pm::k_trace_i32<G, WD><<<h->sw_blocks, 128, dyn, h->stream>>>(a);
+}
+
+void dispatch_trace_int(pemap_ctx* h, const pm::TraceIntArgs& a, int max_len) {
+  if (max_len <= 112) launch_trace_int<16, 7>(h, a);
+  else if (max_len <= 160) launch_trace_int<16, 10>(h, a);
+  else if (max_len <= 256) launch_trace_int<32, 8>(h, a);
+  else launch_trace_int<32, 10>(h, a);
   h->stats.launches++;
 }
 
@@ -340,7 +374,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   const bool paired = h->params.pair_flag && d_r2;
   const bool exact = h->exact || (h->keep & PEMAP_KEEP_DETAIL) || h->params.match_bonus != 1.0;
   CK(cudaMemsetAsync(h->d_cursors, 0, 16, h->stream));
-  CK(cudaMemsetAsync(h->d_cursors + 6, 0, 4, h->stream));
+  CK(cudaMemsetAsync(h->d_cursors + 6, 0, 12, h->stream));
   CK(cudaEventRecord(h->ev[0], h->stream));
   pm::SeedArgs sa;
   sa.pos_index = h->d_pos_index;
@@ -381,13 +415,16 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   wa.stride = stride;
   wa.genome = h->d_genome;
   wa.border = h->d_border;
-  wa.counts = h->d_counts;
   wa.dirs = h->d_dirs;
-  wa.pend = h->d_pend;
-  wa.ins_buf = h->d_ins;
-  wa.ins_cursor = h->d_ins_cursor;
-  wa.ins_cap = h->ins_cap;
+  wa.sink.counts = h->d_counts;
+  wa.sink.pend = h->d_pend;
+  wa.sink.ins_buf = h->d_ins;
+  wa.sink.ins_cursor = h->d_ins_cursor;
+  wa.sink.ins_cap = h->ins_cap;
+  wa.oob_winners = h->d_oob_winners;
+  wa.oob_cursor = h->d_cursors + 8;
   wa.counters = h->d_counters;
+  wa.band_half = h->band_half;
   wa.p = sa.p;
 
   pm::SelectArgs se;
@@ -412,7 +449,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   se.p = sa.p;
 
   if (exact) {  // the reference's arithmetic for every candidate
-    dispatch_sw<false>(h, wa, max_len);
+    dispatch_sw<0>(h, wa, max_len);
     CK(cudaEventRecord(h->ev[2], h->stream));
     pm::k_select<<<(n + 127) / 128, 128, 0, h->stream>>>(se);
     h->stats.launches++;
@@ -460,7 +497,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     ra.winners = h->d_replay_tasks;
     ra.list_mode = 1;
     ra.n_items = h->d_cursors + 3;
-    dispatch_sw<false>(h, ra, max_len);
+    dispatch_sw<0>(h, ra, max_len);
     se.read_list = h->d_replay_reads;
     se.n_list = h->d_cursors + 2;
     pm::k_select<<<(n + 127) / 128, 128, 0, h->stream>>>(se);
@@ -483,9 +520,34 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     da.counters = h->d_counters;
     pm::k_apply_diag<<<h->sm_count * 8, 256, 0, h->stream>>>(da);
     h->stats.launches++;
+    // the other winners: integer traceback; the ones with a rational tie on their path fall through to fp64
+    pm::TraceIntArgs ta;
+    ta.tasks = h->d_tasks;
+    ta.results = h->d_results;
+    ta.winners = h->d_winners;
+    ta.n_items = h->d_cursors + 1;
+    ta.exact_winners = h->d_exact_winners;
+    ta.exact_cursor = h->d_cursors + 7;
+    ta.reads[0] = d_r1;
+    ta.reads[1] = d_r2;
+    ta.len[0] = d_l1;
+    ta.len[1] = d_l2;
+    ta.stride = stride;
+    ta.genome = h->d_genome;
+    ta.sink = wa.sink;
+    ta.band_half = h->band_half;
+    ta.counters = h->d_counters;
+    ta.p = sa.p;
+    dispatch_trace_int(h, ta, max_len);
+    wa.winners = h->d_exact_winners;
+    wa.n_items = h->d_cursors + 7;
+  } else {
+    wa.n_items = h->d_cursors + 1;
   }
-  wa.n_items = h->d_cursors + 1;
-  dispatch_sw<true>(h, wa, max_len);
+  dispatch_sw<2>(h, wa, max_len);  // exact traceback, decision band in shared memory
+  wa.winners = h->d_oob_winners;   // walks that left the band (long indels): every lane's decisions in global memory
+  wa.n_items = h->d_cursors + 8;
+  dispatch_sw<1>(h, wa, max_len);
   CK(cudaEventRecord(h->ev[4], h->stream));
   CK(cudaGetLastError());
   return PEMAP_OK;
@@ -564,6 +626,7 @@ int fetch_counters(pemap_ctx* h) {
   h->stats.tb_cells = c.tb_cells;
   h->stats.replayed = c.replayed;
   h->stats.diag_traced = c.diag_traced;
+  h->stats.exact_traced = c.exact_traced;
   return PEMAP_OK;
 }
 
@@ -1036,7 +1099,7 @@ void pemap_destroy(pemap_t* h) {
                    h->d_reads[0], h->d_reads[1], h->d_len[0], h->d_len[1], h->d_tasks, h->d_results, h->d_cursors,
                    h->d_cand_base, h->d_cand_n, h->d_winners, h->d_m1, h->d_m2, h->d_type, h->d_det_best, h->d_det_orient,
                    h->d_det_score, h->d_seed_scratch, h->d_dirs, h->d_pend, h->d_counters, h->d_ires, h->d_replay_reads,
-                   h->d_replay_tasks, h->d_diag_winners};
+                   h->d_replay_tasks, h->d_diag_winners, h->d_exact_winners, h->d_oob_winners};
     for (void* p : dev)
       if (p) cudaFree(p);
     void* host[] = {h->h_reads[0], h->h_reads[1], h->h_len[0], h->h_len[1], h->h_m1, h->h_m2, h->h_type};

@@ -10,54 +10,46 @@
 //     S0[i][j] = max(S0,S1,S2)[i-1][j-1] + bump               (1713 / 1723; rounding is monotone, so adding
 //                                                              bump after the max gives the same double)
 // so scores, the last-column argmax (1717-1742) and the traceback predicates are bit-identical to the CPU.
-// TRACE stores 4 decision bits per cell in a per-group scratch and lane 0 walks them,
-// applying the pileup increments with atomics.
+// MODE 0 scores.  MODE 1/2 trace: 4 decision bits per cell (layout in trace_walk.cuh) are
+// stored and lane 0 walks them, applying the pileup increments with atomics.  MODE 2 keeps the band around the
+// winner's end diagonal in shared memory (a walk that leaves it hands the winner to the MODE 1 kernel through the
+// `oob` list); MODE 1 keeps every lane's word in a global scratch and can walk anywhere.
 #pragma once
 #include "pemap_common.cuh"
+#include "trace_walk.cuh"
 
 namespace pm {
 
 struct SwArgs {
   const Task* tasks;
-  TaskResult* results;         // score kernel: written; trace kernel: read (maxk/maxi of the winner)
-  const Winner* winners;       // trace kernel: the winners; score kernel with list_mode: the tasks to (re)score
+  TaskResult* results;         // score kernel: written; trace kernels: read (maxk/maxi of the winner)
+  const Winner* winners;       // trace kernels: the winners; score kernel with list_mode: the tasks to (re)score
   int list_mode;
   const uint32_t* n_items;     // device counter: number of tasks (score) or winners (trace)
+  Winner* oob_winners;         // MODE 2: winners whose walk left the shared-memory band
+  uint32_t* oob_cursor;
   const char* reads[2];
   const int* len[2];
   int stride;
   const char* genome;
   const double* border;        // S*[0][j], j < PM_DP_MAX (pemapper.c:2073-2081)
-  uint32_t* counts;            // [genome_size][6] pileup counters
-  unsigned long long* dirs;    // trace scratch: per group PM_DP_MAX * G words
-  char* pend;                  // trace scratch: per group PM_DP_MAX bytes (pending insertion chars)
-  unsigned char* ins_buf;      // insertion records: {u32 pos, u32 len, chars padded to 4}
-  unsigned long long* ins_cursor;
-  unsigned long long ins_cap;
+  unsigned long long* dirs;    // MODE 1 scratch: per group PM_DP_MAX * G words
+  PileSink sink;               // sink.pend: per group PM_DP_MAX bytes
   SeedCounters* counters;
+  int band_half;               // lanes kept on each side of the end-diagonal lane (PM_BAND_LANES / 2)
   DevParams p;
 };
 
-__device__ __forceinline__ char seq_char(const char* read, int len, int orient, int j0) {  // j0 = 0-based read index
-  return orient ? rt_char(read[len - 1 - j0]) : read[j0];
+__device__ __forceinline__ char seq_char(const char* read, int len, int orient, int j0) {
+  return oriented_char(read, len, orient, j0);
 }
 
-__device__ __forceinline__ void emit_insertion(const SwArgs& a, uint32_t site, const char* pend, int n) {
-  unsigned long long need = 8ull + (unsigned long long)((n + 3) & ~3);
-  unsigned long long off = atomicAdd(a.ins_cursor, need);
-  if (off + need <= a.ins_cap) {
-    uint32_t* hdr = reinterpret_cast<uint32_t*>(a.ins_buf + off);
-    hdr[0] = site;
-    hdr[1] = (uint32_t)n;
-    unsigned char* dst = a.ins_buf + off + 8;
-    for (int m = 0; m < n; m++) dst[m] = (unsigned char)pend[n - (m + 1)];  // 1892-1893: un-reverse
-  }
-  atomicAdd(&a.counts[(size_t)site * 6 + 5], 1u);  // no_ins++ (1903 / 1952)
-}
-
-template <int G, int WD, bool TRACE>
+template <int G, int WD, int MODE>
 __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
+  constexpr bool TRACE = MODE != 0;
   constexpr int GROUPS_PER_BLOCK = 128 / G;
+  constexpr int ROWS = (G * WD + 24 < PM_DP_MAX) ? G * WD + 24 : PM_DP_MAX;
+  extern __shared__ unsigned long long s_band_d[];  // MODE 2: [GROUPS_PER_BLOCK][ROWS][PM_BAND_LANES]
   __shared__ char s_win[GROUPS_PER_BLOCK][PM_DP_MAX];
   const int tid = threadIdx.x;
   const int grp = tid / G, gl = tid % G;
@@ -66,6 +58,10 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
   const uint32_t ggid = blockIdx.x * GROUPS_PER_BLOCK + grp, n_groups = gridDim.x * GROUPS_PER_BLOCK;
   const double go = a.p.go, ge = a.p.ge, match = a.p.match, mism = a.p.mism;
   char* win = s_win[grp];
+  unsigned long long* band = MODE == 2 ? s_band_d + (size_t)grp * ROWS * PM_BAND_LANES : nullptr;
+  unsigned long long* dirs = MODE == 1 ? a.dirs + (size_t)ggid * PM_DP_MAX * G : nullptr;
+  PileSink sink = a.sink;
+  if (TRACE) sink.pend = a.sink.pend + (size_t)ggid * PM_DP_MAX;
 
   for (uint32_t item = ggid; item < n_items; item += n_groups) {
     const uint32_t task_id = (TRACE || a.list_mode) ? a.winners[item].task : item;
@@ -74,9 +70,16 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
     const uint32_t rm = tk.rm & 0x7FFFFFFFu;
     const int mate = (int)(rm & 1u);
     const uint32_t r = rm >> 1;
-    const int mm = a.len[mate][r];
-    const char* read = a.reads[mate] + (size_t)r * a.stride;
-    const int nn = tk.blen;
+    const int mm = (mate ? a.len[1] : a.len[0])[r];
+    const char* read = (mate ? a.reads[1] : a.reads[0]) + (size_t)r * a.stride;
+    TaskResult res;
+    res.score = 0.0;
+    res.maxi = 0;
+    res.maxk = 0;
+    if (TRACE) res = a.results[task_id];
+    // the walk never consults rows below the winning cell
+    const int nn = TRACE ? (res.maxi < tk.blen ? res.maxi : tk.blen) : tk.blen;
+    const int dend = res.maxi - mm;
 
     __syncwarp(gmask);
     for (int i = gl; i < nn; i += G) win[i] = a.genome[(size_t)tk.wstart + i];
@@ -101,7 +104,6 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
     double best = a.border[mm];  // S[0][0][mm] (1701-1703)
     int bk = 0, bi = 0;
     double out_s0 = 0.0, out_s2 = 0.0, out_m = 0.0;
-    unsigned long long* dirs = TRACE ? a.dirs + (size_t)ggid * PM_DP_MAX * G : nullptr;
     __syncwarp(gmask);
 
     const int steps = nn > 0 ? nn + G - 1 : 0;
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
             unsigned nib = (unsigned)ak | ((s1 - ge > s0 - go) ? 4u : 0u) | ((s2 - ge > s0 - go) ? 8u : 0u);
             dword |= (unsigned long long)nib << (4 * c);
           }
-          if (c == cmm) {  // scan of the last column, states 0,1,2 in order with strict > (1724-1741)
+          if (!TRACE && c == cmm) {  // scan of the last column, states 0,1,2 in order with strict > (1724-1741)
             if (s0 > best) { best = s0; bk = 0; bi = i; }
             if (s1 > best) { best = s1; bk = 1; bi = i; }
             if (s2 > best) { best = s2; bk = 2; bi = i; }
@@ -149,13 +151,16 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
         out_s0 = l_s0;
         out_s2 = l_s2;
         out_m = diag;  // M[i-1][last column of this lane]
-        if (TRACE) dirs[(size_t)(i - 1) * G + gl] = dword;
+        if (MODE == 1) dirs[(size_t)(i - 1) * G + gl] = dword;
+        if (MODE == 2) {
+          const int slot = gl - (band_center_lane<WD>(i, dend) - a.band_half);
+          if (slot >= 0 && slot <= 2 * a.band_half) band[(i - 1) * PM_BAND_LANES + slot] = dword;
+        }
       }
     }
 
     if (!TRACE) {
       if (cmm >= 0) {  // exactly one lane owns column mm; with nn <= 0 it still holds S[0][0][mm]
-        TaskResult res;
         res.score = best;
         res.maxi = bi;
         res.maxk = bk;
@@ -165,42 +170,24 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
       __syncwarp(gmask);
       if (gl == 0 && nn > 0) {
         // smith_waterman_backtrack (1752-1965) over the stored decisions
-        const TaskResult res = a.results[task_id];
-        char* pend = a.pend + (size_t)ggid * PM_DP_MAX;
-        int n_pend = 0;
-        int k = res.maxk, i = res.maxi, j = mm, i1 = 0, j1 = 0;
-        while (i > 0 && j > 0) {
-          i1 = i - 1;
-          j1 = j - 1;
-          int pi, pj, pk = 0;
-          if (k == 0) {
-            pi = i1; pj = j1;
-            if (pi > 0 && pj > 0) pk = (int)((dirs[(size_t)(pi - 1) * G + (pj - 1) / WD] >> (4 * ((pj - 1) % WD))) & 3ull);
-          } else if (k == 2) {
-            pi = i; pj = j1;
-            if (pj > 0) pk = ((dirs[(size_t)(pi - 1) * G + (pj - 1) / WD] >> (4 * ((pj - 1) % WD))) & 8ull) ? 2 : 0;
+        if (MODE == 1) {
+          FullCell<G, WD, 4> cell;
+          cell.dirs = dirs;
+          walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink);
+          atomicAdd(&a.counters->tb_cells, (unsigned long long)nn * (unsigned long long)mm);
+        } else {
+          BandCell<WD, 4> cell;
+          cell.band = band;
+          cell.dend = dend;
+          cell.half = a.band_half;
+          if (walk_path<false, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink) == PM_WALK_OK) {
+            walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink);
+            atomicAdd(&a.counters->tb_cells, (unsigned long long)nn * (unsigned long long)mm);
           } else {
-            pi = i1; pj = j;
-            if (pi > 0) pk = ((dirs[(size_t)(pi - 1) * G + (pj - 1) / WD] >> (4 * ((pj - 1) % WD))) & 4ull) ? 1 : 0;
+            const uint32_t w = atomicAdd(a.oob_cursor, 1u);
+            a.oob_winners[w] = a.winners[item];
           }
-          const uint32_t site = tk.wstart + (uint32_t)i1;
-          if (pi != i) {
-            if (pj != j) {  // 1846-1858
-              const char ch = seq_char(read, mm, orient, j1);
-              const int col = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1;
-              if (col >= 0) atomicAdd(&a.counts[(size_t)site * 6 + col], 1u);
-            } else {
-              atomicAdd(&a.counts[(size_t)site * 6 + 4], 1u);  // 1868
-            }
-            if (n_pend > 0) emit_insertion(a, site, pend, n_pend);  // 1871-1904
-            n_pend = 0;
-          } else {
-            pend[n_pend++] = seq_char(read, mm, orient, j1);  // 1910-1911
-          }
-          i = pi; j = pj; k = pk;
         }
-        if (n_pend > 0 && i >= 1) emit_insertion(a, tk.wstart + (uint32_t)i1, pend, n_pend);  // 1918-1958
-        atomicAdd(&a.counters->tb_cells, (unsigned long long)nn * (unsigned long long)mm);
       }
       __syncwarp(gmask);
     }

@@ -167,6 +167,32 @@ def test_edge_inputs(get_fixture, ctx_cache, oracle_built):
     assert mapper.finish()[0].shape[0] == 0
 
 
+def test_traceback_band_handover(get_fixture, oracle_built, monkeypatch):
+    """The traceback kernels keep decision bits only for a band around the winner's end diagonal; walks that leave it
+    are redone by the kernel with the full store.  PEMAP_BAND_HALF=0 narrows the band to one lane so that every gapped
+    read of pe150 takes that hand-over; the pileup must not change."""
+    fx = get_fixture("pe150")
+    run = fx.runs[0]
+    oracle = ol.Oracle(fx.genome)
+    kw = dict(min_align=run.min_align, pair_flag=int(run.paired), min_dist=run.min_dist, max_dist=run.max_dist)
+    oracle.set_params(**kw)
+    n = 20000
+    o = oracle.map_batch(run.reads1[:n], run.reads2[:n] if run.paired else None, nthreads=16)
+    orec, oins = oracle.records(), oracle.insertions()
+    for half in ("0", "1"):
+        monkeypatch.setenv("PEMAP_BAND_HALF", half)
+        mapper = pb.PEMapper.from_genome(fx.genome)
+        mapper.set_params(**kw)
+        g = mapper.map_batch(run.reads1[:n], run.reads2[:n] if run.paired else None)
+        for x, y in zip(o[:3], g):
+            assert np.array_equal(x, y)
+        rec, ins = mapper.finish()
+        assert orec.tobytes() == rec.tobytes(), "band half %s: pileup records" % half
+        assert oins == sorted(ins)
+        mapper.close()
+    oracle.close()
+
+
 def test_contig_count_quirk_is_refused():
     """2..7 contigs: find_chrom reads out of bounds in the reference; we refuse instead of guessing."""
     from pecaller_b200 import synth
