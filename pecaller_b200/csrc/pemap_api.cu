@@ -51,6 +51,9 @@ struct pemap_ctx {
   uint32_t* d_cstart = nullptr;
   int n_contigs = 0;
   double* d_border = nullptr;
+  uint32_t* d_filter = nullptr;  // word-blocked Bloom filter of the occupied k-mers (seed_chain.cuh), or null
+  int filter_shift = 0, filter_k = 0;
+  size_t filter_bytes = 0;
   uint32_t* d_counts = nullptr;
 
   unsigned char* d_ins = nullptr;
@@ -257,7 +260,7 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   CK(cudaMalloc(&h->d_det_best, 2 * n * 4));
   CK(cudaMalloc(&h->d_det_orient, 2 * n * 4));
   CK(cudaMalloc(&h->d_det_score, 2 * n * 8));
-  h->seed_blocks = h->sm_count * 4;
+  h->seed_blocks = h->sm_count * 8;
   CK(cudaMalloc(&h->d_seed_scratch, (size_t)h->seed_blocks * kSeedWarps * 2 * PM_MAX_SEG * PM_SEG_CAP * 4));
   h->sw_blocks = h->sm_count * 4;
   const size_t max_groups = (size_t)h->sw_blocks * (128 / 16);
@@ -273,8 +276,52 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   return PEMAP_OK;
 }
 
+// Bloom filter of the occupied k-mers, sized to stay resident in L2 (persisting access-policy window on the stream).
+// Worth it while the genome is small against the 2^32 k-mer space; PEMAP_FILTER=0 disables it.
+int build_filter(pemap_ctx* h) {
+  if (const char* s = getenv("PEMAP_FILTER"))
+    if (atoi(s) == 0) return PEMAP_OK;
+  if (h->n_mers == 0 || h->n_mers > (1ull << 29)) return PEMAP_OK;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->device));
+  size_t cap = 64ull << 20;
+  if (const char* s = getenv("PEMAP_FILTER_MB")) cap = (size_t)std::max(1, atoi(s)) << 20;
+  if (prop.persistingL2CacheMaxSize > 0) cap = std::min(cap, (size_t)prop.persistingL2CacheMaxSize);
+  int lg = 18;  // 32-bit words: 2^18 * 4 B = 1 MB minimum
+  while ((4ull << (lg + 1)) <= cap && (32ull << lg) < 16ull * h->n_mers) lg++;  // up to 16 bits per k-mer
+  while ((4ull << lg) > cap && lg > 10) lg--;
+  h->filter_bytes = 4ull << lg;
+  h->filter_shift = 32 - lg;
+  const double bits_per_key = (double)(32ull << lg) / (double)h->n_mers;
+  h->filter_k = bits_per_key >= 12.0 ? 3 : 2;
+  CK(cudaMalloc(&h->d_filter, h->filter_bytes));
+  CK(cudaMemsetAsync(h->d_filter, 0, h->filter_bytes, h->stream));
+  pm::k_filter_build<<<1u << 22, 256, 0, h->stream>>>(h->d_pos_index, h->d_filter, h->filter_shift, h->filter_k);
+  CK(cudaGetLastError());
+  if (prop.persistingL2CacheMaxSize > 0) {
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)prop.persistingL2CacheMaxSize, h->filter_bytes));
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof(av));
+    av.accessPolicyWindow.base_ptr = h->d_filter;
+    av.accessPolicyWindow.num_bytes = std::min(h->filter_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+    av.accessPolicyWindow.hitRatio = 1.0f;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+    cudaGetLastError();
+  }
+  if (getenv("PEMAP_VERBOSE"))
+    fprintf(stderr, "pemap: k-mer filter %zu MB, %d bits/k-mer set, %.1f bits per k-mer; persisting L2 max %d MB\n",
+            h->filter_bytes >> 20, h->filter_k, bits_per_key, prop.persistingL2CacheMaxSize >> 20);
+  return PEMAP_OK;
+}
+
 int finish_init(pemap_ctx* h) {
   fill_dev_params(h);
+  {
+    int rc0 = build_filter(h);
+    if (rc0) return rc0;
+  }
   int rc = upload_border(h);
   if (rc) return rc;
   CK(cudaMalloc(&h->d_counts, (size_t)h->genome_size * 6 * 4 + 64));
@@ -394,11 +441,15 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   sa.cand_base = h->d_cand_base;
   sa.cand_n = h->d_cand_n;
   sa.counters = h->d_counters;
+  sa.filter = h->d_filter;
+  sa.filter_shift = h->filter_shift;
+  sa.filter_k = h->filter_k;
   sa.p = h->dp;
   sa.p.pair_flag = paired ? 1 : 0;
   const int work = paired ? 2 * n : n;
   const int seed_grid = std::min(h->seed_blocks, (work + kSeedWarps - 1) / kSeedWarps);
-  pm::k_seed_chain<kSeedWarps><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
+  if (h->d_filter) pm::k_seed_chain<kSeedWarps, true><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
+  else pm::k_seed_chain<kSeedWarps, false><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
   h->stats.launches++;
   CK(cudaEventRecord(h->ev[1], h->stream));
 
@@ -1095,7 +1146,7 @@ void pemap_destroy(pemap_t* h) {
   if (h->stream) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    void* dev[] = {h->d_pos_index, h->d_mers, h->d_genome, h->d_cstart, h->d_border, h->d_counts, h->d_ins, h->d_ins_cursor,
+    void* dev[] = {h->d_filter, h->d_pos_index, h->d_mers, h->d_genome, h->d_cstart, h->d_border, h->d_counts, h->d_ins, h->d_ins_cursor,
                    h->d_reads[0], h->d_reads[1], h->d_len[0], h->d_len[1], h->d_tasks, h->d_results, h->d_cursors,
                    h->d_cand_base, h->d_cand_n, h->d_winners, h->d_m1, h->d_m2, h->d_type, h->d_det_best, h->d_det_orient,
                    h->d_det_score, h->d_seed_scratch, h->d_dirs, h->d_pend, h->d_counters, h->d_ires, h->d_replay_reads,

@@ -5,9 +5,14 @@
 // set-up of map_everything (1047-1081).  Output is the candidate list in the reference's order.
 //
 // Memory behaviour: the 2*nseg*49 pos_index lookups of a read are spread over the 32 lanes and issued
-// PM_SEED_UNROLL at a time (two 4-byte read-only loads each, normally one 32-byte sector), so a warp keeps
+// PM_SEED_UNROLL at a time (two 4-byte loads each, normally one 32-byte sector), so a warp keeps
 // 2*32*PM_SEED_UNROLL independent loads in flight into the 16 GiB table; the second-level gathers from `mers`
-// go straight into the warp's private list scratch.  Lists are sorted by a warp bitonic network (registers
+// go straight into the warp's private list scratch.
+// Random 8-byte gathers from HBM run at ~42 G lookups/s on a B200 whatever the fetch size (tools/gather_probe.cu),
+// and ~97 % of the 48 one-substitution neighbours of a k-mer do not occur in a small genome.  FILT = true puts a
+// word-blocked Bloom filter of the occupied k-mers (built at init from pos_index, kept resident in L2 through a
+// persisting access-policy window) in front of the table: only k-mers the filter cannot rule out go to HBM.  The
+// filter has no false negatives, so the lists, the >= too_many_spots veto and everything downstream are unchanged.  Lists are sorted by a warp bitonic network (registers
 // for <=32 entries, scratch above) and chained with binary searches instead of the reference's cursors.
 #pragma once
 #include "pemap_common.cuh"
@@ -32,8 +37,43 @@ struct SeedArgs {
   uint32_t* cand_base;         // [2*n_reads]
   uint32_t* cand_n;            // [2*n_reads]
   SeedCounters* counters;
+  const uint32_t* filter;      // 2^(32 - filter_shift) words, or nullptr
+  int filter_shift;
+  int filter_k;                // bits set per k-mer (2..4)
   DevParams p;
 };
+
+#define PM_SEED_QUEUE 512      // per-warp queue of k-mers that passed the filter (drained 256 at a time)
+
+// word index and bit mask of a k-mer in the word-blocked (32-bit blocks) Bloom filter
+__host__ __device__ __forceinline__ void filter_slot(uint32_t code, int shift, int k, uint32_t* word, uint32_t* mask) {
+  uint32_t x = code * 0x9E3779B1u;
+  x ^= x >> 15;
+  x *= 0x85EBCA77u;
+  x ^= x >> 13;
+  *word = x >> shift;
+  uint32_t m = 1u << (x & 31u);
+  m |= 1u << ((x >> 5) & 31u);
+  if (k > 2) m |= 1u << ((x >> 10) & 31u);
+  if (k > 3) m |= 1u << ((x >> 15) & 31u);
+  *mask = m;
+}
+
+// one thread per 4 consecutive k-mer codes: occupied k-mers (count != 0 with get_mers' 32-bit wrap, 2163) are inserted
+__global__ void __launch_bounds__(256) k_filter_build(const uint32_t* pos_index, uint32_t* filter, int shift, int k) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;  // 2^30 threads
+  const uint32_t w0 = (uint32_t)(t << 2);
+  const uint4 v = *reinterpret_cast<const uint4*>(pos_index + w0);
+  const uint32_t nxt = pos_index[(uint32_t)(w0 + 4u)];  // wraps to pos_index[0] for the last group
+  const uint32_t a[5] = {v.x, v.y, v.z, v.w, nxt};
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    if (a[i + 1] != a[i]) {
+      uint32_t word, mask;
+      filter_slot(w0 + (uint32_t)i, shift, k, &word, &mask);
+      if ((filter[word] & mask) != mask) atomicOr(filter + word, mask);
+    }
+}
 
 struct SeedWarpSmem {
   char rd[2][PM_DP_MAX];       // forward read and its reverse_transcribe (C->T converted when bisulfite)
@@ -45,18 +85,77 @@ struct SeedWarpSmem {
   uint8_t hit_or[PM_MAX_HITS];
 };
 
-// one-substitution neighbour v (1..48) of a packed 16-mer, in fill_mers order: byte (low first), 2-bit field
-// (low first), alternatives ascending (mismatch table, pemapper.c:546-565)
+struct SeedQueueSmem {         // FILT only
+  uint32_t code[PM_SEED_QUEUE];
+  uint8_t ss[PM_SEED_QUEUE];
+};
+
+// pos_index lookup + mers gather of up to 32*PM_SEED_UNROLL queued k-mers (get_mers 2158-2165, loop 1594-1612)
+__device__ __forceinline__ void seed_lookup_tile(const SeedArgs& a, SeedWarpSmem& sm, uint32_t* lists, const uint32_t* qcode,
+                                                 const uint8_t* qss, int n, int lane, unsigned long long& st_pos) {
+  uint32_t lo[PM_SEED_UNROLL], hi[PM_SEED_UNROLL];
+  int ssv[PM_SEED_UNROLL];
+#pragma unroll
+  for (int u = 0; u < PM_SEED_UNROLL; u++) {
+    const int q = u * 32 + lane;
+    ssv[u] = -1;
+    lo[u] = hi[u] = 0;
+    if (q < n) {
+      const uint32_t code = qcode[q];
+      ssv[u] = qss[q];
+      if ((code & 1u) == 0u) {
+        const uint2 v = __ldcg(reinterpret_cast<const uint2*>(a.pos_index + code));
+        lo[u] = v.x;
+        hi[u] = v.y;
+      } else {
+        lo[u] = __ldcg(a.pos_index + code);
+        hi[u] = __ldcg(a.pos_index + (uint32_t)(code + 1u));  // which+1 wraps in 32 bits (2163)
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < PM_SEED_UNROLL; u++) {
+    if (ssv[u] >= 0) {
+      uint32_t cnt = hi[u] - lo[u];
+      if (cnt >= (uint32_t)a.p.too_many_spots) {
+        sm.veto[ssv[u]] = 1;  // 1602-1606: one crowded k-mer empties the whole segment
+      } else if (cnt) {
+        uint32_t off = atomicAdd(&sm.segcnt[ssv[u]], cnt);
+        uint32_t* dst = lists + (size_t)ssv[u] * PM_SEG_CAP + off;
+        const uint32_t* src = a.mers + lo[u];
+        for (uint32_t t = 0; t < cnt; t++) dst[t] = __ldcg(src + t);
+        st_pos += cnt;
+      }
+    }
+  }
+}
+
+// one-substitution neighbour v (1..48) of a packed 16-mer.  fill_mers (1969-2003) walks bytes, 2-bit fields and the
+// three alternative bases; the set it produces is { code ^ (d << 2f) : f = 0..15, d = 1..3 }, and the order of the
+// 49 lookups of a segment does not matter (their lists are concatenated and sorted, the veto is an OR).
 __device__ __forceinline__ uint32_t kmer_variant(uint32_t code, int v) {
   if (v == 0) return code;
-  int byte = (v - 1) / 12, k = (v - 1) % 12, f = k / 3, alt = k % 3;
-  int sh = 8 * byte + 2 * f;
-  uint32_t cur = (code >> sh) & 3u;
-  uint32_t nv = (uint32_t)alt + ((uint32_t)alt >= cur ? 1u : 0u);
-  return code ^ ((cur ^ nv) << sh);
+  const int f = (v - 1) / 3, d = v - 3 * f;  // d = 1..3
+  return code ^ ((uint32_t)d << (2 * f));
 }
 
 __device__ __forceinline__ void warp_sort_list(uint32_t* lst, int n, int lane) {
+  if (n <= 4) {  // the usual case on a unique genome: the exact hit plus a chance neighbour or two
+    if (lane == 0) {
+      uint32_t a = lst[0], b = lst[1], c = n > 2 ? lst[2] : 0xFFFFFFFFu, d = n > 3 ? lst[3] : 0xFFFFFFFFu, t;
+      if (a > b) { t = a; a = b; b = t; }
+      if (c > d) { t = c; c = d; d = t; }
+      if (a > c) { t = a; a = c; c = t; }
+      if (b > d) { t = b; b = d; d = t; }
+      if (b > c) { t = b; b = c; c = t; }
+      lst[0] = a;
+      lst[1] = b;
+      if (n > 2) lst[2] = c;
+      if (n > 3) lst[3] = d;
+    }
+    __syncwarp();
+    return;
+  }
   if (n <= 32) {
     uint32_t v = lane < n ? lst[lane] : 0xFFFFFFFFu;
 #pragma unroll
@@ -104,9 +203,10 @@ __device__ __forceinline__ bool list_has_in_range(const uint32_t* lst, int n, lo
   return a < n && (long long)lst[a] <= hi;
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_seed_chain(SeedArgs a) {
+template <int WARPS, bool FILT>
+__global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
   __shared__ SeedWarpSmem smem[WARPS];
+  __shared__ SeedQueueSmem qsmem[FILT ? WARPS : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   SeedWarpSmem& sm = smem[warp];
   const int gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
@@ -161,41 +261,81 @@ __global__ void __launch_bounds__(WARPS * 32) k_seed_chain(SeedArgs a) {
 
       // ---- lookups (get_mers 2158-2165) and gathers (1594-1612, 1619-1637)
       const int L = 2 * nseg * PM_KV;
-      for (int q0 = 0; q0 < L; q0 += 32 * PM_SEED_UNROLL) {
-        uint32_t lo[PM_SEED_UNROLL], hi[PM_SEED_UNROLL];
-        int ssv[PM_SEED_UNROLL];
+      if (FILT) {
+        SeedQueueSmem& qs = qsmem[warp];
+        int qn = 0;  // warp-uniform queue length
+        for (int q0 = 0; q0 < L; q0 += 32 * PM_SEED_UNROLL) {
+          uint32_t codes[PM_SEED_UNROLL], fw[PM_SEED_UNROLL], fm[PM_SEED_UNROLL];
 #pragma unroll
-        for (int u = 0; u < PM_SEED_UNROLL; u++) {
-          int q = q0 + u * 32 + lane;
-          ssv[u] = -1;
-          lo[u] = hi[u] = 0;
-          if (q < L) {
-            int ss = q / PM_KV, v = q - ss * PM_KV;
-            uint32_t code = kmer_variant(sm.kcode[ss], v);
-            ssv[u] = ss;
-            // L1-bypassing loads: a miss then costs one 32-byte sector instead of a 128-byte line fill
-            if ((code & 1u) == 0u) {
-              const uint2 v = __ldcg(reinterpret_cast<const uint2*>(a.pos_index + code));
-              lo[u] = v.x;
-              hi[u] = v.y;
-            } else {
-              lo[u] = __ldcg(a.pos_index + code);
-              hi[u] = __ldcg(a.pos_index + (uint32_t)(code + 1u));  // which+1 wraps in 32 bits (2163)
+          for (int u = 0; u < PM_SEED_UNROLL; u++) {
+            const int q = q0 + u * 32 + lane;
+            fw[u] = 0;
+            fm[u] = 1;
+            codes[u] = 0;
+            if (q < L) {
+              const int ss = q / PM_KV, v = q - ss * PM_KV;
+              codes[u] = kmer_variant(sm.kcode[ss], v);
+              uint32_t word;
+              filter_slot(codes[u], a.filter_shift, a.filter_k, &word, &fm[u]);
+              fw[u] = a.filter[word];  // L2-resident (persisting window)
             }
           }
-        }
 #pragma unroll
-        for (int u = 0; u < PM_SEED_UNROLL; u++) {
-          if (ssv[u] >= 0) {
-            uint32_t cnt = hi[u] - lo[u];
-            if (cnt >= (uint32_t)a.p.too_many_spots) {
-              sm.veto[ssv[u]] = 1;  // 1602-1606: one crowded k-mer empties the whole segment
-            } else if (cnt) {
-              uint32_t off = atomicAdd(&sm.segcnt[ssv[u]], cnt);
-              uint32_t* dst = lists + (size_t)ssv[u] * PM_SEG_CAP + off;
-              const uint32_t* src = a.mers + lo[u];
-              for (uint32_t t = 0; t < cnt; t++) dst[t] = __ldcg(src + t);
-              st_pos += cnt;
+          for (int u = 0; u < PM_SEED_UNROLL; u++) {
+            const bool pass = (fw[u] & fm[u]) == fm[u];  // lanes past L hold fw = 0, fm = 1
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
+            if (pass) {
+              const int at = qn + __popc(bal & ((1u << lane) - 1u));
+              qs.code[at] = codes[u];
+              qs.ss[at] = (uint8_t)((q0 + u * 32 + lane) / PM_KV);
+            }
+            qn += __popc(bal);
+          }
+          __syncwarp();
+          while (qn >= 32 * PM_SEED_UNROLL) {  // drain a full tile from the tail
+            qn -= 32 * PM_SEED_UNROLL;
+            seed_lookup_tile(a, sm, lists, qs.code + qn, qs.ss + qn, 32 * PM_SEED_UNROLL, lane, st_pos);
+            __syncwarp();
+          }
+        }
+        if (qn > 0) seed_lookup_tile(a, sm, lists, qs.code, qs.ss, qn, lane, st_pos);
+      } else {
+        for (int q0 = 0; q0 < L; q0 += 32 * PM_SEED_UNROLL) {
+          uint32_t lo[PM_SEED_UNROLL], hi[PM_SEED_UNROLL];
+          int ssv[PM_SEED_UNROLL];
+#pragma unroll
+          for (int u = 0; u < PM_SEED_UNROLL; u++) {
+            int q = q0 + u * 32 + lane;
+            ssv[u] = -1;
+            lo[u] = hi[u] = 0;
+            if (q < L) {
+              int ss = q / PM_KV, v = q - ss * PM_KV;
+              uint32_t code = kmer_variant(sm.kcode[ss], v);
+              ssv[u] = ss;
+              // L1-bypassing loads (the line would never be reused)
+              if ((code & 1u) == 0u) {
+                const uint2 v = __ldcg(reinterpret_cast<const uint2*>(a.pos_index + code));
+                lo[u] = v.x;
+                hi[u] = v.y;
+              } else {
+                lo[u] = __ldcg(a.pos_index + code);
+                hi[u] = __ldcg(a.pos_index + (uint32_t)(code + 1u));  // which+1 wraps in 32 bits (2163)
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < PM_SEED_UNROLL; u++) {
+            if (ssv[u] >= 0) {
+              uint32_t cnt = hi[u] - lo[u];
+              if (cnt >= (uint32_t)a.p.too_many_spots) {
+                sm.veto[ssv[u]] = 1;  // 1602-1606: one crowded k-mer empties the whole segment
+              } else if (cnt) {
+                uint32_t off = atomicAdd(&sm.segcnt[ssv[u]], cnt);
+                uint32_t* dst = lists + (size_t)ssv[u] * PM_SEG_CAP + off;
+                const uint32_t* src = a.mers + lo[u];
+                for (uint32_t t = 0; t < cnt; t++) dst[t] = __ldcg(src + t);
+                st_pos += cnt;
+              }
             }
           }
         }
