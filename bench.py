@@ -265,11 +265,8 @@ def main():
     torch.cuda.synchronize()
 
     lib_stream = torch.cuda.ExternalStream(mapper.stream_ptr(), device=dev)
-    counts_ptr, counts_words = mapper.counts_device()
-
-    class _Alias:  # torch view of the library's counter array for the NCCL sum
-        __cuda_array_interface__ = {"shape": (counts_words,), "typestr": "<i4", "data": (counts_ptr, False), "version": 2}
-    counts_t = torch.as_tensor(_Alias(), device=dev) if world > 1 else None
+    from pecaller_b200 import sharding
+    counts_t = sharding.counts_tensor(mapper, dev) if world > 1 else None  # torch view of the library's counter array
 
     def barrier():
         torch.cuda.synchronize()
@@ -281,13 +278,13 @@ def main():
         mapper.map_device(n, d_r1.data_ptr(), d_len.data_ptr(), d_r2.data_ptr(), d_len.data_ptr(), STRIDE, READ_LEN,
                           d_m1.data_ptr(), d_m2.data_ptr(), d_ty.data_ptr())
         if world > 1:
-            dist.reduce(counts_t, dst=0)
+            sharding.reduce_counts(counts_t, dst=0)
 
     def step_host():
         mapper._ck(mapper._L.pemap_map_batch_rows(mapper._h, n, h_r1.data_ptr(), h_len.data_ptr(), h_r2.data_ptr(),
                                                   h_len.data_ptr(), STRIDE, h_m1.data_ptr(), h_m2.data_ptr(), h_ty.data_ptr()))
         if world > 1:
-            dist.reduce(counts_t, dst=0)
+            sharding.reduce_counts(counts_t, dst=0)
 
     # ---- device-resident leg
     for _ in range(a.warmup):
@@ -337,32 +334,45 @@ def main():
 
     if rank == 0:
         hbm_peak, peak_src, _ = peaks()
-        per_step = {k: stats[k] / a.steps for k in ("lookups", "mer_positions", "candidates", "sw_cells", "tb_cells")}
+        per_step = {k: stats[k] / a.steps for k in ("lookups", "mer_positions", "candidates", "sw_cells", "tb_cells",
+                                                     "tb_cells_int")}
         seed_bytes = per_step["lookups"] * 8 + per_step["mer_positions"] * 4 + 2 * n * ((READ_LEN + 3) // 4)
         seed_s = stats["ms_seed"] / a.steps / 1000.0
         sw_s = stats["ms_sw"] / a.steps / 1000.0
         tb_s = stats["ms_traceback"] / a.steps / 1000.0
+        tbi_s = max(stats["ms_tb_int"] / a.steps / 1000.0, 1e-9)
+        tbf_s = max(stats["ms_tb_fp64"] / a.steps / 1000.0, 1e-9)
         seed_gbs = seed_bytes / seed_s / 1e9
         sw_gcups = per_step["sw_cells"] / sw_s / 1e9
-        tb_gcups = per_step["tb_cells"] / tb_s / 1e9
-        ap_ = alu_peak()
+        ap_ = alu_peak() or {}
+        pk16, pk32, pk64 = ap_.get("sw_s16x2_gcups_peak"), ap_.get("sw_s32_gcups_peak"), ap_.get("sw_fp64_gcups_peak")
+        src = "profiles/alu_peak.json (issue rates measured with tools/alu_peak.cu on a B200, SURVEY 8d: 10 ops per cell)"
+
+        def alu_roof(kernel, cells, secs, peak):
+            g = cells / secs / 1e9
+            return {"kernel": kernel, "bound": "alu", "achieved": g, "peak": peak, "unit": "GCUPS",
+                    "frac": (g / peak) if peak else None, "traffic": None, "ms_per_step": 1000 * secs,
+                    "peak_source": src if peak else "not measured"}
         roof_seed = {"kernel": "k_seed_chain", "bound": "hbm", "achieved": seed_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": seed_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "ms_per_step": 1000 * seed_s}
-        sw_peak = ap_["sw_fp64_gcups_peak"] if ap_ and "sw_fp64_gcups_peak" in ap_ else None
-        roof_sw = {"kernel": "k_sw_fp64 (score)", "bound": "alu", "achieved": sw_gcups, "peak": sw_peak, "unit": "GCUPS",
-                   "frac": (sw_gcups / sw_peak) if sw_peak else None, "traffic": None, "ms_per_step": 1000 * sw_s,
-                   "peak_source": "profiles/alu_peak.json (measured issue rates)" if sw_peak else "not measured yet"}
-        roof_tb = {"kernel": "k_sw_fp64 (traceback)", "bound": "alu", "achieved": tb_gcups, "peak": sw_peak, "unit": "GCUPS",
-                   "frac": (tb_gcups / sw_peak) if sw_peak else None, "ms_per_step": 1000 * tb_s}
-        dominant = max((roof_seed, roof_sw, roof_tb), key=lambda r: r["ms_per_step"])
+                     "frac": seed_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "ms_per_step": 1000 * seed_s,
+                     "note": "algorithmic bytes (SURVEY 8d: 8 B per pos_index lookup + 4 B per position + packed read) over the "
+                             "stage time; random 8-byte gathers from HBM top out at %.1f G lookups/s = %.0f GB/s of algorithmic "
+                             "bytes on this part (profiles/gather_probe_r01.json), the L2-resident k-mer filter is how the "
+                             "kernel gets past that" % (ap_.get("random_gather_glookups_s", 41.7),
+                                                        8 * ap_.get("random_gather_glookups_s", 41.7))}
+        roof_sw = alu_roof("k_sw_i16 (s16x2 DPX scoring of every candidate)", per_step["sw_cells"], sw_s, pk16)
+        roof_tbi = alu_roof("k_trace_i32 (integer traceback of gapped winners)", per_step["tb_cells_int"], tbi_s, pk32)
+        roof_tbf = alu_roof("k_sw_fp64 (exact traceback after a rational tie)", per_step["tb_cells"], tbf_s, pk64)
+        dominant = max((roof_seed, roof_sw, roof_tbi, roof_tbf), key=lambda r: r["ms_per_step"])
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             trj = json.load(open(tr))
-            for rf in (roof_seed, roof_sw, roof_tb):
-                rf["traffic"] = trj.get(rf["kernel"])
+            for rf in (roof_seed, roof_sw, roof_tbi, roof_tbf):
+                rf["traffic"] = trj.get(rf["kernel"].split(" ")[0])
         line = {"metric": "mapped reads/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "vs_baseline": None, "dtype": "s16x2 integer DP in units of 1/36 (fp64 only for rational ties)",
+                "data": "synthetic",
                 "config": {"workload": "cfg2: 64 Mb single-contig genome, %d paired-end 150 bp reads per GPU per step, "
                                        "1%% subs + 0.1%% ins + 0.1%% del, insert U[250,450]" % n,
                            "l2": "inputs (%.1f GB of reads per step) and the 16 GiB index exceed the 126 MB L2" % (2 * n * STRIDE / 1e9),
@@ -372,10 +382,13 @@ def main():
                         "d2h_bytes_per_step": 3 * n * 4, "ms_per_step": ms_e2e / a.steps, "matches_device_leg": same},
                 "gpu_launches": int(stats["launches"]),
                 "clocks": clocks,
-                "roofline": dominant, "roofline_seed": roof_seed, "roofline_sw": roof_sw, "roofline_traceback": roof_tb,
+                "roofline": dominant, "roofline_seed": roof_seed, "roofline_sw": roof_sw,
+                "roofline_traceback_int": roof_tbi, "roofline_traceback_fp64": roof_tbf,
                 "sw_gcups": sw_gcups, "seed_gather_gbs": seed_gbs,
                 "stage_ms_per_step": {"seed": 1000 * seed_s, "sw": 1000 * sw_s, "select": stats["ms_select"] / a.steps,
-                                      "traceback": 1000 * tb_s, "sum_of_chunks": stats["ms_total"] / a.steps},
+                                      "traceback": 1000 * tb_s, "traceback_diag": stats["ms_tb_diag"] / a.steps,
+                                      "traceback_int": 1000 * tbi_s, "traceback_fp64": 1000 * tbf_s,
+                                      "sum_of_chunks": stats["ms_total"] / a.steps},
                 "mapped_reads_per_step": mapped, "mapping_types": types,
                 "tracebacks_per_step": {"pure_diagonal": stats["diag_traced"] / a.steps,
                                         "fp64_after_tie": stats["exact_traced"] / a.steps,

@@ -91,12 +91,14 @@ typedef struct pemap_stats {
   uint64_t mer_positions;   /* positions copied out of mers */
   uint64_t candidates;      /* (read, locus) pairs scored */
   uint64_t sw_cells;        /* sum of nn*mm over scored candidates (pemapper.c:1705-1742 loop bounds) */
-  uint64_t tb_cells;        /* cells recomputed for the winners' tracebacks */
+  uint64_t tb_cells;        /* cells recomputed in fp64 for the winners' tracebacks */
   uint64_t replayed;        /* read-mates whose integer result had a rational tie and was re-scored in fp64 */
   double ms_seed, ms_sw, ms_select, ms_traceback, ms_total; /* CUDA-event time per stage, accumulated */
   uint64_t launches;        /* kernels launched by this library */
   uint64_t diag_traced;     /* winners whose traceback was a pure diagonal (no gap, no rational tie): no DP recompute */
   uint64_t exact_traced;    /* winners whose integer traceback met a rational tie and was redone in fp64 */
+  double ms_tb_diag, ms_tb_int, ms_tb_fp64; /* ms_traceback split: pure-diagonal pileup, integer traceback, fp64 traceback */
+  uint64_t tb_cells_int;    /* cells recomputed by the integer traceback kernel */
 } pemap_stats;
 
 typedef struct pemap_ctx pemap_t;

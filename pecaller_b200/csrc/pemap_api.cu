@@ -63,8 +63,20 @@ struct pemap_ctx {
   // chunk buffers
   int chunk = 0;       // reads (pairs) per chunk
   int stride_cap = 0;  // bytes per read row in the device buffers
-  char* d_reads[2] = {nullptr, nullptr};
-  int* d_len[2] = {nullptr, nullptr};
+  struct Slot {  // double-buffered chunk I/O: chunk c+1 is copied in while chunk c computes
+    char* d_reads[2] = {nullptr, nullptr};
+    int* d_len[2] = {nullptr, nullptr};
+    char* h_reads[2] = {nullptr, nullptr};  // pinned staging for pageable / pointer-array callers
+    int* h_len[2] = {nullptr, nullptr};
+    uint32_t *d_m1 = nullptr, *d_m2 = nullptr, *h_m1 = nullptr, *h_m2 = nullptr;
+    int *d_type = nullptr, *h_type = nullptr;
+    cudaEvent_t ev[7] = {};                 // stage boundaries of the chunk on the compute stream
+    cudaEvent_t ev_h2d = nullptr, ev_d2h = nullptr;
+    bool pending = false;
+    int n = 0, first = 0;
+    bool paired = false, direct = false;
+  } slots[2];
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   pm::Task* d_tasks = nullptr;
   pm::TaskResult* d_results = nullptr;
   uint32_t task_cap = 0;
@@ -81,9 +93,6 @@ struct pemap_ctx {
   uint32_t* d_cand_base = nullptr;
   uint32_t* d_cand_n = nullptr;
   pm::Winner* d_winners = nullptr;
-  uint32_t* d_m1 = nullptr;
-  uint32_t* d_m2 = nullptr;
-  int* d_type = nullptr;
   int32_t* d_det_best = nullptr;
   int32_t* d_det_orient = nullptr;
   double* d_det_score = nullptr;
@@ -94,15 +103,7 @@ struct pemap_ctx {
   int sw_blocks = 0;
   pm::SeedCounters* d_counters = nullptr;
 
-  // pinned staging
-  char* h_reads[2] = {nullptr, nullptr};
-  int* h_len[2] = {nullptr, nullptr};
-  uint32_t* h_m1 = nullptr;
-  uint32_t* h_m2 = nullptr;
-  int* h_type = nullptr;
-
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[6] = {};
 
   // retained from the last batch
   std::vector<pemap_detail> detail;
@@ -218,7 +219,13 @@ int open_device(pemap_ctx* h, int device) {
   cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
   cudaGetLastError();
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  for (auto& ev : h->ev) CK(cudaEventCreate(&ev));
+  CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+  for (auto& sl : h->slots) {
+    for (auto& ev : sl.ev) CK(cudaEventCreate(&ev));
+    CK(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sl.ev_d2h, cudaEventDisableTiming));
+  }
   return PEMAP_OK;
 }
 
@@ -228,15 +235,20 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   h->chunk = chunk;
   h->stride_cap = PM_DP_MAX;
   const size_t n = (size_t)chunk;
-  for (int m = 0; m < 2; m++) {
-    CK(cudaMalloc(&h->d_reads[m], n * h->stride_cap));
-    CK(cudaMalloc(&h->d_len[m], n * sizeof(int)));
-    CK(cudaHostAlloc(&h->h_reads[m], n * h->stride_cap, cudaHostAllocDefault));
-    CK(cudaHostAlloc(&h->h_len[m], n * sizeof(int), cudaHostAllocDefault));
+  for (auto& sl : h->slots) {
+    for (int m = 0; m < 2; m++) {
+      CK(cudaMalloc(&sl.d_reads[m], n * h->stride_cap));
+      CK(cudaMalloc(&sl.d_len[m], n * sizeof(int)));
+      CK(cudaHostAlloc(&sl.h_reads[m], n * h->stride_cap, cudaHostAllocDefault));
+      CK(cudaHostAlloc(&sl.h_len[m], n * sizeof(int), cudaHostAllocDefault));
+    }
+    CK(cudaHostAlloc(&sl.h_m1, n * 4, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&sl.h_m2, n * 4, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&sl.h_type, n * 4, cudaHostAllocDefault));
+    CK(cudaMalloc(&sl.d_m1, n * 4));
+    CK(cudaMalloc(&sl.d_m2, n * 4));
+    CK(cudaMalloc(&sl.d_type, n * 4));
   }
-  CK(cudaHostAlloc(&h->h_m1, n * 4, cudaHostAllocDefault));
-  CK(cudaHostAlloc(&h->h_m2, n * 4, cudaHostAllocDefault));
-  CK(cudaHostAlloc(&h->h_type, n * 4, cudaHostAllocDefault));
   h->task_cap = (uint32_t)std::min<size_t>(2 * n * PM_MAX_HITS, 0x7FFFFFFFull);
   CK(cudaMalloc(&h->d_tasks, (size_t)h->task_cap * sizeof(pm::Task)));
   CK(cudaMalloc(&h->d_results, (size_t)h->task_cap * sizeof(pm::TaskResult)));
@@ -254,9 +266,6 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   CK(cudaMalloc(&h->d_diag_winners, 2 * n * sizeof(pm::Winner)));
   CK(cudaMalloc(&h->d_exact_winners, 2 * n * sizeof(pm::Winner)));
   CK(cudaMalloc(&h->d_oob_winners, 2 * n * sizeof(pm::Winner)));
-  CK(cudaMalloc(&h->d_m1, n * 4));
-  CK(cudaMalloc(&h->d_m2, n * 4));
-  CK(cudaMalloc(&h->d_type, n * 4));
   CK(cudaMalloc(&h->d_det_best, 2 * n * 4));
   CK(cudaMalloc(&h->d_det_orient, 2 * n * 4));
   CK(cudaMalloc(&h->d_det_score, 2 * n * 8));
@@ -417,12 +426,12 @@ void dispatch_sw_int(pemap_ctx* h, pm::SwIntArgs& a, int max_len, int uniform_le
 
 // map one chunk whose reads are already in d_r1/d_r2 (device); results go to d_m1/d_m2/d_type (device)
 int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char* d_r2, const int* d_l2, int stride,
-              int max_len, int uniform_len, uint32_t* d_m1, uint32_t* d_m2, int* d_type) {
+              int max_len, int uniform_len, uint32_t* d_m1, uint32_t* d_m2, int* d_type, cudaEvent_t* ev) {
   const bool paired = h->params.pair_flag && d_r2;
   const bool exact = h->exact || (h->keep & PEMAP_KEEP_DETAIL) || h->params.match_bonus != 1.0;
   CK(cudaMemsetAsync(h->d_cursors, 0, 16, h->stream));
   CK(cudaMemsetAsync(h->d_cursors + 6, 0, 12, h->stream));
-  CK(cudaEventRecord(h->ev[0], h->stream));
+  CK(cudaEventRecord(ev[0], h->stream));
   pm::SeedArgs sa;
   sa.pos_index = h->d_pos_index;
   sa.mers = h->d_mers;
@@ -451,7 +460,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   if (h->d_filter) pm::k_seed_chain<kSeedWarps, true><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
   else pm::k_seed_chain<kSeedWarps, false><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
   h->stats.launches++;
-  CK(cudaEventRecord(h->ev[1], h->stream));
+  CK(cudaEventRecord(ev[1], h->stream));
 
   pm::SwArgs wa;
   wa.tasks = h->d_tasks;
@@ -501,7 +510,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
 
   if (exact) {  // the reference's arithmetic for every candidate
     dispatch_sw<0>(h, wa, max_len);
-    CK(cudaEventRecord(h->ev[2], h->stream));
+    CK(cudaEventRecord(ev[2], h->stream));
     pm::k_select<<<(n + 127) / 128, 128, 0, h->stream>>>(se);
     h->stats.launches++;
   } else {
@@ -519,7 +528,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     ia.lane_mm = -1;
     ia.p = sa.p;
     dispatch_sw_int(h, ia, max_len, uniform_len);
-    CK(cudaEventRecord(h->ev[2], h->stream));
+    CK(cudaEventRecord(ev[2], h->stream));
     pm::SelectIntArgs si;
     si.tasks = h->d_tasks;
     si.ires = h->d_ires;
@@ -554,7 +563,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     pm::k_select<<<(n + 127) / 128, 128, 0, h->stream>>>(se);
     h->stats.launches += 2;
   }
-  CK(cudaEventRecord(h->ev[3], h->stream));
+  CK(cudaEventRecord(ev[3], h->stream));
 
   if (!exact) {  // winners whose walk is a pure diagonal need no DP recompute
     pm::DiagArgs da;
@@ -571,6 +580,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     da.counters = h->d_counters;
     pm::k_apply_diag<<<h->sm_count * 8, 256, 0, h->stream>>>(da);
     h->stats.launches++;
+    CK(cudaEventRecord(ev[5], h->stream));
     // the other winners: integer traceback; the ones with a rational tie on their path fall through to fp64
     pm::TraceIntArgs ta;
     ta.tasks = h->d_tasks;
@@ -590,32 +600,41 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     ta.counters = h->d_counters;
     ta.p = sa.p;
     dispatch_trace_int(h, ta, max_len);
+    CK(cudaEventRecord(ev[6], h->stream));
     wa.winners = h->d_exact_winners;
     wa.n_items = h->d_cursors + 7;
   } else {
     wa.n_items = h->d_cursors + 1;
+    CK(cudaEventRecord(ev[5], h->stream));
+    CK(cudaEventRecord(ev[6], h->stream));
   }
   dispatch_sw<2>(h, wa, max_len);  // exact traceback, decision band in shared memory
   wa.winners = h->d_oob_winners;   // walks that left the band (long indels): every lane's decisions in global memory
   wa.n_items = h->d_cursors + 8;
   dispatch_sw<1>(h, wa, max_len);
-  CK(cudaEventRecord(h->ev[4], h->stream));
+  CK(cudaEventRecord(ev[4], h->stream));
   CK(cudaGetLastError());
   return PEMAP_OK;
 }
 
-int account_chunk(pemap_ctx* h, int n, bool paired) {
+int account_chunk(pemap_ctx* h, int n, bool paired, cudaEvent_t* ev) {
   float ms;
-  CK(cudaEventSynchronize(h->ev[4]));
-  CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+  CK(cudaEventSynchronize(ev[4]));
+  CK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
   h->stats.ms_seed += ms;
-  CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]));
+  CK(cudaEventElapsedTime(&ms, ev[1], ev[2]));
   h->stats.ms_sw += ms;
-  CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+  CK(cudaEventElapsedTime(&ms, ev[2], ev[3]));
   h->stats.ms_select += ms;
-  CK(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]));
+  CK(cudaEventElapsedTime(&ms, ev[3], ev[4]));
   h->stats.ms_traceback += ms;
-  CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4]));
+  CK(cudaEventElapsedTime(&ms, ev[3], ev[5]));
+  h->stats.ms_tb_diag += ms;
+  CK(cudaEventElapsedTime(&ms, ev[5], ev[6]));
+  h->stats.ms_tb_int += ms;
+  CK(cudaEventElapsedTime(&ms, ev[6], ev[4]));
+  h->stats.ms_tb_fp64 += ms;
+  CK(cudaEventElapsedTime(&ms, ev[0], ev[4]));
   h->stats.ms_total += ms;
   h->stats.reads += (uint64_t)n * (paired ? 2 : 1);
   return PEMAP_OK;
@@ -678,6 +697,7 @@ int fetch_counters(pemap_ctx* h) {
   h->stats.replayed = c.replayed;
   h->stats.diag_traced = c.diag_traced;
   h->stats.exact_traced = c.exact_traced;
+  h->stats.tb_cells_int = c.tb_cells_int;
   return PEMAP_OK;
 }
 
@@ -700,6 +720,18 @@ bool is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
+// wait for a chunk's results, hand them to the caller and book its stage times
+int finish_slot(pemap_ctx* h, pemap_ctx::Slot& sl, uint32_t* m1, uint32_t* m2, int* mapping_type) {
+  CK(cudaEventSynchronize(sl.ev_d2h));
+  if (!sl.direct) {
+    memcpy(m1 + sl.first, sl.h_m1, (size_t)sl.n * 4);
+    memcpy(m2 + sl.first, sl.h_m2, (size_t)sl.n * 4);
+    memcpy(mapping_type + sl.first, sl.h_type, (size_t)sl.n * 4);
+  }
+  sl.pending = false;
+  return account_chunk(h, sl.n, sl.paired, sl.ev);
+}
+
 // rows: reads as (n x stride) matrices on the host, or, when ptrs != nullptr, as arrays of pointers
 int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, const int* len1, const char* rows2,
              const char* const* ptr2, const int* len2, int stride, uint32_t* m1, uint32_t* m2, int* mapping_type) {
@@ -711,8 +743,15 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
   begin_batch(h, n);
   const bool direct = rows1 && is_pinned(rows1) && is_pinned(len1) && (!paired || (is_pinned(rows2) && is_pinned(len2))) &&
                       is_pinned(m1) && is_pinned(m2) && is_pinned(mapping_type);
-  for (int first = 0; first < n; first += h->chunk) {
+  const bool pipelined = h->keep == 0;  // the inspection modes read shared scratch after every chunk
+  int chunk_no = 0;
+  for (int first = 0; first < n; first += h->chunk, chunk_no++) {
     const int cn = std::min(h->chunk, n - first);
+    pemap_ctx::Slot& sl = h->slots[chunk_no & 1];
+    if (sl.pending) {  // the chunk that used this slot two iterations ago
+      int rc = finish_slot(h, sl, m1, m2, mapping_type);
+      if (rc) return rc;
+    }
     int max_len = 0, min_len = 1 << 30;
     for (int m = 0; m < (paired ? 2 : 1); m++) {
       const int* len = (m ? len2 : len1) + first;
@@ -730,7 +769,7 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
       if (dstride < 16) dstride = 16;
       for (int m = 0; m < (paired ? 2 : 1); m++) {
         const int* len = (m ? len2 : len1) + first;
-        char* dst = h->h_reads[m];
+        char* dst = sl.h_reads[m];
         if (m ? ptr2 != nullptr : ptr1 != nullptr) {
           const char* const* pp = (m ? ptr2 : ptr1) + first;
           for (int i = 0; i < cn; i++) memcpy(dst + (size_t)i * dstride, pp[i], (size_t)len[i]);
@@ -738,35 +777,47 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
           const char* rows = src_rows[m];
           for (int i = 0; i < cn; i++) memcpy(dst + (size_t)i * dstride, rows + (size_t)i * stride, (size_t)len[i]);
         }
-        memcpy(h->h_len[m], len, (size_t)cn * sizeof(int));
+        memcpy(sl.h_len[m], len, (size_t)cn * sizeof(int));
         src_rows[m] = dst;
       }
     }
     if (dstride > h->stride_cap) return fail(h, PEMAP_ERR_ARG, "row stride larger than 320 bytes");
     for (int m = 0; m < (paired ? 2 : 1); m++) {
-      const int* lsrc = (!direct || ptr1) ? h->h_len[m] : (m ? len2 : len1) + first;
-      CK(cudaMemcpyAsync(h->d_reads[m], src_rows[m], (size_t)cn * dstride, cudaMemcpyHostToDevice, h->stream));
-      CK(cudaMemcpyAsync(h->d_len[m], lsrc, (size_t)cn * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      const int* lsrc = (!direct || ptr1) ? sl.h_len[m] : (m ? len2 : len1) + first;
+      CK(cudaMemcpyAsync(sl.d_reads[m], src_rows[m], (size_t)cn * dstride, cudaMemcpyHostToDevice, h->s_h2d));
+      CK(cudaMemcpyAsync(sl.d_len[m], lsrc, (size_t)cn * sizeof(int), cudaMemcpyHostToDevice, h->s_h2d));
     }
-    int rc = run_chunk(h, cn, h->d_reads[0], h->d_len[0], paired ? h->d_reads[1] : nullptr, paired ? h->d_len[1] : nullptr,
-                       dstride, max_len, min_len == max_len ? max_len : 0, h->d_m1, h->d_m2, h->d_type);
+    CK(cudaEventRecord(sl.ev_h2d, h->s_h2d));
+    CK(cudaStreamWaitEvent(h->stream, sl.ev_h2d, 0));
+    int rc = run_chunk(h, cn, sl.d_reads[0], sl.d_len[0], paired ? sl.d_reads[1] : nullptr, paired ? sl.d_len[1] : nullptr,
+                       dstride, max_len, min_len == max_len ? max_len : 0, sl.d_m1, sl.d_m2, sl.d_type, sl.ev);
     if (rc) return rc;
-    uint32_t* o1 = direct ? m1 + first : h->h_m1;
-    uint32_t* o2 = direct ? m2 + first : h->h_m2;
-    int* ot = direct ? mapping_type + first : h->h_type;
-    CK(cudaMemcpyAsync(o1, h->d_m1, (size_t)cn * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(o2, h->d_m2, (size_t)cn * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(ot, h->d_type, (size_t)cn * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (!direct) {
-      memcpy(m1 + first, h->h_m1, (size_t)cn * 4);
-      memcpy(m2 + first, h->h_m2, (size_t)cn * 4);
-      memcpy(mapping_type + first, h->h_type, (size_t)cn * 4);
+    CK(cudaStreamWaitEvent(h->s_d2h, sl.ev[4], 0));
+    uint32_t* o1 = direct ? m1 + first : sl.h_m1;
+    uint32_t* o2 = direct ? m2 + first : sl.h_m2;
+    int* ot = direct ? mapping_type + first : sl.h_type;
+    CK(cudaMemcpyAsync(o1, sl.d_m1, (size_t)cn * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+    CK(cudaMemcpyAsync(o2, sl.d_m2, (size_t)cn * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+    CK(cudaMemcpyAsync(ot, sl.d_type, (size_t)cn * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+    CK(cudaEventRecord(sl.ev_d2h, h->s_d2h));
+    sl.pending = true;
+    sl.n = cn;
+    sl.first = first;
+    sl.paired = paired;
+    sl.direct = direct;
+    if (!pipelined) {
+      rc = finish_slot(h, sl, m1, m2, mapping_type);
+      if (rc) return rc;
+      rc = retain_chunk(h, cn, first, paired);
+      if (rc) return rc;
     }
-    rc = account_chunk(h, cn, paired);
-    if (rc) return rc;
-    rc = retain_chunk(h, cn, first, paired);
-    if (rc) return rc;
+  }
+  for (int k = 0; k < 2; k++) {  // drain in submission order
+    pemap_ctx::Slot& sl = h->slots[(chunk_no + k) & 1];
+    if (sl.pending) {
+      int rc = finish_slot(h, sl, m1, m2, mapping_type);
+      if (rc) return rc;
+    }
   }
   return PEMAP_OK;
 }
@@ -971,9 +1022,9 @@ int pemap_map_batch_device(pemap_t* h, int n, const char* d_reads1, const int* d
     const int cn = std::min(h->chunk, n - first);
     int rc = run_chunk(h, cn, d_reads1 + (size_t)first * stride, d_len1 + first,
                        paired ? d_reads2 + (size_t)first * stride : nullptr, paired ? d_len2 + first : nullptr, stride,
-                       max_len, uniform_len, d_m1 + first, d_m2 + first, d_mapping_type + first);
+                       max_len, uniform_len, d_m1 + first, d_m2 + first, d_mapping_type + first, h->slots[0].ev);
     if (rc) return rc;
-    rc = account_chunk(h, cn, paired);
+    rc = account_chunk(h, cn, paired, h->slots[0].ev);
     if (rc) return rc;
     rc = retain_chunk(h, cn, first, paired);
     if (rc) return rc;
@@ -1147,17 +1198,26 @@ void pemap_destroy(pemap_t* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* dev[] = {h->d_filter, h->d_pos_index, h->d_mers, h->d_genome, h->d_cstart, h->d_border, h->d_counts, h->d_ins, h->d_ins_cursor,
-                   h->d_reads[0], h->d_reads[1], h->d_len[0], h->d_len[1], h->d_tasks, h->d_results, h->d_cursors,
-                   h->d_cand_base, h->d_cand_n, h->d_winners, h->d_m1, h->d_m2, h->d_type, h->d_det_best, h->d_det_orient,
+                   h->d_tasks, h->d_results, h->d_cursors,
+                   h->d_cand_base, h->d_cand_n, h->d_winners, h->d_det_best, h->d_det_orient,
                    h->d_det_score, h->d_seed_scratch, h->d_dirs, h->d_pend, h->d_counters, h->d_ires, h->d_replay_reads,
                    h->d_replay_tasks, h->d_diag_winners, h->d_exact_winners, h->d_oob_winners};
     for (void* p : dev)
       if (p) cudaFree(p);
-    void* host[] = {h->h_reads[0], h->h_reads[1], h->h_len[0], h->h_len[1], h->h_m1, h->h_m2, h->h_type};
-    for (void* p : host)
-      if (p) cudaFreeHost(p);
-    for (auto& ev : h->ev)
-      if (ev) cudaEventDestroy(ev);
+    for (auto& sl : h->slots) {
+      void* dv[] = {sl.d_reads[0], sl.d_reads[1], sl.d_len[0], sl.d_len[1], sl.d_m1, sl.d_m2, sl.d_type};
+      for (void* p : dv)
+        if (p) cudaFree(p);
+      void* hv[] = {sl.h_reads[0], sl.h_reads[1], sl.h_len[0], sl.h_len[1], sl.h_m1, sl.h_m2, sl.h_type};
+      for (void* p : hv)
+        if (p) cudaFreeHost(p);
+      for (auto& ev : sl.ev)
+        if (ev) cudaEventDestroy(ev);
+      if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+      if (sl.ev_d2h) cudaEventDestroy(sl.ev_d2h);
+    }
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     cudaStreamDestroy(h->stream);
   }
   delete h;

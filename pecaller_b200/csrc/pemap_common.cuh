@@ -42,7 +42,7 @@ struct Winner {
 };
 
 struct SeedCounters {  // device-side statistics, accumulated with atomics once per warp
-  unsigned long long lookups, mer_positions, candidates, sw_cells, tb_cells, replayed, diag_traced, exact_traced;
+  unsigned long long lookups, mer_positions, candidates, sw_cells, tb_cells, replayed, diag_traced, exact_traced, tb_cells_int;
 };
 
 __host__ __device__ __forceinline__ double dmax(double a, double b) { return (a > b) ? a : b; }  // maxim(), pemapper.c:36

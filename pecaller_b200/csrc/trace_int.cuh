@@ -6,14 +6,19 @@
 //     bits 0-1  A  = argmax_k S_k[i][j], priority 0 > 1 > 2                  (consulted from state 0, 1799-1813)
 //     bit  2    X1 = S1[i][j] - ge > S0[i][j] - go                            (consulted from state 1, 1823-1831)
 //     bit  3    X2 = S2[i][j] - ge > S0[i][j] - go                            (consulted from state 2, 1814-1822)
-//     bit  4    the A decision compared equal integers   (S1 == S0, or S2 == max(S0, S1))
-//     bit  5    an X decision compared equal integers    (S1 - ge == S0 - go, or S2 - ge == S0 - go)
+//     bit  4    S1 == S0          } the A decision compared equal integers
+//     bit  5    S2 == max(S0,S1)  }
+//     A == 3    marks a cell where an X decision compared equal integers (S1 - ge == S0 - go or S2 - ge == S0 - go)
 // (layout in trace_walk.cuh).  The words of the PM_BAND_LANES lanes around the winner's end diagonal are kept in
 // shared memory, so the walk never waits on global memory.
 // The reference decides on rounded doubles with strict '>', so a comparison of rationally equal values may go
 // either way.  Lane 0 therefore walks the path twice: a dry pass that only looks for a
-// tie bit on a consulted decision or a step outside the band (then the winner is handed to the exact fp64
-// traceback kernel instead), and, if there was none, the pass that applies the pileup increments.  Every consulted comparison then has integer
+// tie on a consulted decision or a step outside the band, and, if there was none, the pass that applies the pileup
+// increments.  An A tie is first put to resolve_tie(): the two tied values are traced back in lock step, and if
+// their histories join again after nothing but exact double operations (adding +-1.0 / -2.0 without moving to a
+// higher binade) they are one double plus the same integer, i.e. EQUAL doubles, and the reference's strict '>'
+// keeps the lower state - exactly the integer argmax.  Typical case: a gap inside a homopolymer run.  Only ties
+// that cannot be certified this way hand the winner to the exact fp64 traceback kernel.  Every consulted comparison then has integer
 // operands that differ, i.e. doubles that differ by >= 1/36, and the walk is the reference's walk.
 #pragma once
 #include "pemap_common.cuh"
@@ -42,6 +47,171 @@ template <int G, int WD>
 __host__ __device__ constexpr int trace_rows() { return (G * WD + 24 < PM_DP_MAX) ? G * WD + 24 : PM_DP_MAX; }
 template <int G, int WD>
 __host__ __device__ constexpr size_t trace_band_bytes() { return (size_t)(128 / G) * trace_rows<G, WD>() * PM_BAND_LANES * 8; }
+
+// ---- exactness bookkeeping for resolve_tie ------------------------------------------------------------------
+// binade index of |x| / 36 (x in units of 1/36): number of powers of two 2^e (e >= -5) that are <= |x| / 36; 0 for x = 0
+__device__ __forceinline__ int binade36(int x) {
+  const unsigned a = (unsigned)(x < 0 ? -x : x);
+  if (a < 9u) return a >= 5u ? 4 : a >= 3u ? 3 : (int)a;  // thresholds 36 * 2^e rounded up: 1, 2, 3, 5
+  return 5 + (31 - __clz(a / 9u));                         // 9, 18, 36, 72, ...
+}
+// adding an integer-valued double (+-1.0, -2.0) to a double is exact unless the result lands in a higher binade
+__device__ __forceinline__ bool exact_step(int from36, int to36) { return binade36(to36) <= binade36(from36); }
+
+struct ChainPos {
+  int i, j, k, r;   // state k of cell (i, j) holds the rational value r / 36
+  int end;          // 0 walking, 1 ended on an exact constant (column 0), 2 ended on the row-0 border cell (0, j)
+};
+
+struct TieCtx {
+  const unsigned char* win;   // one-hot reference codes of the window rows
+  const char* read;
+  int mm, orient;
+};
+
+__device__ __forceinline__ bool cells_match(const TieCtx& t, int i, int j) {
+  const char ch = oriented_char(t.read, t.mm, t.orient, j - 1);
+  const unsigned qc = ch == 'A' ? 1u : ch == 'C' ? 2u : ch == 'G' ? 4u : ch == 'T' ? 8u : (ch == 'N' || ch == 'n') ? 15u : 0u;
+  return (qc & t.win[i - 1]) != 0u;
+}
+
+// set of states holding the maximum of a cell, from its decision bits (A != 3)
+__device__ __forceinline__ int top_set(int c) {
+  const int ak = c & 3;
+  if (ak == 2) return 4;
+  int t = 1 << ak;
+  if (c & 16) t |= 3;   // S1 == S0 (then ak == 0)
+  if (c & 32) t |= 4;   // S2 == max(S0, S1)
+  return t;
+}
+
+#define PM_TIE_LIST 12
+#define PM_TIE_BUDGET 384
+
+// One backward step of a value's history.  Returns false when the step is not an exact double operation (mismatch,
+// gap extension, binade change), leaves the band, or consults a decision that is itself undecidable here.
+// Sub-ties met on the way (a predecessor cell whose maximum is shared) are appended to the work list.
+template <class Cell>
+__device__ __forceinline__ bool chain_step(const Cell& cell, const TieCtx& t, ChainPos& p, int* wl_i, int* wl_j, int& wl_n) {
+  if (p.j == 0) { p.end = 1; return true; }             // S0[i][0] = S1[i][0] = 0, S2[i][0] = -go: exact constants
+  if (p.i == 0) { p.end = 2; return true; }             // S*[0][j] = -(go + (j-1) ge): one rounded constant per column
+  if (p.k == 0) {
+    if (!cells_match(t, p.i, p.j)) return false;        // + (-1/3): rounds
+    const int prev = p.r - 36;
+    if (!exact_step(prev, p.r)) return false;
+    p.i--; p.j--; p.r = prev;
+    if (p.i == 0 || p.j == 0) { p.k = 0; return true; } // M of a border cell: every state there is handled above
+    const int c = cell(p.i, p.j);
+    if (c < 0 || (c & 3) == 3) return false;
+    const int ts = top_set(c);
+    if (ts & (ts - 1)) {                                // shared maximum: certify it later
+      bool seen = false;
+      for (int q = 0; q < wl_n; q++) seen |= (wl_i[q] == p.i && wl_j[q] == p.j);
+      if (!seen) {
+        if (wl_n >= PM_TIE_LIST) return false;
+        wl_i[wl_n] = p.i; wl_j[wl_n] = p.j; wl_n++;
+      }
+    }
+    p.k = c & 3;
+    return true;
+  }
+  // gap states: S1[i][j] = max(S0[i-1][j] - go, S1[i-1][j] - ge), S2[i][j] = max(S0[i][j-1] - go, S2[i][j-1] - ge)
+  const int pi = p.k == 1 ? p.i - 1 : p.i, pj = p.k == 1 ? p.j : p.j - 1;
+  if (pi == 0 || pj == 0) {
+    // from a border cell: opening from S0 = 0 (column 0) is exact; everything else involves a rounded value
+    if (p.k == 2 && pj == 0) {                          // S2[i][1] = max(0 - go, -go - ge) = -go, exact
+      p.i = pi; p.j = pj; p.k = 0; p.r += 72;
+      return true;
+    }
+    return false;
+  }
+  const int c = cell(pi, pj);
+  if (c < 0 || (c & 3) == 3) return false;
+  if (c & (p.k == 1 ? 4 : 8)) return false;             // extension: - 1/36 rounds
+  const int prev = p.r + 72;
+  if (!exact_step(prev, p.r)) return false;
+  p.i = pi; p.j = pj; p.k = 0; p.r = prev;
+  return true;
+}
+
+// Are the doubles of states a and b of cell (i, j), both of rational value r36 / 36, provably equal?
+template <class Cell>
+__device__ bool resolve_tie(const Cell& cell, const TieCtx& t, int i, int j, int r36) {
+  int wl_i[PM_TIE_LIST], wl_j[PM_TIE_LIST], wl_r[PM_TIE_LIST];
+  int wl_n = 1, budget = PM_TIE_BUDGET;
+  wl_i[0] = i; wl_j[0] = j; wl_r[0] = r36;
+  for (int w = 0; w < wl_n; w++) {
+    const int c = cell(wl_i[w], wl_j[w]);
+    if (c < 0 || (c & 3) == 3) return false;
+    const int ts = top_set(c);
+    const int first = __ffs(ts) - 1;
+    // every other state of the top set against the lowest one
+    for (int other = first + 1; other < 3; other++) {
+      if (!(ts & (1 << other))) continue;
+      ChainPos A, B;
+      A.i = B.i = wl_i[w]; A.j = B.j = wl_j[w]; A.r = B.r = wl_r[w];
+      A.k = first; B.k = other; A.end = B.end = 0;
+      for (;;) {
+        if (A.end && B.end) {
+          // two exact constants, or the same row-0 border cell
+          if (A.end == 1 && B.end == 1) break;
+          if (A.end == 2 && B.end == 2 && A.j == B.j) break;
+          return false;
+        }
+        if (!A.end && !B.end && A.i == B.i && A.j == B.j && A.k == B.k) break;  // the histories joined
+        if (--budget < 0) return false;
+        // advance the one farther from the origin (the only one that can still reach the other)
+        const bool stepA = !A.end && (B.end || A.i + A.j > B.i + B.j || (A.i + A.j == B.i + B.j && A.i >= B.i));
+        ChainPos& p = stepA ? A : B;
+        const int n0 = wl_n;
+        if (!chain_step(cell, t, p, wl_i, wl_j, wl_n)) return false;
+        if (wl_n > n0) wl_r[n0] = p.r;                 // value of the shared maximum just queued
+        if (A.end == 1 && B.end == 1) break;
+      }
+    }
+  }
+  return true;
+}
+
+// dry walk of the integer kernel: like walk_path<false> but tracks the rational value along the path so that A ties
+// can be put to resolve_tie()
+template <class Cell>
+__device__ int walk_check_int(const Cell& cell, const TieCtx& t, int k, int i, int j, int r36) {
+  while (i > 0 && j > 0) {
+    int pi, pj, pk = 0;
+    if (k == 0) {
+      pi = i - 1; pj = j - 1;
+      r36 -= cells_match(t, i, j) ? 36 : -12;          // value of M[i-1][j-1]
+      if (pi > 0 && pj > 0) {
+        const int c = cell(pi, pj);
+        if (c < 0) return PM_WALK_OOB;
+        if ((c & 3) == 3) return PM_WALK_TIE;
+        if ((c & 48) && (top_set(c) & (top_set(c) - 1)) && !resolve_tie(cell, t, pi, pj, r36)) return PM_WALK_TIE;
+        pk = c & 3;
+      }
+    } else if (k == 2) {
+      pi = i; pj = j - 1;
+      if (pj > 0) {
+        const int c = cell(pi, pj);
+        if (c < 0) return PM_WALK_OOB;
+        if ((c & 3) == 3) return PM_WALK_TIE;
+        pk = (c & 8) ? 2 : 0;
+      }
+      r36 += pk == 2 ? 1 : 72;
+    } else {
+      pi = i - 1; pj = j;
+      if (pi > 0) {
+        const int c = cell(pi, pj);
+        if (c < 0) return PM_WALK_OOB;
+        if ((c & 3) == 3) return PM_WALK_TIE;
+        pk = (c & 4) ? 1 : 0;
+      }
+      r36 += pk == 1 ? 1 : 72;
+    }
+    i = pi; j = pj; k = pk;
+  }
+  return PM_WALK_OK;
+}
 
 template <int G, int WD>
 __global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
@@ -125,10 +295,10 @@ __global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
           diag = mu[c];
           const int m01 = max(s0, s1);
           const int m = max(m01, s2);
-          const unsigned ak = (s2 > m01) ? 2u : (s1 > s0) ? 1u : 0u;
           const int opn = s0 - 72;
-          const unsigned bits = ak | ((s1 - 1 > opn) ? 4u : 0u) | ((s2 - 1 > opn) ? 8u : 0u) |
-                                ((s1 == s0 || s2 == m01) ? 16u : 0u) | ((s1 - 1 == opn || s2 - 1 == opn) ? 32u : 0u);
+          const unsigned ak = (s1 - 1 == opn || s2 - 1 == opn) ? 3u : (s2 > m01) ? 2u : (s1 > s0) ? 1u : 0u;
+          const unsigned bits = ak | ((s1 - 1 > opn) ? 4u : 0u) | ((s2 - 1 > opn) ? 8u : 0u) | ((s1 == s0) ? 16u : 0u) |
+                                ((s2 == m01) ? 32u : 0u);
           dword |= (unsigned long long)bits << (6 * c);
           s0u[c] = s0;
           s1u[c] = s1;
@@ -150,10 +320,16 @@ __global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
       cell.band = band;
       cell.dend = dend;
       cell.half = a.band_half;
-      int rc = bad ? PM_WALK_TIE : walk_path<false, 1>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink);
+      TieCtx tc;
+      tc.win = win;
+      tc.read = read;
+      tc.mm = mm;
+      tc.orient = orient;
+      const int r36 = (int)lrint(res.score * 36.0);
+      int rc = bad ? PM_WALK_TIE : walk_check_int(cell, tc, res.maxk, res.maxi, mm, r36);
+      atomicAdd(&a.counters->tb_cells_int, (unsigned long long)nn * (unsigned long long)mm);
       if (rc == PM_WALK_OK) {
         walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink);
-        atomicAdd(&a.counters->tb_cells, (unsigned long long)nn * (unsigned long long)mm);
       } else {
         const uint32_t w = atomicAdd(a.exact_cursor, 1u);
         a.exact_winners[w] = a.winners[item];

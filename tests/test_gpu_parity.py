@@ -193,6 +193,64 @@ def test_traceback_band_handover(get_fixture, oracle_built, monkeypatch):
     oracle.close()
 
 
+def _two_gpu_worker(rank, world, port, out_path):
+    import os
+    import torch
+    import torch.distributed as dist
+    import fixtures_def
+    from pecaller_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    fx = fixtures_def.FIXTURES["pe150"]()
+    run = fx.runs[0]
+    n = 30000
+    kw = dict(min_align=run.min_align, pair_flag=1, min_dist=run.min_dist, max_dist=run.max_dist)
+    mapper = pb.PEMapper.from_genome(fx.genome, device=rank)
+    mapper.set_params(**kw)
+    ranges = sharding.shard_batches(n, rank, world, 4096)
+    parts = [mapper.map_batch(run.reads1[a:b], run.reads2[a:b]) for a, b in ranges]
+    m1, m2, ty = (np.concatenate([p[k] for p in parts]) for k in range(3))
+    sharding.reduce_counts(sharding.counts_tensor(mapper, torch.device("cuda", rank)), dst=0)
+    torch.cuda.synchronize()
+    res = sharding.gather_results(n, ranges, m1, m2, ty, dst=0)
+    rec, ins = mapper.finish()
+    all_ins = [None] * world
+    dist.all_gather_object(all_ins, ins)
+    if rank == 0:
+        np.savez(out_path, rec=rec, m1=res[0], m2=res[1], ty=res[2])
+        import pickle
+        pickle.dump(sorted(sum(all_ins, [])), open(out_path + ".ins", "wb"))
+    mapper.close()
+    dist.destroy_process_group()
+
+
+def test_two_gpus_equal_one(get_fixture, tmp_path):
+    """Reads sharded over 2 GPUs + one NCCL sum of the counter arrays == 1 GPU, byte for byte."""
+    import pickle
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "two.npz")
+    mp.spawn(_two_gpu_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    fx = get_fixture("pe150")
+    run = fx.runs[0]
+    n = 30000
+    mapper = pb.PEMapper.from_genome(fx.genome)
+    mapper.set_params(min_align=run.min_align, pair_flag=1, min_dist=run.min_dist, max_dist=run.max_dist)
+    m1, m2, ty = mapper.map_batch(run.reads1[:n], run.reads2[:n])
+    rec, ins = mapper.finish()
+    mapper.close()
+    assert np.array_equal(got["m1"], m1) and np.array_equal(got["m2"], m2) and np.array_equal(got["ty"], ty)
+    assert got["rec"].tobytes() == rec.tobytes()
+    assert pickle.load(open(out + ".ins", "rb")) == sorted(ins)
+
+
 def test_contig_count_quirk_is_refused():
     """2..7 contigs: find_chrom reads out of bounds in the reference; we refuse instead of guessing."""
     from pecaller_b200 import synth
