@@ -89,6 +89,7 @@ struct pemap_ctx {
   uint32_t* d_replay_reads = nullptr;
   pm::Winner* d_replay_tasks = nullptr;
   int band_half = PM_BAND_LANES / 2;  // PEMAP_BAND_HALF=0/1 narrows the traceback band (tests of the hand-over path)
+  int trace32 = 0;
   int exact = 0;  // 1: fp64 kernels for everything (PEMAP_EXACT=1, PEMAP_KEEP_DETAIL, match_bonus != 1)
   uint32_t* d_cand_base = nullptr;
   uint32_t* d_cand_n = nullptr;
@@ -257,6 +258,7 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   CK(cudaMalloc(&h->d_replay_reads, n * 4));
   CK(cudaMalloc(&h->d_replay_tasks, (size_t)h->task_cap * sizeof(pm::Winner)));
   if (const char* s = getenv("PEMAP_EXACT")) h->exact = atoi(s) != 0;
+  if (const char* s = getenv("PEMAP_TRACE32")) h->trace32 = atoi(s) != 0;
   if (const char* s = getenv("PEMAP_BAND_HALF")) h->band_half = std::min(PM_BAND_LANES / 2, std::max(0, atoi(s)));
   CK(cudaMalloc(&h->d_cand_base, 2 * n * 4));
   CK(cudaMalloc(&h->d_cand_n, 2 * n * 4));
@@ -275,7 +277,7 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   const size_t max_groups = (size_t)h->sw_blocks * (128 / 16);
   // trace scratch: groups * G == sw_blocks * 128 lanes for every instantiation, PM_DP_MAX rows of one word per lane
   CK(cudaMalloc(&h->d_dirs, (size_t)h->sw_blocks * 128 * PM_DP_MAX * sizeof(unsigned long long)));
-  CK(cudaMalloc(&h->d_pend, max_groups * PM_DP_MAX));
+  CK(cudaMalloc(&h->d_pend, 2 * max_groups * PM_DP_MAX));
   CK(cudaMalloc(&h->d_counters, sizeof(pm::SeedCounters)));
   CK(cudaMemset(h->d_counters, 0, sizeof(pm::SeedCounters)));
   if (const char* s = getenv("PEMAP_INS_MB")) h->ins_cap = (uint64_t)std::max(1, atoi(s)) << 20;
@@ -383,13 +385,23 @@ void dispatch_sw(pemap_ctx* h, const pm::SwArgs& a, int max_len) {
 
 template <int G, int WD>
 void launch_trace_int(pemap_ctx* h, const pm::TraceIntArgs& a) {
-  const size_t dyn = pm::trace_band_bytes<G, WD>();
-  static bool once = false;
-  if (!once) {
-    cudaFuncSetAttribute(pm::k_trace_i32<G, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    once = true;
+  if (h->trace32) {  // one winner per sub-warp, 32-bit integers (PEMAP_TRACE32=1; kept as a cross-check)
+    const size_t dyn = pm::trace_band_bytes<G, WD>();
+    static bool once = false;
+    if (!once) {
+      cudaFuncSetAttribute(pm::k_trace_i32<G, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      once = true;
+    }
+    pm::k_trace_i32<G, WD><<<h->sw_blocks, 128, dyn, h->stream>>>(a);
+    return;
   }
-  pm::k_trace_i32<G, WD><<<h->sw_blocks, 128, dyn, h->stream>>>(a);
+  const size_t dyn = pm::trace16_band_bytes<G, WD>();
+  static bool once16 = false;
+  if (!once16) {
+    cudaFuncSetAttribute(pm::k_trace_i16<G, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    once16 = true;
+  }
+  pm::k_trace_i16<G, WD><<<h->sw_blocks, 128, dyn, h->stream>>>(a);
 }
 
 void dispatch_trace_int(pemap_ctx* h, const pm::TraceIntArgs& a, int max_len) {

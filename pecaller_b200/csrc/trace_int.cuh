@@ -64,7 +64,8 @@ struct ChainPos {
 };
 
 struct TieCtx {
-  const unsigned char* win;   // one-hot reference codes of the window rows
+  const unsigned char* win;   // one-hot reference codes of the window rows, win_stride bytes apart
+  int win_stride;
   const char* read;
   int mm, orient;
 };
@@ -72,7 +73,7 @@ struct TieCtx {
 __device__ __forceinline__ bool cells_match(const TieCtx& t, int i, int j) {
   const char ch = oriented_char(t.read, t.mm, t.orient, j - 1);
   const unsigned qc = ch == 'A' ? 1u : ch == 'C' ? 2u : ch == 'G' ? 4u : ch == 'T' ? 8u : (ch == 'N' || ch == 'n') ? 15u : 0u;
-  return (qc & t.win[i - 1]) != 0u;
+  return (qc & t.win[(i - 1) * t.win_stride]) != 0u;
 }
 
 // set of states holding the maximum of a cell, from its decision bits (A != 3)
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
       cell.half = a.band_half;
       TieCtx tc;
       tc.win = win;
+      tc.win_stride = 1;
       tc.read = read;
       tc.mm = mm;
       tc.orient = orient;
@@ -333,6 +335,209 @@ __global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
       } else {
         const uint32_t w = atomicAdd(a.exact_cursor, 1u);
         a.exact_winners[w] = a.winners[item];
+        atomicAdd(&a.counters->exact_traced, 1ull);
+      }
+    }
+    __syncwarp(gmask);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_trace_i16: the same traceback with TWO winners packed per lane (s16x2, biased by PM_TBIAS like sw_int16.cuh)
+// and the decision flags extracted with SWAR compares: for halves a, b in [0, 2^15), (a + 0x8000 - b) has bit 15
+// set iff a >= b, and neither half borrows from the other.  Six flag words are accumulated per lane and row,
+// one bit per cell and half:
+//     F0  S1 > S0 (or X tie)      F1  S2 > max(S0,S1)     F2  X1     F3  X2
+//     F4  S1 == S0 (or X tie)     F5  S2 == max(S0,S1)
+// (F0 and F4 both set cannot happen otherwise and marks the cell like A == 3 above.)  Only the PM_BAND16_LANES
+// lanes around the two winners' end diagonals keep their words, in shared memory; lane 0 walks the first winner
+// and lane 1 the second, with the same walker and tie certification as k_trace_i32.
+// ---------------------------------------------------------------------------------------------------
+#define PM_TBIAS 1024
+#define PM_BAND16_LANES 3
+
+template <int G, int WD>
+__host__ __device__ constexpr size_t trace16_band_bytes() {
+  return (size_t)(128 / G) * trace_rows<G, WD>() * PM_BAND16_LANES * 6 * 4;
+}
+
+template <int WD>
+struct PackedBandCell {
+  const uint32_t* band;  // [rows][PM_BAND16_LANES][6]
+  int dmid, half, hi;    // hi: 0 = low halves (first winner), 1 = high halves
+  __device__ __forceinline__ int operator()(int pi, int pj) const {
+    const int l = (pj - 1) / WD, c = (pj - 1) - l * WD;
+    const int slot = l - (band_center_lane<WD>(pi, dmid) - half);
+    if (slot < 0 || slot > 2 * half) return -1;
+    const uint32_t* w = band + ((pi - 1) * PM_BAND16_LANES + slot) * 6;
+    const int bit = 16 - WD + c + 16 * hi;
+    const uint2 w01 = *reinterpret_cast<const uint2*>(w), w23 = *reinterpret_cast<const uint2*>(w + 2),
+                w45 = *reinterpret_cast<const uint2*>(w + 4);
+    const int f0 = (w01.x >> bit) & 1, f1 = (w01.y >> bit) & 1, f2 = (w23.x >> bit) & 1, f3 = (w23.y >> bit) & 1,
+              f4 = (w45.x >> bit) & 1, f5 = (w45.y >> bit) & 1;
+    if (f0 & f4) return 3;  // an X decision compared equal integers: undecidable here
+    return (f1 ? 2 : f0) | (f2 << 2) | (f3 << 3) | (f4 << 4) | (f5 << 5);
+  }
+};
+
+template <int G, int WD>
+__global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
+  constexpr int GPB = 128 / G;
+  constexpr int ROWS = trace_rows<G, WD>();
+  extern __shared__ uint32_t s_band16[];  // [GPB][ROWS][PM_BAND16_LANES][6]
+  __shared__ uint32_t s_win[GPB][ROWS];   // packed one-hot window codes (low half first winner, high half second)
+  const int tid = threadIdx.x, grp = tid / G, gl = tid % G;
+  const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) / G * G));
+  const uint32_t n_items = *a.n_items, n_pairs = (n_items + 1) >> 1;
+  const uint32_t ggid = blockIdx.x * GPB + grp, n_groups = gridDim.x * GPB;
+  uint32_t* win = s_win[grp];
+  uint32_t* band = s_band16 + (size_t)grp * ROWS * PM_BAND16_LANES * 6;
+  const int bis = a.p.is_bisulfite;
+  const int half = a.band_half < PM_BAND16_LANES / 2 ? a.band_half : PM_BAND16_LANES / 2;
+  constexpr uint32_t K1 = 0x00010001u, K12 = 0x000C000Cu, NEG72 = 0xFFB8FFB8u, H = 0x80008000u;
+  constexpr uint32_t BIASP = (PM_TBIAS << 16) | PM_TBIAS;
+  constexpr uint32_t HX = H + 70u * K1;  // x = S + 70 >= S0  <=>  S - ge > S0 - go
+  PileSink sink = a.sink;
+  sink.pend = a.sink.pend + ((size_t)ggid * 2 + (gl & 1)) * PM_DP_MAX;  // lanes 0 and 1 walk concurrently
+
+  for (uint32_t pair = ggid; pair < n_pairs; pair += n_groups) {
+    const uint32_t itA = 2 * pair, itB = (2 * pair + 1 < n_items) ? 2 * pair + 1 : 2 * pair;
+    const uint32_t idA = a.winners[itA].task, idB = a.winners[itB].task;
+    const Task tA = a.tasks[idA], tB = a.tasks[idB];
+    const TaskResult rA = a.results[idA], rB = a.results[idB];
+    const int orA = (int)(tA.rm >> 31), orB = (int)(tB.rm >> 31);
+    const uint32_t rmA = tA.rm & 0x7FFFFFFFu, rmB = tB.rm & 0x7FFFFFFFu;
+    const int mmA = ((rmA & 1u) ? a.len[1] : a.len[0])[rmA >> 1], mmB = ((rmB & 1u) ? a.len[1] : a.len[0])[rmB >> 1];
+    const char* readA = ((rmA & 1u) ? a.reads[1] : a.reads[0]) + (size_t)(rmA >> 1) * a.stride;
+    const char* readB = ((rmB & 1u) ? a.reads[1] : a.reads[0]) + (size_t)(rmB >> 1) * a.stride;
+    const int nnA = rA.maxi < tA.blen ? rA.maxi : tA.blen, nnB = rB.maxi < tB.blen ? rB.maxi : tB.blen;
+    const int nn = nnA > nnB ? nnA : nnB;
+    const int dmid = ((rA.maxi - mmA) + (rB.maxi - mmB)) >> 1;  // one band for both winners
+
+    __syncwarp(gmask);
+    bool badA = false, badB = false;
+    for (int i = gl; i < nn; i += G) {
+      uint32_t cA = 0, cB = 0;
+      if (i < nnA) {
+        const char ch = a.genome[(size_t)tA.wstart + i];
+        cA = ch == 'A' ? 1u : ch == 'C' ? (bis ? 10u : 2u) : ch == 'G' ? 4u : ch == 'T' ? 8u : (ch == 'N' || ch == 'n') ? 15u : 0u;
+        badA |= (cA == 0u);
+      }
+      if (i < nnB) {
+        const char ch = a.genome[(size_t)tB.wstart + i];
+        cB = ch == 'A' ? 1u : ch == 'C' ? (bis ? 10u : 2u) : ch == 'G' ? 4u : ch == 'T' ? 8u : (ch == 'N' || ch == 'n') ? 15u : 0u;
+        badB |= (cB == 0u);
+      }
+      win[i] = cA | (cB << 16);
+    }
+    uint32_t q[WD], s0u[WD], s1u[WD], mu[WD];
+    const int jbase = gl * WD;
+#pragma unroll
+    for (int c = 0; c < WD; c++) {
+      const int j0 = jbase + c;
+      uint32_t cA = 0, cB = 0;
+      if (j0 < mmA) {
+        const char ch = oriented_char(readA, mmA, orA, j0);
+        cA = ch == 'A' ? 1u : ch == 'C' ? 2u : ch == 'G' ? 4u : ch == 'T' ? 8u : (ch == 'N' || ch == 'n') ? 15u : 0u;
+        badA |= (cA == 0u);
+      }
+      if (j0 < mmB) {
+        const char ch = oriented_char(readB, mmB, orB, j0);
+        cB = ch == 'A' ? 1u : ch == 'C' ? 2u : ch == 'G' ? 4u : ch == 'T' ? 8u : (ch == 'N' || ch == 'n') ? 15u : 0u;
+        badB |= (cB == 0u);
+      }
+      q[c] = cA | (cB << 16);
+      const uint32_t b = (uint32_t)(PM_TBIAS - 72 - j0);  // S*[0][j] = -(72 + j - 1), j = j0 + 1 (2073-2081)
+      s0u[c] = b | (b << 16);
+      s1u[c] = s0u[c];
+      mu[c] = s0u[c] - K12;  // mu holds max(S0,S1,S2) - 12
+    }
+    badA = __any_sync(gmask, badA);
+    badB = __any_sync(gmask, badB);
+    uint32_t out_s0 = 0, out_s2 = 0, out_m = 0;
+    __syncwarp(gmask);
+
+    const int steps = nn > 0 ? nn + G - 1 : 0;
+    for (int s = 0; s < steps; s++) {
+      uint32_t l_s0 = __shfl_up_sync(gmask, out_s0, 1, G);
+      uint32_t l_s2 = __shfl_up_sync(gmask, out_s2, 1, G);
+      uint32_t diag = __shfl_up_sync(gmask, out_m, 1, G);
+      if (gl == 0) {  // column 0: S0 = 0, S2 = -72, M(row above) - 12 = -12 (2062-2081)
+        l_s0 = BIASP;
+        l_s2 = BIASP - 0x00480048u;
+        diag = BIASP - K12;
+      }
+      const int i = s - gl + 1;
+      if (i >= 1 && i <= nn) {
+        const uint32_t rc = win[i - 1];
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+#pragma unroll
+        for (int c = 0; c < WD; c++) {
+          const uint32_t s2 = __viaddmax_s16x2(l_s0, NEG72, l_s2 - K1);      // 1710 / 1720
+          const uint32_t s1 = __viaddmax_s16x2(s0u[c], NEG72, s1u[c] - K1);  // 1711 / 1721
+          const uint32_t m01 = __vminu2(q[c] & rc, K1);                      // 1 where the bases match
+          const uint32_t s0 = m01 * 48u + diag;                              // (M - 12) + 48 or + 0
+          diag = mu[c];
+          const uint32_t x01 = __vmaxs2(s0, s1);
+          const uint32_t m = __vmaxs2(x01, s2);
+          // SWAR decisions, bit 15 of each half
+          const uint32_t g = s0 + H - s1, g2 = s1 + H - s0;                  // S0 >= S1, S1 >= S0
+          const uint32_t hh = x01 + H - s2, h2 = s2 + H - x01;               // max01 >= S2, S2 >= max01
+          const uint32_t w1 = s1 + HX - s0, w2 = s2 + HX - s0;               // X1, X2
+          const uint32_t tx = ((w1 + K1) & ~w1) | ((w2 + K1) & ~w2);         // S1 + 71 == S0 or S2 + 71 == S0
+          a0 = (a0 >> 1) | ((~g | tx) & H);
+          a1 = (a1 >> 1) | (~hh & H);
+          a2 = (a2 >> 1) | (w1 & H);
+          a3 = (a3 >> 1) | (w2 & H);
+          a4 = (a4 >> 1) | (((g & g2) | tx) & H);
+          a5 = (a5 >> 1) | (hh & h2 & H);
+          s0u[c] = s0;
+          s1u[c] = s1;
+          mu[c] = m - K12;
+          l_s0 = s0;
+          l_s2 = s2;
+        }
+        out_s0 = l_s0;
+        out_s2 = l_s2;
+        out_m = diag;
+        const int slot = gl - (band_center_lane<WD>(i, dmid) - half);
+        if (slot >= 0 && slot <= 2 * half) {
+          uint32_t* w = band + ((i - 1) * PM_BAND16_LANES + slot) * 6;
+          *reinterpret_cast<uint2*>(w) = make_uint2(a0, a1);
+          *reinterpret_cast<uint2*>(w + 2) = make_uint2(a2, a3);
+          *reinterpret_cast<uint2*>(w + 4) = make_uint2(a4, a5);
+        }
+      }
+    }
+    __syncwarp(gmask);
+
+    if (gl < 2 && nn > 0 && (gl == 0 || itB != itA)) {
+      const bool second = gl == 1;
+      const Task& tk = second ? tB : tA;
+      const TaskResult& res = second ? rB : rA;
+      const char* read = second ? readB : readA;
+      const int mm = second ? mmB : mmA, orient = second ? orB : orA, nnw = second ? nnB : nnA;
+      const bool bad = second ? badB : badA;
+      PackedBandCell<WD> cell;
+      cell.band = band;
+      cell.dmid = dmid;
+      cell.half = half;
+      cell.hi = second ? 1 : 0;
+      // the tie certification reads one-hot window codes: give it this winner's half through a byte view
+      TieCtx tc;
+      tc.win = reinterpret_cast<const unsigned char*>(win) + (second ? 2 : 0);
+      tc.win_stride = 4;
+      tc.read = read;
+      tc.mm = mm;
+      tc.orient = orient;
+      const int r36 = (int)lrint(res.score * 36.0);
+      int rc = (bad || nnw <= 0) ? PM_WALK_TIE : walk_check_int(cell, tc, res.maxk, res.maxi, mm, r36);
+      atomicAdd(&a.counters->tb_cells_int, (unsigned long long)nnw * (unsigned long long)mm);
+      if (rc == PM_WALK_OK) {
+        walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink);
+      } else {
+        const uint32_t w = atomicAdd(a.exact_cursor, 1u);
+        a.exact_winners[w] = a.winners[second ? itB : itA];
         atomicAdd(&a.counters->exact_traced, 1ull);
       }
     }
