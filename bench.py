@@ -361,7 +361,7 @@ def main():
                              "kernel gets past that" % (ap_.get("random_gather_glookups_s", 41.7),
                                                         8 * ap_.get("random_gather_glookups_s", 41.7))}
         roof_sw = alu_roof("k_sw_i16 (s16x2 DPX scoring of every candidate)", per_step["sw_cells"], sw_s, pk16)
-        roof_tbi = alu_roof("k_trace_i32 (integer traceback of gapped winners)", per_step["tb_cells_int"], tbi_s, pk32)
+        roof_tbi = alu_roof("k_trace_i16 (s16x2 integer traceback of gapped winners)", per_step["tb_cells_int"], tbi_s, pk16)
         roof_tbf = alu_roof("k_sw_fp64 (exact traceback after a rational tie)", per_step["tb_cells"], tbf_s, pk64)
         dominant = max((roof_seed, roof_sw, roof_tbi, roof_tbf), key=lambda r: r["ms_per_step"])
         tr = os.path.join(ROOT, "profiles", "traffic.json")

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
   constexpr int ROWS = (G * WD + 24 < PM_DP_MAX) ? G * WD + 24 : PM_DP_MAX;
   extern __shared__ unsigned long long s_band_d[];  // MODE 2: [GROUPS_PER_BLOCK][ROWS][PM_BAND_LANES]
   __shared__ char s_win[GROUPS_PER_BLOCK][PM_DP_MAX];
+  __shared__ unsigned char s_q[TRACE ? GROUPS_PER_BLOCK : 1][TRACE ? PM_DP_MAX : 1];  // one-hot codes of the oriented read
   const int tid = threadIdx.x;
   const int grp = tid / G, gl = tid % G;
   const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) / G * G));
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
     for (int c = 0; c < WD; c++) {
       int j0 = jbase + c;
       q[c] = (j0 < mm) ? seq_char(read, mm, orient, j0) : (char)0;
+      if (TRACE && j0 < PM_DP_MAX) s_q[grp][j0] = (unsigned char)base_onehot(q[c]);
     }
     // row 0 (init_penalty_matrices 2073-2081): S0 = S1 = S2 = M = border[j]
     double s0u[WD], s1u[WD], mu[WD];
@@ -173,15 +175,15 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
         if (MODE == 1) {
           FullCell<G, WD, 4> cell;
           cell.dirs = dirs;
-          walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink);
+          walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink, s_q[grp], 0);
           atomicAdd(&a.counters->tb_cells, (unsigned long long)nn * (unsigned long long)mm);
         } else {
           BandCell<WD, 4> cell;
           cell.band = band;
           cell.dend = dend;
           cell.half = a.band_half;
-          if (walk_path<false, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink) == PM_WALK_OK) {
-            walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink);
+          if (walk_path<false, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink, s_q[grp], 0) == PM_WALK_OK) {
+            walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink, s_q[grp], 0);
             atomicAdd(&a.counters->tb_cells, (unsigned long long)nn * (unsigned long long)mm);
           } else {
             const uint32_t w = atomicAdd(a.oob_cursor, 1u);

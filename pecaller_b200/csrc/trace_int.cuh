@@ -64,16 +64,13 @@ struct ChainPos {
 };
 
 struct TieCtx {
-  const unsigned char* win;   // one-hot reference codes of the window rows, win_stride bytes apart
-  int win_stride;
-  const char* read;
-  int mm, orient;
+  const unsigned char* win;    // one-hot reference codes of the window rows (shared memory), one byte per row
+  const unsigned char* qcode;  // one-hot codes of the oriented read (shared memory), one byte per column
+  int shift;                   // the winner's code sits in bits shift..shift+3 of each byte
 };
 
 __device__ __forceinline__ bool cells_match(const TieCtx& t, int i, int j) {
-  const char ch = oriented_char(t.read, t.mm, t.orient, j - 1);
-  const unsigned qc = ch == 'A' ? 1u : ch == 'C' ? 2u : ch == 'G' ? 4u : ch == 'T' ? 8u : (ch == 'N' || ch == 'n') ? 15u : 0u;
-  return (qc & t.win[(i - 1) * t.win_stride]) != 0u;
+  return (((unsigned)t.qcode[j - 1] & (unsigned)t.win[i - 1]) >> t.shift & 15u) != 0u;
 }
 
 // set of states holding the maximum of a cell, from its decision bits (A != 3)
@@ -221,6 +218,7 @@ __global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
   constexpr int ROWS = trace_rows<G, WD>();
   extern __shared__ unsigned long long s_band_i[];  // [GPB][ROWS][PM_BAND_LANES]
   __shared__ unsigned char s_win[GPB][ROWS];
+  __shared__ unsigned char s_q[GPB][ROWS];          // one-hot codes of the oriented read (columns <= G * WD <= ROWS)
   const int tid = threadIdx.x, grp = tid / G, gl = tid % G;
   const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) / G * G));
   const uint32_t n_items = *a.n_items;
@@ -265,6 +263,7 @@ __global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
         bad |= (qc == 0u);
       }
       q[c] = qc;
+      s_q[grp][j0] = (unsigned char)qc;
       const int b = -(72 + j0);  // S*[0][j] = -(go + (j-1) ge), j = j0 + 1 (2073-2081)
       s0u[c] = b;
       s1u[c] = b;
@@ -323,15 +322,13 @@ __global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
       cell.half = a.band_half;
       TieCtx tc;
       tc.win = win;
-      tc.win_stride = 1;
-      tc.read = read;
-      tc.mm = mm;
-      tc.orient = orient;
+      tc.qcode = s_q[grp];
+      tc.shift = 0;
       const int r36 = (int)lrint(res.score * 36.0);
       int rc = bad ? PM_WALK_TIE : walk_check_int(cell, tc, res.maxk, res.maxi, mm, r36);
       atomicAdd(&a.counters->tb_cells_int, (unsigned long long)nn * (unsigned long long)mm);
       if (rc == PM_WALK_OK) {
-        walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink);
+        walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink, s_q[grp], 0);
       } else {
         const uint32_t w = atomicAdd(a.exact_cursor, 1u);
         a.exact_winners[w] = a.winners[item];
@@ -385,12 +382,13 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
   constexpr int GPB = 128 / G;
   constexpr int ROWS = trace_rows<G, WD>();
   extern __shared__ uint32_t s_band16[];  // [GPB][ROWS][PM_BAND16_LANES][6]
-  __shared__ uint32_t s_win[GPB][ROWS];   // packed one-hot window codes (low half first winner, high half second)
+  __shared__ unsigned char s_win[GPB][ROWS];  // one-hot window codes: low nibble first winner, high nibble second
+  __shared__ unsigned char s_q16[GPB][ROWS];  // one-hot codes of the two oriented reads, same packing
   const int tid = threadIdx.x, grp = tid / G, gl = tid % G;
   const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) / G * G));
   const uint32_t n_items = *a.n_items, n_pairs = (n_items + 1) >> 1;
   const uint32_t ggid = blockIdx.x * GPB + grp, n_groups = gridDim.x * GPB;
-  uint32_t* win = s_win[grp];
+  unsigned char* win = s_win[grp];
   uint32_t* band = s_band16 + (size_t)grp * ROWS * PM_BAND16_LANES * 6;
   const int bis = a.p.is_bisulfite;
   const int half = a.band_half < PM_BAND16_LANES / 2 ? a.band_half : PM_BAND16_LANES / 2;
@@ -428,7 +426,7 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
         cB = ch == 'A' ? 1u : ch == 'C' ? (bis ? 10u : 2u) : ch == 'G' ? 4u : ch == 'T' ? 8u : (ch == 'N' || ch == 'n') ? 15u : 0u;
         badB |= (cB == 0u);
       }
-      win[i] = cA | (cB << 16);
+      win[i] = (unsigned char)(cA | (cB << 4));
     }
     uint32_t q[WD], s0u[WD], s1u[WD], mu[WD];
     const int jbase = gl * WD;
@@ -447,6 +445,7 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
         badB |= (cB == 0u);
       }
       q[c] = cA | (cB << 16);
+      s_q16[grp][j0] = (unsigned char)(cA | (cB << 4));
       const uint32_t b = (uint32_t)(PM_TBIAS - 72 - j0);  // S*[0][j] = -(72 + j - 1), j = j0 + 1 (2073-2081)
       s0u[c] = b | (b << 16);
       s1u[c] = s0u[c];
@@ -469,7 +468,8 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
       }
       const int i = s - gl + 1;
       if (i >= 1 && i <= nn) {
-        const uint32_t rc = win[i - 1];
+        const uint32_t rb = win[i - 1];
+        const uint32_t rc = (rb & 15u) | ((rb >> 4) << 16);
         uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
 #pragma unroll
         for (int c = 0; c < WD; c++) {
@@ -525,16 +525,14 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
       cell.hi = second ? 1 : 0;
       // the tie certification reads one-hot window codes: give it this winner's half through a byte view
       TieCtx tc;
-      tc.win = reinterpret_cast<const unsigned char*>(win) + (second ? 2 : 0);
-      tc.win_stride = 4;
-      tc.read = read;
-      tc.mm = mm;
-      tc.orient = orient;
+      tc.win = win;
+      tc.qcode = s_q16[grp];
+      tc.shift = second ? 4 : 0;
       const int r36 = (int)lrint(res.score * 36.0);
       int rc = (bad || nnw <= 0) ? PM_WALK_TIE : walk_check_int(cell, tc, res.maxk, res.maxi, mm, r36);
       atomicAdd(&a.counters->tb_cells_int, (unsigned long long)nnw * (unsigned long long)mm);
       if (rc == PM_WALK_OK) {
-        walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink);
+        walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink, tc.qcode, tc.shift);
       } else {
         const uint32_t w = atomicAdd(a.exact_cursor, 1u);
         a.exact_winners[w] = a.winners[second ? itB : itA];

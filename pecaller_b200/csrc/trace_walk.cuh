@@ -55,9 +55,20 @@ __device__ __forceinline__ int band_center_lane(int i, int dend) {
 
 // Cell: int operator()(int pi, int pj) -> decision bits of cell (pi, pj), or -1 when the cell is not stored.
 // APPLY = false: dry run that only reports PM_WALK_TIE / PM_WALK_OOB; APPLY = true: the pileup increments.
+// one-hot base code (A 1, C 2, G 4, T 8, N 15, anything else 0) -> pileup column, -1 = counted nowhere (1846-1858)
+__device__ __forceinline__ int code_column(unsigned code) {
+  return code == 1u ? 0 : code == 2u ? 1 : code == 4u ? 2 : code == 8u ? 3 : -1;
+}
+__device__ __forceinline__ unsigned base_onehot(char ch) {
+  return ch == 'A' ? 1u : ch == 'C' ? 2u : ch == 'G' ? 4u : ch == 'T' ? 8u : (ch == 'N' || ch == 'n') ? 15u : 0u;
+}
+
+// qcode: one-hot codes of the oriented read in shared memory, one byte per column, the code in bits qshift..qshift+3
+// (the walk is a chain of dependent steps on one lane: it must not wait on global memory); the characters themselves
+// are only fetched for insertions.
 template <bool APPLY, int TIE_BITS, class Cell>
 __device__ __forceinline__ int walk_path(const Cell& cell, int k, int i, int j, const char* read, int mm, int orient,
-                                         uint32_t wstart, const PileSink& sink) {
+                                         uint32_t wstart, const PileSink& sink, const unsigned char* qcode, int qshift) {
   int n_pend = 0, i1 = 0, j1 = 0;
   while (i > 0 && j > 0) {
     i1 = i - 1;
@@ -92,8 +103,7 @@ __device__ __forceinline__ int walk_path(const Cell& cell, int k, int i, int j, 
       const uint32_t site = wstart + (uint32_t)i1;
       if (pi != i) {
         if (pj != j) {  // 1846-1858
-          const char ch = oriented_char(read, mm, orient, j1);
-          const int col = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1;
+          const int col = code_column((qcode[j1] >> qshift) & 15u);
           if (col >= 0) atomicAdd(&sink.counts[(size_t)site * 6 + col], 1u);
         } else {
           atomicAdd(&sink.counts[(size_t)site * 6 + 4], 1u);  // 1868

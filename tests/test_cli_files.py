@@ -1,0 +1,73 @@
+"""GPU: the C host (pecaller_b200/host/pemapper_gpu: reference argv, FASTQ reader and writers over the C-ABI) against
+the committed output FILES of the unmodified reference pemapper (tests/golden, tools/make_golden.py):
+.mfile and the inflated .pileup.gz byte for byte, .summary.txt verbatim, .indel.txt.gz up to the order of the
+insertion strings of a site (not deterministic in the reference either)."""
+import gzip
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_io as gio
+import oracle_lib as ol
+from pecaller_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "pecaller_b200", "host", "pemapper_gpu")
+
+
+def _normalise_indel(path):
+    lines = []
+    with gzip.open(path, "rt") as f:
+        for ln in f.read().split("\n"):
+            parts = ln.split("\t")
+            if len(parts) > 7 and parts[0] != "Fragment":
+                parts = parts[:7] + sorted(parts[7:])
+            lines.append("\t".join(parts))
+    return "\n".join(lines)
+
+
+@pytest.mark.parametrize("name", ["tiny", "edge9"])
+def test_cli_files_match_reference(name, get_fixture, oracle_built, tmp_path):
+    if not os.path.exists(CLI):
+        pytest.fail("C host not built: run __graft_entry__.build()")
+    fx = get_fixture(name)
+    work = str(tmp_path)
+    oracle = ol.Oracle(fx.genome)
+    oracle.write_index(os.path.join(work, "g"), fx.names, with_idx=False)   # .sdx/.seq (+.mdx); .idx is rebuilt on the GPU
+    oracle.close()
+    assert open(os.path.join(work, "g.sdx")).read() == gio.index_meta(name)["sdx"]
+    env = dict(os.environ, PEMAP_DEVICE_INDEX="1")
+    checked = 0
+    for run in fx.runs:
+        if not gio.have(name, run.name):
+            continue
+        n = run.reads1.shape[0]
+        synth.write_fastq(os.path.join(work, run.name + "_1.fq"), run.reads1)
+        bis = "y" if run.bisulfite else "n"
+        if run.paired:
+            synth.write_fastq(os.path.join(work, run.name + "_2.fq"), run.reads2)
+            cmd = [CLI, run.name, "g.sdx", "p", run.name + "_1.fq", run.name + "_2.fq", str(run.max_dist), str(run.min_dist),
+                   bis, repr(run.min_align), "4", str(n + 8)]
+        else:
+            cmd = [CLI, run.name, "g.sdx", "s", run.name + "_1.fq", bis, repr(run.min_align), "4", str(n + 8)]
+        r = subprocess.run(cmd, cwd=work, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        tag = "%s/%s" % (name, run.name)
+        m1 = np.fromfile(os.path.join(work, run.name + "_1.fq.mfile"), dtype=np.uint32)
+        assert np.array_equal(m1, gio.mfile(name, run.name, 1)), tag + ": .mfile 1"
+        if run.paired:
+            m2 = np.fromfile(os.path.join(work, run.name + "_2.fq.mfile"), dtype=np.uint32)
+            assert np.array_equal(m2, gio.mfile(name, run.name, 2)), tag + ": .mfile 2"
+        raw = gzip.open(os.path.join(work, run.name + ".pileup.gz"), "rb").read()
+        assert hashlib.sha256(raw).hexdigest() == gio.pileup_meta(name, run.name)["sha256"], tag + ": .pileup.gz"
+        gold_summary = open(os.path.join(gio.GOLD, name, run.name + ".summary.txt")).read()
+        assert open(os.path.join(work, run.name + ".summary.txt")).read() == gold_summary, tag + ": .summary.txt"
+        gold_indel = gzip.open(os.path.join(gio.GOLD, name, run.name + ".indel.norm.txt.gz"), "rt").read()
+        assert _normalise_indel(os.path.join(work, run.name + ".indel.txt.gz")) == gold_indel, tag + ": .indel.txt.gz"
+        checked += 1
+    assert checked > 0
