@@ -273,7 +273,7 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   CK(cudaMalloc(&h->d_det_score, 2 * n * 8));
   h->seed_blocks = h->sm_count * 8;
   CK(cudaMalloc(&h->d_seed_scratch, (size_t)h->seed_blocks * kSeedWarps * 2 * PM_MAX_SEG * PM_SEG_CAP * 4));
-  h->sw_blocks = h->sm_count * 4;
+  h->sw_blocks = h->sm_count * 6;  // upper bound of CTAs per SM of the wavefront kernels (scratch is sized for it)
   const size_t max_groups = (size_t)h->sw_blocks * (128 / 16);
   // trace scratch: groups * G == sw_blocks * 128 lanes for every instantiation, PM_DP_MAX rows of one word per lane
   CK(cudaMalloc(&h->d_dirs, (size_t)h->sw_blocks * 128 * PM_DP_MAX * sizeof(unsigned long long)));
@@ -361,17 +361,27 @@ int check_contigs(pemap_ctx* h, int n) {
   return PEMAP_OK;
 }
 
+// persistent grid-stride kernels: exactly one wave, as many CTAs per SM as registers and shared memory allow
+// (capped by the per-group scratch the context allocated: h->sw_blocks CTAs)
+template <class K>
+int one_wave_grid(pemap_ctx* h, K kernel, int block, size_t dyn) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, dyn) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  return std::min(h->sw_blocks, per_sm * h->sm_count);
+}
+
 template <int G, int WD, int MODE>
 void launch_sw(pemap_ctx* h, const pm::SwArgs& a) {
   const size_t dyn = MODE == 2 ? pm::trace_band_bytes<G, WD>() : 0;
-  if (MODE == 2) {
-    static bool once = false;  // per instantiation
-    if (!once) {
-      cudaFuncSetAttribute(pm::k_sw_fp64<G, WD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-      once = true;
-    }
+  static int grid = 0;  // per instantiation
+  if (!grid) {
+    if (MODE == 2) cudaFuncSetAttribute(pm::k_sw_fp64<G, WD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    grid = one_wave_grid(h, pm::k_sw_fp64<G, WD, MODE>, 128, dyn);
   }
-  pm::k_sw_fp64<G, WD, MODE><<<h->sw_blocks, 128, dyn, h->stream>>>(a);
+  pm::k_sw_fp64<G, WD, MODE><<<grid, 128, dyn, h->stream>>>(a);
 }
 
 template <int MODE>
@@ -396,12 +406,12 @@ void launch_trace_int(pemap_ctx* h, const pm::TraceIntArgs& a) {
     return;
   }
   const size_t dyn = pm::trace16_band_bytes<G, WD>();
-  static bool once16 = false;
-  if (!once16) {
+  static int grid16 = 0;
+  if (!grid16) {
     cudaFuncSetAttribute(pm::k_trace_i16<G, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    once16 = true;
+    grid16 = one_wave_grid(h, pm::k_trace_i16<G, WD>, 128, dyn);
   }
-  pm::k_trace_i16<G, WD><<<h->sw_blocks, 128, dyn, h->stream>>>(a);
+  pm::k_trace_i16<G, WD><<<grid16, 128, dyn, h->stream>>>(a);
 }
 
 void dispatch_trace_int(pemap_ctx* h, const pm::TraceIntArgs& a, int max_len) {
@@ -415,13 +425,21 @@ void dispatch_trace_int(pemap_ctx* h, const pm::TraceIntArgs& a, int max_len) {
 template <int G, int WD, int CMM>
 struct CmmDispatch {
   static void go(pemap_ctx* h, const pm::SwIntArgs& a, int cmm) {
-    if (cmm == CMM) pm::k_sw_i16<G, WD, CMM><<<h->sw_blocks, 128, 0, h->stream>>>(a);
+    if (cmm == CMM) {
+      static int grid = 0;
+      if (!grid) grid = one_wave_grid(h, pm::k_sw_i16<G, WD, CMM>, 128, 0);
+      pm::k_sw_i16<G, WD, CMM><<<grid, 128, 0, h->stream>>>(a);
+    }
     else CmmDispatch<G, WD, CMM - 1>::go(h, a, cmm);
   }
 };
 template <int G, int WD>
 struct CmmDispatch<G, WD, -1> {
-  static void go(pemap_ctx* h, const pm::SwIntArgs& a, int) { pm::k_sw_i16<G, WD, -1><<<h->sw_blocks, 128, 0, h->stream>>>(a); }
+  static void go(pemap_ctx* h, const pm::SwIntArgs& a, int) {
+    static int grid = 0;
+    if (!grid) grid = one_wave_grid(h, pm::k_sw_i16<G, WD, -1>, 128, 0);
+    pm::k_sw_i16<G, WD, -1><<<grid, 128, 0, h->stream>>>(a);
+  }
 };
 
 // uniform_len > 0: every read of the chunk has that length (lets the kernel fix the last read column at compile time)

@@ -347,11 +347,11 @@ __global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
 //     F0  S1 > S0 (or X tie)      F1  S2 > max(S0,S1)     F2  X1     F3  X2
 //     F4  S1 == S0 (or X tie)     F5  S2 == max(S0,S1)
 // (F0 and F4 both set cannot happen otherwise and marks the cell like A == 3 above.)  Only the PM_BAND16_LANES
-// lanes around the two winners' end diagonals keep their words, in shared memory; lane 0 walks the first winner
+// lanes nearest the two winners' end diagonals keep their words, in shared memory; lane 0 walks the first winner
 // and lane 1 the second, with the same walker and tie certification as k_trace_i32.
 // ---------------------------------------------------------------------------------------------------
 #define PM_TBIAS 1024
-#define PM_BAND16_LANES 3
+#define PM_BAND16_LANES 2   // the lane of the end-diagonal column and its nearer neighbour: >= WD/2 columns each side
 
 template <int G, int WD>
 __host__ __device__ constexpr size_t trace16_band_bytes() {
@@ -361,11 +361,11 @@ __host__ __device__ constexpr size_t trace16_band_bytes() {
 template <int WD>
 struct PackedBandCell {
   const uint32_t* band;  // [rows][PM_BAND16_LANES][6]
-  int dmid, half, hi;    // hi: 0 = low halves (first winner), 1 = high halves
+  int dmid, half, hi;    // hi: 0 = low halves (first winner), 1 = high halves; half = 0 keeps one lane (tests)
   __device__ __forceinline__ int operator()(int pi, int pj) const {
     const int l = (pj - 1) / WD, c = (pj - 1) - l * WD;
-    const int slot = l - (band_center_lane<WD>(pi, dmid) - half);
-    if (slot < 0 || slot > 2 * half) return -1;
+    const int slot = l - (band_center_lane<WD>(pi + WD / 2, dmid) - half);
+    if (slot < 0 || slot > half) return -1;
     const uint32_t* w = band + ((pi - 1) * PM_BAND16_LANES + slot) * 6;
     const int bit = 16 - WD + c + 16 * hi;
     const uint2 w01 = *reinterpret_cast<const uint2*>(w), w23 = *reinterpret_cast<const uint2*>(w + 2),
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
   unsigned char* win = s_win[grp];
   uint32_t* band = s_band16 + (size_t)grp * ROWS * PM_BAND16_LANES * 6;
   const int bis = a.p.is_bisulfite;
-  const int half = a.band_half < PM_BAND16_LANES / 2 ? a.band_half : PM_BAND16_LANES / 2;
+  const int half = a.band_half < 1 ? a.band_half : 1;  // lanes kept = half + 1
   constexpr uint32_t K1 = 0x00010001u, K12 = 0x000C000Cu, NEG72 = 0xFFB8FFB8u, H = 0x80008000u;
   constexpr uint32_t BIASP = (PM_TBIAS << 16) | PM_TBIAS;
   constexpr uint32_t HX = H + 70u * K1;  // x = S + 70 >= S0  <=>  S - ge > S0 - go
@@ -500,8 +500,8 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
         out_s0 = l_s0;
         out_s2 = l_s2;
         out_m = diag;
-        const int slot = gl - (band_center_lane<WD>(i, dmid) - half);
-        if (slot >= 0 && slot <= 2 * half) {
+        const int slot = gl - (band_center_lane<WD>(i + WD / 2, dmid) - half);
+        if (slot >= 0 && slot <= half) {
           uint32_t* w = band + ((i - 1) * PM_BAND16_LANES + slot) * 6;
           *reinterpret_cast<uint2*>(w) = make_uint2(a0, a1);
           *reinterpret_cast<uint2*>(w + 2) = make_uint2(a2, a3);

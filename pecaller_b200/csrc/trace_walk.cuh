@@ -10,12 +10,12 @@
 //
 // Band store: a lane writes one 64-bit word per row (its WD columns).  Only the PM_BAND_LANES lanes around the lane
 // that owns the column of the winner's end diagonal (j = i - (maxi - mm)) are kept, in shared memory; a walk that
-// leaves the band (net indel drift > 2*WD columns) reports PM_WALK_OOB and the winner is redone by the kernel that
+// leaves the band (net indel drift > WD columns) reports PM_WALK_OOB and the winner is redone by the kernel that
 // keeps every lane's word in global memory.
 #pragma once
 #include "pemap_common.cuh"
 
-#define PM_BAND_LANES 5
+#define PM_BAND_LANES 3
 #define PM_WALK_OK 0
 #define PM_WALK_TIE 1
 #define PM_WALK_OOB 2
