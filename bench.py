@@ -220,8 +220,9 @@ def main():
         line = {"impl": "reference", "metric": "mapped reads/sec", "value": v, "unit": "reads/s", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * 2 * n / v, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "cfg2: 64 Mb genome, paired-end 150 bp, 1% subs + 0.1% ins + 0.1% del",
-                           "sample": "%d pairs per step" % n},
+                "config": {"workload": "cfg2: 64 Mb single-contig genome, %d paired-end 150 bp reads per GPU per step, "
+                                       "1%% subs + 0.1%% ins + 0.1%% del, insert U[250,450]" % a.pairs,
+                           "sample": "each step maps the first %d pairs of that workload on %d host threads" % (n, threads)},
                 "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": kind,
                                  "sample": "%d pairs (%d read-mates) per step, %d threads" % (n, 2 * n, threads)},
                 "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -486,7 +486,18 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   sa.p = h->dp;
   sa.p.pair_flag = paired ? 1 : 0;
   const int work = paired ? 2 * n : n;
-  const int seed_grid = std::min(h->seed_blocks, (work + kSeedWarps - 1) / kSeedWarps);
+  static int seed_wave[2] = {0, 0};  // one resident wave of the persistent seed kernel, per variant
+  const int sv = h->d_filter ? 1 : 0;
+  if (!seed_wave[sv]) {
+    int per_sm = 0;
+    cudaError_t oe = sv ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_seed_chain<kSeedWarps, true>, kSeedWarps * 32, 0)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_seed_chain<kSeedWarps, false>, kSeedWarps * 32, 0);
+    if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
+    cudaGetLastError();
+    seed_wave[sv] = std::min(h->seed_blocks, per_sm * h->sm_count);
+    if (getenv("PEMAP_VERBOSE")) fprintf(stderr, "pemap: seed kernel %d CTAs per SM\n", per_sm);
+  }
+  const int seed_grid = std::min(seed_wave[sv], (work + kSeedWarps - 1) / kSeedWarps);
   if (h->d_filter) pm::k_seed_chain<kSeedWarps, true><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
   else pm::k_seed_chain<kSeedWarps, false><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
   h->stats.launches++;

@@ -43,7 +43,9 @@ struct SeedArgs {
   DevParams p;
 };
 
-#define PM_SEED_QUEUE 512      // per-warp queue of k-mers that passed the filter (drained 256 at a time)
+#define PM_SLIST 4             // positions of a segment kept in shared memory (complete list when segcnt <= PM_SLIST)
+#define PM_SEED_DRAIN 128      // queued k-mers looked up per drain (4 per lane in flight)
+#define PM_SEED_QUEUE (PM_SEED_DRAIN + 32 * PM_SEED_UNROLL)  // per-warp queue of k-mers that passed the filter
 
 // word index and bit mask of a k-mer in the word-blocked (32-bit blocks) Bloom filter
 __host__ __device__ __forceinline__ void filter_slot(uint32_t code, int shift, int k, uint32_t* word, uint32_t* mask) {
@@ -83,6 +85,9 @@ struct SeedWarpSmem {
   uint32_t hit_pos[PM_MAX_HITS];
   uint16_t hit_off[PM_MAX_HITS];
   uint8_t hit_or[PM_MAX_HITS];
+  // head of every segment list: on a unique genome a segment has one or two positions, and sorting / chaining them
+  // out of shared memory takes the L2 round trips off the warp's critical path; longer lists live in the global scratch
+  uint32_t slist[2 * PM_MAX_SEG][PM_SLIST];
 };
 
 struct SeedQueueSmem {         // FILT only
@@ -123,7 +128,11 @@ __device__ __forceinline__ void seed_lookup_tile(const SeedArgs& a, SeedWarpSmem
         uint32_t off = atomicAdd(&sm.segcnt[ssv[u]], cnt);
         uint32_t* dst = lists + (size_t)ssv[u] * PM_SEG_CAP + off;
         const uint32_t* src = a.mers + lo[u];
-        for (uint32_t t = 0; t < cnt; t++) dst[t] = __ldcg(src + t);
+        for (uint32_t t = 0; t < cnt; t++) {
+          const uint32_t v = __ldcg(src + t);
+          dst[t] = v;
+          if (off + t < PM_SLIST) sm.slist[ssv[u]][off + t] = v;
+        }
         st_pos += cnt;
       }
     }
@@ -292,9 +301,9 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
             qn += __popc(bal);
           }
           __syncwarp();
-          while (qn >= 32 * PM_SEED_UNROLL) {  // drain a full tile from the tail
-            qn -= 32 * PM_SEED_UNROLL;
-            seed_lookup_tile(a, sm, lists, qs.code + qn, qs.ss + qn, 32 * PM_SEED_UNROLL, lane, st_pos);
+          while (qn >= PM_SEED_DRAIN) {  // drain from the tail
+            qn -= PM_SEED_DRAIN;
+            seed_lookup_tile(a, sm, lists, qs.code + qn, qs.ss + qn, PM_SEED_DRAIN, lane, st_pos);
             __syncwarp();
           }
         }
@@ -333,7 +342,11 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
                 uint32_t off = atomicAdd(&sm.segcnt[ssv[u]], cnt);
                 uint32_t* dst = lists + (size_t)ssv[u] * PM_SEG_CAP + off;
                 const uint32_t* src = a.mers + lo[u];
-                for (uint32_t t = 0; t < cnt; t++) dst[t] = __ldcg(src + t);
+                for (uint32_t t = 0; t < cnt; t++) {
+                  const uint32_t v = __ldcg(src + t);
+                  dst[t] = v;
+                  if (off + t < PM_SLIST) sm.slist[ssv[u]][off + t] = v;
+                }
                 st_pos += cnt;
               }
             }
@@ -348,7 +361,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
       // ---- ascending sort of every segment list (1613-1614, 1638-1639)
       for (int ss = 0; ss < 2 * nseg; ss++) {
         int n = (int)sm.segcnt[ss];
-        if (n > 1) warp_sort_list(lists + (size_t)ss * PM_SEG_CAP, n, lane);
+        if (n > 1) warp_sort_list(n <= PM_SLIST ? sm.slist[ss] : lists + (size_t)ss * PM_SEG_CAP, n, lane);
       }
       __syncwarp();
 
@@ -361,6 +374,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
         if (strand == 1 && tot >= a.p.max_hits) break;  // 1658
         const uint32_t* cnts = sm.segcnt + strand * nseg;
         const uint32_t* slists = lists + (size_t)strand * nseg * PM_SEG_CAP;
+        const uint32_t(*shead)[PM_SLIST] = sm.slist + strand * nseg;
         uint32_t ms = 10000;
         if (lane < nseg) ms = cnts[lane];
         ms = __reduce_min_sync(0xFFFFFFFFu, ms);
@@ -372,7 +386,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
         for (int loop = 0; !done && loop <= 1 + max_depth - min_match; loop++) {
           const int off_loop = (loop < total_cuts) ? 16 * loop : len - 16;
           const int na = (int)cnts[loop];
-          const uint32_t* anchors = slists + (size_t)loop * PM_SEG_CAP;
+          const uint32_t* anchors = na <= PM_SLIST ? shead[loop] : slists + (size_t)loop * PM_SEG_CAP;
           for (int i0 = 0; i0 < na && !done; i0 += 32) {
             const int i = i0 + lane;
             const bool valid = i < na;
@@ -386,7 +400,8 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
                 // |(anchor - p) - (offsets[loop] - offsets[j])| < max_off = 12  (2244)
                 const long long c = (long long)av + d;
                 const int mo = (a.p.idepth - 4 > 2) ? a.p.idepth - 4 : 2;
-                found += list_has_in_range(slists + (size_t)j * PM_SEG_CAP, nj, c - (mo - 1), c + (mo - 1)) ? 1 : 0;
+                found += list_has_in_range(nj <= PM_SLIST ? shead[j] : slists + (size_t)j * PM_SEG_CAP, nj, c - (mo - 1),
+                                           c + (mo - 1)) ? 1 : 0;
               }
             unsigned mask = __ballot_sync(0xFFFFFFFFu, valid && found >= min_match);
             while (mask) {
