@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
   constexpr int ROWS = (G * WD + 24 < PM_DP_MAX) ? G * WD + 24 : PM_DP_MAX;
   extern __shared__ unsigned long long s_band_d[];  // MODE 2: [GROUPS_PER_BLOCK][ROWS][PM_BAND_LANES]
   __shared__ char s_win[GROUPS_PER_BLOCK][PM_DP_MAX];
+  __shared__ unsigned char s_wk[GROUPS_PER_BLOCK][PM_DP_MAX];  // one-hot codes of the window (0 = outside ACGTN)
   __shared__ unsigned char s_q[TRACE ? GROUPS_PER_BLOCK : 1][TRACE ? PM_DP_MAX : 1];  // one-hot codes of the oriented read
   const int tid = threadIdx.x;
   const int grp = tid / G, gl = tid % G;
@@ -83,15 +84,28 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
     const int dend = res.maxi - mm;
 
     __syncwarp(gmask);
-    for (int i = gl; i < nn; i += G) win[i] = a.genome[(size_t)tk.wstart + i];
+    const int bis = a.p.is_bisulfite;
+    for (int i = gl; i < nn; i += G) {
+      const char ch = a.genome[(size_t)tk.wstart + i];
+      win[i] = ch;
+      unsigned code = base_onehot(ch);
+      if (bis && ch == 'C') code = 10u;  // reference C also matches read T (2026-2033)
+      s_wk[grp][i] = (unsigned char)code;
+    }
     // this lane's read characters (reverse strand = reverse_transcribe'd read, 1021/1098)
+    // Bases match iff their one-hot codes share a bit (N = all bits); a code of 0 (any character outside ACGTN,
+    // lower case included) sends the row to the character comparison of init_bonus_matrices (2006-2035).
     char q[WD];
+    unsigned qk[WD];
+    bool lane_other = false;
     const int jbase = gl * WD;  // columns jbase+1 .. jbase+WD
 #pragma unroll
     for (int c = 0; c < WD; c++) {
       int j0 = jbase + c;
       q[c] = (j0 < mm) ? seq_char(read, mm, orient, j0) : (char)0;
-      if (TRACE && j0 < PM_DP_MAX) s_q[grp][j0] = (unsigned char)base_onehot(q[c]);
+      qk[c] = base_onehot(q[c]);
+      lane_other |= (j0 < mm) && qk[c] == 0u;
+      if (TRACE && j0 < PM_DP_MAX) s_q[grp][j0] = (unsigned char)qk[c];
     }
     // row 0 (init_penalty_matrices 2073-2081): S0 = S1 = S2 = M = border[j]
     double s0u[WD], s1u[WD], mu[WD];
@@ -121,13 +135,16 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
       const int i = s - gl + 1;
       if (i >= 1 && i <= nn) {
         const char rc = win[i - 1];
+        const unsigned rk = s_wk[grp][i - 1];
+        const bool by_char = lane_other || rk == 0u;
         double l_s0 = in_s0, l_s2 = in_s2, diag = in_m;
         unsigned long long dword = 0;
 #pragma unroll
         for (int c = 0; c < WD; c++) {
           const double s2 = dmax(l_s0 - go, l_s2 - ge);
           const double s1 = dmax(s0u[c] - go, s1u[c] - ge);
-          const double bump = bases_match(rc, q[c], a.p.is_bisulfite) ? match : mism;
+          const bool same = by_char ? bases_match(rc, q[c], bis) : (qk[c] & rk) != 0u;
+          const double bump = same ? match : mism;
           const double s0 = diag + bump;
           diag = mu[c];
           // argmax with the traceback's priority 0 > 1 > 2 (1804-1811)

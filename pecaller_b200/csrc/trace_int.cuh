@@ -14,11 +14,10 @@
 // The reference decides on rounded doubles with strict '>', so a comparison of rationally equal values may go
 // either way.  Lane 0 therefore walks the path twice: a dry pass that only looks for a
 // tie on a consulted decision or a step outside the band, and, if there was none, the pass that applies the pileup
-// increments.  An A tie is first put to resolve_tie(): the two tied values are traced back in lock step, and if
-// their histories join again after nothing but exact double operations (adding +-1.0 / -2.0 without moving to a
-// higher binade) they are one double plus the same integer, i.e. EQUAL doubles, and the reference's strict '>'
-// keeps the lower state - exactly the integer argmax.  Typical case: a gap inside a homopolymer run.  Only ties
-// that cannot be certified this way hand the winner to the exact fp64 traceback kernel.  Every consulted comparison then has integer
+// increments.  An A tie is first put to resolve_tie(): the tied values are traced back in lock step, and if their
+// histories join again and are provably EQUAL doubles (two certificates, see resolve_tie) the reference's strict '>'
+// keeps the lower state - exactly the integer argmax.  Typical case: a gap inside a homopolymer run or a short
+// tandem repeat.  Only ties that cannot be certified hand the winner to the exact fp64 traceback kernel.  Every consulted comparison then has integer
 // operands that differ, i.e. doubles that differ by >= 1/36, and the walk is the reference's walk.
 #pragma once
 #include "pemap_common.cuh"
@@ -49,18 +48,32 @@ template <int G, int WD>
 __host__ __device__ constexpr size_t trace_band_bytes() { return (size_t)(128 / G) * trace_rows<G, WD>() * PM_BAND_LANES * 8; }
 
 // ---- exactness bookkeeping for resolve_tie ------------------------------------------------------------------
-// binade index of |x| / 36 (x in units of 1/36): number of powers of two 2^e (e >= -5) that are <= |x| / 36; 0 for x = 0
+// Values are rationals x / 36; the doubles the reference holds differ from them by a few ulps at most.
+// binade36: number of powers of two 2^e (e >= -5) that are <= |x| / 36; 0 for x = 0.  A rational exactly on a
+// power of two may have its double on either side: on_boundary36.
 __device__ __forceinline__ int binade36(int x) {
   const unsigned a = (unsigned)(x < 0 ? -x : x);
   if (a < 9u) return a >= 5u ? 4 : a >= 3u ? 3 : (int)a;  // thresholds 36 * 2^e rounded up: 1, 2, 3, 5
   return 5 + (31 - __clz(a / 9u));                         // 9, 18, 36, 72, ...
 }
+__device__ __forceinline__ bool on_boundary36(int x) {
+  const unsigned a = (unsigned)(x < 0 ? -x : x);
+  if (a < 9u || a % 9u) return false;
+  const unsigned q = a / 9u;
+  return (q & (q - 1u)) == 0u;
+}
 // adding an integer-valued double (+-1.0, -2.0) to a double is exact unless the result lands in a higher binade
-__device__ __forceinline__ bool exact_step(int from36, int to36) { return binade36(to36) <= binade36(from36); }
+__device__ __forceinline__ bool exact_step(int from36, int to36) {
+  return binade36(to36) <= binade36(from36) - (on_boundary36(from36) ? 1 : 0);
+}
 
 struct ChainPos {
   int i, j, k, r;   // state k of cell (i, j) holds the rational value r / 36
   int end;          // 0 walking, 1 ended on an exact constant (column 0), 2 ended on the row-0 border cell (0, j)
+  bool exact;       // every operation so far was an exact double addition (rule 1)
+  bool same;        // every value so far lies strictly inside the binade of the tied value (rule 2)
+  unsigned sig;     // the rounding operations so far, in order: base-3 digits 1 = mismatch (-1/3), 2 = extension (-1/36)
+  int n_round;
 };
 
 struct TieCtx {
@@ -85,18 +98,33 @@ __device__ __forceinline__ int top_set(int c) {
 
 #define PM_TIE_LIST 12
 #define PM_TIE_BUDGET 384
+#define PM_TIE_ROUNDS 18       // 3^18 < 2^32
 
-// One backward step of a value's history.  Returns false when the step is not an exact double operation (mismatch,
-// gap extension, binade change), leaves the band, or consults a decision that is itself undecidable here.
+// book one operation "prev -> p.r" of a history: is_round = it adds a rounded constant (digit 1 or 2)
+__device__ __forceinline__ bool chain_book(ChainPos& p, int prev, int digit, int b0) {
+  if (digit) {
+    p.exact = false;
+    if (++p.n_round > PM_TIE_ROUNDS) p.same = false;
+    p.sig = p.sig * 3u + (unsigned)digit;
+  } else if (!exact_step(prev, p.r)) {
+    p.exact = false;
+  }
+  if (binade36(prev) != b0 || on_boundary36(prev)) p.same = false;
+  return p.exact || p.same;
+}
+
+// One backward step of a value's history.  Returns false when neither certificate can hold any more (see
+// resolve_tie), the step leaves the band, or it consults a decision that is itself undecidable here.
 // Sub-ties met on the way (a predecessor cell whose maximum is shared) are appended to the work list.
 template <class Cell>
-__device__ __forceinline__ bool chain_step(const Cell& cell, const TieCtx& t, ChainPos& p, int* wl_i, int* wl_j, int& wl_n) {
+__device__ __forceinline__ bool chain_step(const Cell& cell, const TieCtx& t, ChainPos& p, int b0, int* wl_i, int* wl_j,
+                                           int& wl_n) {
   if (p.j == 0) { p.end = 1; return true; }             // S0[i][0] = S1[i][0] = 0, S2[i][0] = -go: exact constants
   if (p.i == 0) { p.end = 2; return true; }             // S*[0][j] = -(go + (j-1) ge): one rounded constant per column
   if (p.k == 0) {
-    if (!cells_match(t, p.i, p.j)) return false;        // + (-1/3): rounds
-    const int prev = p.r - 36;
-    if (!exact_step(prev, p.r)) return false;
+    const bool match = cells_match(t, p.i, p.j);
+    const int prev = p.r - (match ? 36 : -12);          // M[i-1][j-1]
+    if (!chain_book(p, prev, match ? 0 : 1, b0)) return false;
     p.i--; p.j--; p.r = prev;
     if (p.i == 0 || p.j == 0) { p.k = 0; return true; } // M of a border cell: every state there is handled above
     const int c = cell(p.i, p.j);
@@ -118,21 +146,35 @@ __device__ __forceinline__ bool chain_step(const Cell& cell, const TieCtx& t, Ch
   if (pi == 0 || pj == 0) {
     // from a border cell: opening from S0 = 0 (column 0) is exact; everything else involves a rounded value
     if (p.k == 2 && pj == 0) {                          // S2[i][1] = max(0 - go, -go - ge) = -go, exact
-      p.i = pi; p.j = pj; p.k = 0; p.r += 72;
+      const int prev = p.r + 72;
+      if (!chain_book(p, prev, 0, b0)) return false;
+      p.i = pi; p.j = pj; p.k = 0; p.r = prev;
       return true;
     }
     return false;
   }
   const int c = cell(pi, pj);
   if (c < 0 || (c & 3) == 3) return false;
-  if (c & (p.k == 1 ? 4 : 8)) return false;             // extension: - 1/36 rounds
-  const int prev = p.r + 72;
-  if (!exact_step(prev, p.r)) return false;
+  if (c & (p.k == 1 ? 4 : 8)) {                         // extension: - 1/36 rounds; the gap state continues
+    const int prev = p.r + 1;
+    if (!chain_book(p, prev, 2, b0)) return false;
+    p.i = pi; p.j = pj; p.r = prev;
+    return true;
+  }
+  const int prev = p.r + 72;                            // opening: - 2.0
+  if (!chain_book(p, prev, 0, b0)) return false;
   p.i = pi; p.j = pj; p.k = 0; p.r = prev;
   return true;
 }
 
-// Are the doubles of states a and b of cell (i, j), both of rational value r36 / 36, provably equal?
+// Are the doubles of the states sharing the maximum of cell (i, j), of rational value r36 / 36, provably equal?
+// The tied values are traced back in lock step until their histories join.  Two certificates:
+//  rule 1  both histories consist of exact double additions only (+-1.0, -2.0, never into a higher binade): both
+//          values are the common ancestor (or an exact border constant) plus the same integer;
+//  rule 2  both histories apply the same rounded constants (-1/3, -1/36) in the same order, merely interleaved
+//          differently with integer additions, and every value involved lies strictly inside one binade: there
+//          fl(y + c) - (y + c) depends only on y modulo the (common) ulp, which integer shifts leave alone (they are
+//          even multiples of the ulp, so round-half-even is preserved too); by induction the two values are equal.
 template <class Cell>
 __device__ bool resolve_tie(const Cell& cell, const TieCtx& t, int i, int j, int r36) {
   int wl_i[PM_TIE_LIST], wl_j[PM_TIE_LIST], wl_r[PM_TIE_LIST];
@@ -143,28 +185,37 @@ __device__ bool resolve_tie(const Cell& cell, const TieCtx& t, int i, int j, int
     if (c < 0 || (c & 3) == 3) return false;
     const int ts = top_set(c);
     const int first = __ffs(ts) - 1;
+    const int b0 = binade36(wl_r[w]);
+    const bool b0_ok = !on_boundary36(wl_r[w]);
     // every other state of the top set against the lowest one
     for (int other = first + 1; other < 3; other++) {
       if (!(ts & (1 << other))) continue;
       ChainPos A, B;
       A.i = B.i = wl_i[w]; A.j = B.j = wl_j[w]; A.r = B.r = wl_r[w];
       A.k = first; B.k = other; A.end = B.end = 0;
+      A.exact = B.exact = true;
+      A.same = B.same = b0_ok;
+      A.sig = B.sig = 0u;
+      A.n_round = B.n_round = 0;
       for (;;) {
-        if (A.end && B.end) {
-          // two exact constants, or the same row-0 border cell
-          if (A.end == 1 && B.end == 1) break;
-          if (A.end == 2 && B.end == 2 && A.j == B.j) break;
+        const bool joined = (!A.end && !B.end && A.i == B.i && A.j == B.j && A.k == B.k) ||
+                            (A.end == 2 && B.end == 2 && A.j == B.j);  // same cell and state / same row-0 border cell
+        if (joined) {
+          if (A.exact && B.exact) break;
+          if (A.same && B.same && A.sig == B.sig && A.n_round == B.n_round) break;
           return false;
         }
-        if (!A.end && !B.end && A.i == B.i && A.j == B.j && A.k == B.k) break;  // the histories joined
+        if (A.end && B.end) {
+          if (A.end == 1 && B.end == 1 && A.exact && B.exact) break;  // two exact constants plus integers
+          return false;
+        }
         if (--budget < 0) return false;
         // advance the one farther from the origin (the only one that can still reach the other)
         const bool stepA = !A.end && (B.end || A.i + A.j > B.i + B.j || (A.i + A.j == B.i + B.j && A.i >= B.i));
         ChainPos& p = stepA ? A : B;
         const int n0 = wl_n;
-        if (!chain_step(cell, t, p, wl_i, wl_j, wl_n)) return false;
+        if (!chain_step(cell, t, p, b0, wl_i, wl_j, wl_n)) return false;
         if (wl_n > n0) wl_r[n0] = p.r;                 // value of the shared maximum just queued
-        if (A.end == 1 && B.end == 1) break;
       }
     }
   }
