@@ -27,7 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-GENOME_LEN = 64_000_000
+GENOME_LEN = int(os.environ.get("PEMAP_BENCH_GENOME", 64_000_000))  # cfg2: 64 Mb
 PAIRS = 10_000_000
 READ_LEN = 150
 STRIDE = 160
@@ -220,8 +220,8 @@ def main():
         line = {"impl": "reference", "metric": "mapped reads/sec", "value": v, "unit": "reads/s", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * 2 * n / v, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "cfg2: 64 Mb single-contig genome, %d paired-end 150 bp reads per GPU per step, "
-                                       "1%% subs + 0.1%% ins + 0.1%% del, insert U[250,450]" % a.pairs,
+                "config": {"workload": "cfg2: %d Mb single-contig genome, %d paired-end 150 bp reads per GPU per step, "
+                                       "1%% subs + 0.1%% ins + 0.1%% del, insert U[250,450]" % (GENOME_LEN // 1000000, a.pairs),
                            "sample": "each step maps the first %d pairs of that workload on %d host threads" % (n, threads)},
                 "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": kind,
                                  "sample": "%d pairs (%d read-mates) per step, %d threads" % (n, 2 * n, threads)},
@@ -374,8 +374,8 @@ def main():
                 "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "s16x2 integer DP in units of 1/36 (fp64 only for rational ties)",
                 "data": "synthetic",
-                "config": {"workload": "cfg2: 64 Mb single-contig genome, %d paired-end 150 bp reads per GPU per step, "
-                                       "1%% subs + 0.1%% ins + 0.1%% del, insert U[250,450]" % n,
+                "config": {"workload": "cfg2: %d Mb single-contig genome, %d paired-end 150 bp reads per GPU per step, "
+                                       "1%% subs + 0.1%% ins + 0.1%% del, insert U[250,450]" % (GENOME_LEN // 1000000, n),
                            "l2": "inputs (%.1f GB of reads per step) and the 16 GiB index exceed the 126 MB L2" % (2 * n * STRIDE / 1e9),
                            "parallelism": "reads sharded over %d GPU(s), index replicated, NCCL sum of pileup counters" % world,
                            "index_build_s": round(t_index, 2), "datagen_s": round(t_gen, 2)},

@@ -301,10 +301,11 @@ int build_filter(pemap_ctx* h) {
   int lg = 18;  // 32-bit words: 2^18 * 4 B = 1 MB minimum
   while ((4ull << (lg + 1)) <= cap && (32ull << lg) < 16ull * h->n_mers) lg++;  // up to 16 bits per k-mer
   while ((4ull << lg) > cap && lg > 10) lg--;
+  const double bits_per_key = (double)(32ull << lg) / (double)h->n_mers;
+  if (bits_per_key < 1.5) return PEMAP_OK;   // too dense to reject much: go straight to the table
   h->filter_bytes = 4ull << lg;
   h->filter_shift = 32 - lg;
-  const double bits_per_key = (double)(32ull << lg) / (double)h->n_mers;
-  h->filter_k = bits_per_key >= 12.0 ? 3 : 2;
+  h->filter_k = bits_per_key >= 12.0 ? 3 : bits_per_key >= 3.0 ? 2 : 1;
   CK(cudaMalloc(&h->d_filter, h->filter_bytes));
   CK(cudaMemsetAsync(h->d_filter, 0, h->filter_bytes, h->stream));
   pm::k_filter_build<<<1u << 22, 256, 0, h->stream>>>(h->d_pos_index, h->d_filter, h->filter_shift, h->filter_k);

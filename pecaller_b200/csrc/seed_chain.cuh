@@ -39,7 +39,7 @@ struct SeedArgs {
   SeedCounters* counters;
   const uint32_t* filter;      // 2^(32 - filter_shift) words, or nullptr
   int filter_shift;
-  int filter_k;                // bits set per k-mer (2..4)
+  int filter_k;                // bits set per k-mer (1..4)
   DevParams p;
 };
 
@@ -55,7 +55,7 @@ __host__ __device__ __forceinline__ void filter_slot(uint32_t code, int shift, i
   x ^= x >> 13;
   *word = x >> shift;
   uint32_t m = 1u << (x & 31u);
-  m |= 1u << ((x >> 5) & 31u);
+  if (k > 1) m |= 1u << ((x >> 5) & 31u);
   if (k > 2) m |= 1u << ((x >> 10) & 31u);
   if (k > 3) m |= 1u << ((x >> 15) & 31u);
   *mask = m;

@@ -45,6 +45,7 @@ def main():
         m1 = torch.zeros(n, dtype=torch.int32, device=dev)
         m2 = torch.zeros(n, dtype=torch.int32, device=dev)
         ty = torch.zeros(n, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()  # the library runs on its own non-blocking stream
         for it in range(4):  # 3 warm-up passes, the 4th is measured
             mapper.reset_counts()
             mapper.reset_stats()
