@@ -251,6 +251,47 @@ def test_two_gpus_equal_one(get_fixture, tmp_path):
     assert pickle.load(open(out + ".ins", "rb")) == sorted(ins)
 
 
+def test_integer_path_equals_exact_path_at_scale(monkeypatch):
+    """Size-independent property at bench scale (cfg2 model, 4 M pairs = 8 M read-mates, ~2.2 M gapped tracebacks):
+    the default path (s16x2 scoring, diagonal fast path, integer traceback with tie certificates, fp64 only for
+    uncertified ties) must give the same m1/m2/type and byte-identical pileup records and insertion multiset as the
+    all-fp64 path (PEMAP_EXACT=1), which evaluates the reference's own double expressions for every candidate and is
+    pinned bit for bit to the oracle and the reference binary on the fixtures above."""
+    import torch
+    import bench
+    n = 4_000_000
+    dev = torch.device("cuda", 0)
+    genome = bench.make_genome(20, 64_000_000)
+    gt = torch.from_numpy(genome).to(dev)
+    d_r1, d_r2 = bench.torch_reads(gt, n, 77, dev)
+    d_len = torch.full((n,), bench.READ_LEN, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    params = pb.default_params(min_align=bench.MIN_ALIGN, pair_flag=1, min_dist=bench.MIN_DIST, max_dist=bench.MAX_DIST)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PEMAP_EXACT", mode)
+        mapper = pb.PEMapper.from_genome([genome], params)
+        m1 = torch.zeros(n, dtype=torch.int32, device=dev)
+        m2 = torch.zeros(n, dtype=torch.int32, device=dev)
+        ty = torch.zeros(n, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        mapper.map_device(n, d_r1.data_ptr(), d_len.data_ptr(), d_r2.data_ptr(), d_len.data_ptr(), bench.STRIDE,
+                          bench.READ_LEN, m1.data_ptr(), m2.data_ptr(), ty.data_ptr())
+        rec, ins = mapper.finish()
+        st = mapper.stats()
+        out[mode] = (m1.cpu().numpy(), m2.cpu().numpy(), ty.cpu().numpy(), hashlib.sha256(rec.tobytes()).hexdigest(),
+                     rec.shape[0], hashlib.sha256(repr(sorted(ins)).encode()).hexdigest(), len(ins), st)
+        mapper.close()
+    a, b = out["0"], out["1"]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[4] == b[4] and a[3] == b[3], "pileup records differ between the integer and the exact path"
+    assert a[6] == b[6] and a[5] == b[5], "insertion strings differ between the integer and the exact path"
+    # mass conservation: every counted base / deletion comes from a mapped read-mate, at most len per mate
+    mapped = int((a[0] != 0).sum() + (a[1] != 0).sum())
+    assert mapped > 0.99 * 2 * n
+    assert a[7]["diag_traced"] > 0 and a[7]["exact_traced"] < 0.1 * mapped
+
+
 def test_contig_count_quirk_is_refused():
     """2..7 contigs: find_chrom reads out of bounds in the reference; we refuse instead of guessing."""
     from pecaller_b200 import synth
