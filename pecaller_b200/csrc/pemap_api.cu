@@ -966,9 +966,7 @@ int pemap_init_from_genome(pemap_t** out, const char* genome, const int64_t* con
                                                                          p->is_bisulfite, d_key, d_val, d_flag);
   void* tmp = nullptr;
   size_t tmp_bytes = 0, need = 0;
-  // chunked select/sort calls keep every CUB problem size below 2^31 items
-  if (gs >= 0x7FFFFFFFull) return fail(h, PEMAP_ERR_UNSUPPORTED, "device index build is limited to genomes < 2^31 bases; use pemap_init");
-  const int n_items = (int)gs;
+  const long long n_items = (long long)gs;  // CUB takes 64-bit item counts: genomes up to the 2^32 coordinate limit
   cub::DeviceSelect::Flagged(nullptr, need, d_key, d_flag, d_key2, d_nsel, n_items, h->stream);
   tmp_bytes = need;
   cub::DeviceRadixSort::SortPairs(nullptr, need, d_key2, d_key, d_val2, d_val, n_items, 0, 32, h->stream);
@@ -983,7 +981,7 @@ int pemap_init_from_genome(pemap_t** out, const char* genome, const int64_t* con
   CK(cudaStreamSynchronize(h->stream));
   h->n_mers = nsel;
   need = tmp_bytes;
-  CK(cub::DeviceRadixSort::SortPairs(tmp, need, d_key2, d_key, d_val2, d_val, (int)nsel, 0, 32, h->stream));
+  CK(cub::DeviceRadixSort::SortPairs(tmp, need, d_key2, d_key, d_val2, d_val, (long long)nsel, 0, 32, h->stream));
   // d_key = sorted k-mers, d_val = positions grouped by k-mer (= .mdx)
   const size_t idx_words = ((size_t)1 << 32) + 1;
   CK(cudaMalloc(&h->d_pos_index, idx_words * 4));
