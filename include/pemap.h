@@ -163,6 +163,13 @@ int pemap_reset_counts(pemap_t *h);
    Insertions stay per shard: each rank's pemap_finish returns its own. */
 int pemap_counts_device(pemap_t *h, void **d_counts, uint64_t *n_words);
 
+/* Single-process multi-GPU hosts (one pemap_t per GPU, e.g. one submitting thread each): add the pileup counters of
+   `src` (another GPU of the same box) into `dst` with one kernel on dst's device that reads src's array through
+   NVLink peer memory; src's counters are left unchanged.  Replaces what the reference gets for free from its shared
+   all_base_list (pemapper.c:1752-1965: every worker thread increments the same array).  Call before
+   pemap_finish(dst); insertion strings stay with the handle that produced them. */
+int pemap_reduce_counts_peer(pemap_t *dst, pemap_t *src);
+
 /* The CUDA stream (cudaStream_t as void*) all of this handle's work is issued on, so that a caller can bracket
    calls with its own events. */
 int pemap_stream(pemap_t *h, void **stream);

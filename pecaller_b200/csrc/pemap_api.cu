@@ -26,6 +26,7 @@
 namespace {
 
 constexpr int kSeedWarps = 4;
+constexpr int kMaxDev = 16;  // per-device caches of launch configurations
 constexpr uint64_t kInsCapDefault = 256ull << 20;
 
 struct Timer {
@@ -377,7 +378,8 @@ int one_wave_grid(pemap_ctx* h, K kernel, int block, size_t dyn) {
 template <int G, int WD, int MODE>
 void launch_sw(pemap_ctx* h, const pm::SwArgs& a) {
   const size_t dyn = MODE == 2 ? pm::trace_band_bytes<G, WD>() : 0;
-  static int grid = 0;  // per instantiation
+  static int grids[kMaxDev] = {};  // per instantiation and device (function attributes are per device)
+  int& grid = grids[h->device % kMaxDev];
   if (!grid) {
     if (MODE == 2) cudaFuncSetAttribute(pm::k_sw_fp64<G, WD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     grid = one_wave_grid(h, pm::k_sw_fp64<G, WD, MODE>, 128, dyn);
@@ -398,16 +400,18 @@ template <int G, int WD>
 void launch_trace_int(pemap_ctx* h, const pm::TraceIntArgs& a) {
   if (h->trace32) {  // one winner per sub-warp, 32-bit integers (PEMAP_TRACE32=1; kept as a cross-check)
     const size_t dyn = pm::trace_band_bytes<G, WD>();
-    static bool once = false;
-    if (!once) {
+    static int grids32[kMaxDev] = {};
+    int& grid32 = grids32[h->device % kMaxDev];
+    if (!grid32) {
       cudaFuncSetAttribute(pm::k_trace_i32<G, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-      once = true;
+      grid32 = one_wave_grid(h, pm::k_trace_i32<G, WD>, 128, dyn);
     }
-    pm::k_trace_i32<G, WD><<<h->sw_blocks, 128, dyn, h->stream>>>(a);
+    pm::k_trace_i32<G, WD><<<grid32, 128, dyn, h->stream>>>(a);
     return;
   }
   const size_t dyn = pm::trace16_band_bytes<G, WD>();
-  static int grid16 = 0;
+  static int grids16[kMaxDev] = {};
+  int& grid16 = grids16[h->device % kMaxDev];
   if (!grid16) {
     cudaFuncSetAttribute(pm::k_trace_i16<G, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     grid16 = one_wave_grid(h, pm::k_trace_i16<G, WD>, 128, dyn);
@@ -427,7 +431,8 @@ template <int G, int WD, int CMM>
 struct CmmDispatch {
   static void go(pemap_ctx* h, const pm::SwIntArgs& a, int cmm) {
     if (cmm == CMM) {
-      static int grid = 0;
+      static int grids[kMaxDev] = {};
+      int& grid = grids[h->device % kMaxDev];
       if (!grid) grid = one_wave_grid(h, pm::k_sw_i16<G, WD, CMM>, 128, 0);
       pm::k_sw_i16<G, WD, CMM><<<grid, 128, 0, h->stream>>>(a);
     }
@@ -437,7 +442,8 @@ struct CmmDispatch {
 template <int G, int WD>
 struct CmmDispatch<G, WD, -1> {
   static void go(pemap_ctx* h, const pm::SwIntArgs& a, int) {
-    static int grid = 0;
+    static int grids[kMaxDev] = {};
+    int& grid = grids[h->device % kMaxDev];
     if (!grid) grid = one_wave_grid(h, pm::k_sw_i16<G, WD, -1>, 128, 0);
     pm::k_sw_i16<G, WD, -1><<<grid, 128, 0, h->stream>>>(a);
   }
@@ -487,8 +493,9 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   sa.p = h->dp;
   sa.p.pair_flag = paired ? 1 : 0;
   const int work = paired ? 2 * n : n;
-  static int seed_wave[2] = {0, 0};  // one resident wave of the persistent seed kernel, per variant
+  static int seed_waves[kMaxDev][2] = {};  // one resident wave of the persistent seed kernel, per device and variant
   const int sv = h->d_filter ? 1 : 0;
+  int* seed_wave = seed_waves[h->device % kMaxDev];
   if (!seed_wave[sv]) {
     int per_sm = 0;
     cudaError_t oe = sv ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_seed_chain<kSeedWarps, true>, kSeedWarps * 32, 0)
@@ -1185,6 +1192,29 @@ int pemap_counts_device(pemap_t* h, void** d_counts, uint64_t* n_words) {
   return PEMAP_OK;
 }
 
+int pemap_reduce_counts_peer(pemap_t* h, pemap_t* src) {
+  if (!h || !src) return PEMAP_ERR_ARG;
+  if (h->genome_size != src->genome_size) return fail(h, PEMAP_ERR_ARG, "handles index different genomes");
+  CK(cudaSetDevice(src->device));
+  CK(cudaStreamSynchronize(src->stream));
+  CK(cudaSetDevice(h->device));
+  const uint64_t n_words = h->genome_size * 6;
+  if (h->device != src->device) {
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, h->device, src->device));
+    if (!can) return fail(h, PEMAP_ERR_UNSUPPORTED, "no peer access between the two devices");
+    cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+      return fail(h, PEMAP_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+  pm::k_add_peer_counts<<<h->sm_count * 8, 256, 0, h->stream>>>(h->d_counts, src->d_counts, n_words);
+  h->stats.launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return PEMAP_OK;
+}
+
 int pemap_stream(pemap_t* h, void** stream) {
   if (!h || !stream) return PEMAP_ERR_ARG;
   *stream = (void*)h->stream;
@@ -1237,6 +1267,7 @@ void pemap_destroy(pemap_t* h) {
   if (h->stream) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->d_filter) cudaCtxResetPersistingL2Cache();  // give the persisting carve-out back
     void* dev[] = {h->d_filter, h->d_pos_index, h->d_mers, h->d_genome, h->d_cstart, h->d_border, h->d_counts, h->d_ins, h->d_ins_cursor,
                    h->d_tasks, h->d_results, h->d_cursors,
                    h->d_cand_base, h->d_cand_n, h->d_winners, h->d_det_best, h->d_det_orient,

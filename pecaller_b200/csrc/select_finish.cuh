@@ -236,6 +236,19 @@ __global__ void __launch_bounds__(PM_COMPACT_BLOCK) k_compact_write(const uint32
   }
 }
 
+// counts[i] += peer[i]; `peer` is another GPU's counter array mapped through NVLink peer access (16-byte loads)
+__global__ void __launch_bounds__(256) k_add_peer_counts(uint32_t* counts, const uint32_t* peer, uint64_t n_words) {
+  const uint64_t n4 = n_words >> 2;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uint4 p = reinterpret_cast<const uint4*>(peer)[i];
+    uint4 c = reinterpret_cast<uint4*>(counts)[i];
+    c.x += p.x; c.y += p.y; c.z += p.z; c.w += p.w;
+    reinterpret_cast<uint4*>(counts)[i] = c;
+  }
+  for (uint64_t i = (n4 << 2) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) counts[i] += peer[i];
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Device index build: what index_genome_whole.c computes (169-177 codes, 248-299 rolling k-mer with N reset,
 // 213-216/271 index coordinates, 334-342 prefix table), as data-parallel passes.

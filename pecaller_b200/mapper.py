@@ -57,7 +57,7 @@ class Stats(C.Structure):
 EXPORTS = ["pemap_version", "pemap_default_params", "pemap_init", "pemap_init_from_genome", "pemap_set_params",
            "pemap_map_batch", "pemap_map_batch_rows", "pemap_map_batch_device", "pemap_keep", "pemap_get_detail",
            "pemap_get_candidates", "pemap_finish", "pemap_reset_counts", "pemap_counts_device", "pemap_get_stats",
-           "pemap_reset_stats", "pemap_stream", "pemap_index_device", "pemap_read_pos_index", "pemap_read_mers", "pemap_last_error",
+           "pemap_reset_stats", "pemap_stream", "pemap_reduce_counts_peer", "pemap_index_device", "pemap_read_pos_index", "pemap_read_mers", "pemap_last_error",
            "pemap_destroy"]
 
 _lib = None
@@ -95,6 +95,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.pemap_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.pemap_reset_stats.argtypes = [vp]
     L.pemap_stream.argtypes = [vp, C.POINTER(vp)]
+    L.pemap_reduce_counts_peer.argtypes = [vp, vp]
     L.pemap_index_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.pemap_read_pos_index.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
     L.pemap_read_mers.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
@@ -227,6 +228,10 @@ class PEMapper:
         ty = np.zeros(n, dtype=np.int32)
         self._ck(self._L.pemap_map_batch(self._h, n, a1, l1, a2, l2, m1.ctypes.data, m2.ctypes.data, ty.ctypes.data))
         return m1, m2, ty
+
+    def reduce_counts_from(self, other: "PEMapper"):
+        """Add another handle's (another GPU's) pileup counters into this one over NVLink peer memory."""
+        self._ck(self._L.pemap_reduce_counts_peer(self._h, other._h))
 
     def map_device(self, n, d_r1, d_l1, d_r2, d_l2, stride, max_len, d_m1, d_m2, d_ty):
         """All arguments are raw device pointers (ints)."""

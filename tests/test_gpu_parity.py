@@ -292,6 +292,36 @@ def test_integer_path_equals_exact_path_at_scale(monkeypatch):
     assert a[7]["diag_traced"] > 0 and a[7]["exact_traced"] < 0.1 * mapped
 
 
+def test_peer_reduce_single_process(get_fixture):
+    """C-ABI path for single-process multi-GPU hosts: two handles on two GPUs, batches split between them,
+    pemap_reduce_counts_peer over NVLink peer memory, then finish on the first == everything on one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    fx = get_fixture("pe150")
+    run = fx.runs[0]
+    n = 20000
+    kw = dict(min_align=run.min_align, pair_flag=1, min_dist=run.min_dist, max_dist=run.max_dist)
+    a = pb.PEMapper.from_genome(fx.genome, device=0)
+    b = pb.PEMapper.from_genome(fx.genome, device=1)
+    one = pb.PEMapper.from_genome(fx.genome, device=0)
+    for m in (a, b, one):
+        m.set_params(**kw)
+    ra = a.map_batch(run.reads1[:n // 2], run.reads2[:n // 2])
+    rb = b.map_batch(run.reads1[n // 2:n], run.reads2[n // 2:n])
+    r1 = one.map_batch(run.reads1[:n], run.reads2[:n])
+    a.reduce_counts_from(b)
+    rec, ins_a = a.finish()
+    _, ins_b = b.finish()   # b's own records are not used; its insertion strings are
+    rec1, ins1 = one.finish()
+    for k in range(3):
+        assert np.array_equal(np.concatenate([ra[k], rb[k]]), r1[k])
+    assert rec.tobytes() == rec1.tobytes()
+    assert sorted(ins_a + ins_b) == sorted(ins1)
+    for m in (a, b, one):
+        m.close()
+
+
 def test_contig_count_quirk_is_refused():
     """2..7 contigs: find_chrom reads out of bounds in the reference; we refuse instead of guessing."""
     from pecaller_b200 import synth
