@@ -6,13 +6,17 @@
  *   pemapper_gpu out sdx s|sa file1 is_bisulfite min_match max_threads max_reads
  *   pemapper_gpu out sdx p|pa file1 file2 max_dist min_dist is_bisulfite min_match max_threads max_reads
  *
- * max_threads is accepted and ignored (one submitting thread, one GPU).  Environment:
- *   PEMAP_DEVICE        GPU ordinal (default 0)
+ * max_threads is accepted and ignored: the reader thread fills batches, one submitting thread per GPU maps them.
+ * Environment:
+ *   PEMAP_GPUS          number of GPUs of this box to use (default 1): batch b goes to GPU b mod N, every GPU keeps
+ *                       its own counters, and pemap_reduce_counts_peer sums them onto GPU 0 over NVLink at the end
+ *   PEMAP_DEVICE        first GPU ordinal (default 0)
  *   PEMAP_DEVICE_INDEX  1 = rebuild pos_index/mers on the GPU from .seq/.sdx instead of loading .idx/.mdx
  *   PEMAP_BATCH         reads per pemap_map_batch_rows call (default 1,000,000; results do not depend on it)
  * Written from scratch; what must be byte-compatible (file formats, summary text) cites the reference line.
  */
 #include <ctype.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -156,6 +160,90 @@ static void gz_read_all(gzFile f, void *dst, size_t n) {
   if (done != n) die(" Short read on a compressed index file ");
 }
 
+/* ---- one submitting thread per GPU (replaces the reference's pool of map_everything threads, 677-702) ---- */
+typedef struct {
+  pemap_t *h;
+  int paired;
+  long cap, filled, first; /* batch capacity, reads in the batch, index of its first read in the file */
+  char *rows1, *rows2;
+  int *len1, *len2;
+  uint32_t *bm1, *bm2;
+  int *btype;
+  uint32_t *maps1, *maps2;       /* shared per-file arrays; batches write disjoint ranges */
+  long max_dist;
+  long mate_counts[9], total_reads, total_bases, total_dist, no_dists; /* per worker, summed at the end */
+  pthread_t thread;
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  int state; /* 0 idle (buffers free), 1 batch ready, 2 quit */
+} worker_t;
+
+static void worker_epilogue(worker_t *w) { /* batch epilogue, 1238-1265 */
+  for (long j = 0; j < w->filled; j++) {
+    w->mate_counts[w->btype[j]]++;
+    w->maps1[w->first + j] = w->bm1[j];
+    if (w->bm1[j]) {
+      w->total_reads++;
+      w->total_bases += w->len1[j];
+      if (w->bm2[j]) {
+        w->total_reads++;
+        w->total_bases += w->len2[j];
+        long test = (long)(uint32_t)(w->bm1[j] - w->bm2[j]); /* labs() of an unsigned difference (1250) */
+        w->maps2[w->first + j] = w->bm2[j];
+        if (test < w->max_dist * 4) {
+          w->total_dist += test;
+          w->no_dists++;
+        }
+      }
+    } else if (w->bm2[j]) {
+      w->total_reads++;
+      w->total_bases += w->len2[j];
+      w->maps2[w->first + j] = w->bm2[j];
+    }
+  }
+}
+
+static void *worker_main(void *arg) {
+  worker_t *w = arg;
+  for (;;) {
+    pthread_mutex_lock(&w->mu);
+    while (w->state == 0) pthread_cond_wait(&w->cv, &w->mu);
+    const int st = w->state;
+    pthread_mutex_unlock(&w->mu);
+    if (st == 2) return NULL;
+    int rc = pemap_map_batch_rows(w->h, (int)w->filled, w->rows1, w->len1, w->rows2, w->paired ? w->len2 : NULL, ROW, w->bm1,
+                                  w->bm2, w->btype);
+    if (rc) {
+      printf("\n pemap_map_batch failed: %s \n", pemap_last_error(w->h));
+      exit(1);
+    }
+    worker_epilogue(w);
+    pthread_mutex_lock(&w->mu);
+    w->state = 0;
+    pthread_cond_broadcast(&w->cv);
+    pthread_mutex_unlock(&w->mu);
+  }
+}
+
+static void worker_wait_idle(worker_t *w) {
+  pthread_mutex_lock(&w->mu);
+  while (w->state != 0) pthread_cond_wait(&w->cv, &w->mu);
+  pthread_mutex_unlock(&w->mu);
+}
+
+static void worker_submit(worker_t *w, int state) {
+  pthread_mutex_lock(&w->mu);
+  w->state = state;
+  pthread_cond_broadcast(&w->cv);
+  pthread_mutex_unlock(&w->mu);
+}
+
+static int cmp_ins(const void *a, const void *b) {
+  const pemap_insertion *x = a, *y = b;
+  if (x->pos != y->pos) return x->pos < y->pos ? -1 : 1;
+  return strcmp(x->seq, y->seq);
+}
+
 int main(int argc, char **argv) {
   if (argc < 4) die("Usage: pemapper_gpu out_file sdx_file [s,sa,p,pa] ... (same arguments as pemapper)");
   const char mode = (char)toupper(argv[3][0]), arr = (char)toupper(argv[3][1]);
@@ -232,12 +320,18 @@ int main(int argc, char **argv) {
   prm.min_dist = min_dist;
   prm.max_dist = max_dist;
   const int device = getenv("PEMAP_DEVICE") ? atoi(getenv("PEMAP_DEVICE")) : 0;
-  pemap_t *h = NULL;
-  int rc;
+  int n_gpus = getenv("PEMAP_GPUS") ? atoi(getenv("PEMAP_GPUS")) : 1;
+  if (n_gpus < 1) n_gpus = 1;
+  if (n_gpus > 16) n_gpus = 16;
+  pemap_t *hs[16] = {NULL};
+  int rc = 0;
   if (getenv("PEMAP_DEVICE_INDEX") && atoi(getenv("PEMAP_DEVICE_INDEX"))) {
     int64_t *lens = malloc(sizeof(int64_t) * (size_t)sdx.n);
     for (int i = 0; i < sdx.n; i++) lens[i] = (int64_t)(sdx.starts[i + 1] - sdx.starts[i]) + 15;
-    rc = pemap_init_from_genome(&h, genome, lens, sdx.n, &prm, device);
+    for (int g = 0; g < n_gpus && !rc; g++) {
+      rc = pemap_init_from_genome(&hs[g], genome, lens, sdx.n, &prm, device + g);
+      if (rc) printf("\n pemap_init failed on GPU %d: %s \n", device + g, pemap_last_error(hs[g]));
+    }
     free(lens);
   } else { /* init_index_buffer 2129-2155 */
     const size_t words = ((size_t)1 << 32) + 1;
@@ -257,23 +351,44 @@ int main(int argc, char **argv) {
     if (!mf || fread(mers, 4, n_mers, mf) != n_mers) die(" Could not read the .mdx file ");
     fclose(mf);
     pemap_index ix = {pos_index, mers, n_mers, genome, genome_size, sdx.starts, sdx.n};
-    rc = pemap_init(&h, &ix, &prm, device);
+    for (int g = 0; g < n_gpus && !rc; g++) {
+      rc = pemap_init(&hs[g], &ix, &prm, device + g);
+      if (rc) printf("\n pemap_init failed on GPU %d: %s \n", device + g, pemap_last_error(hs[g]));
+    }
     free(pos_index);
     free(mers);
   }
-  if (rc) {
-    printf("\n pemap_init failed: %s \n", pemap_last_error(h));
-    exit(1);
-  }
+  if (rc) exit(1);
+  pemap_t *h = hs[0];
 
   const long batch_cap = getenv("PEMAP_BATCH") ? atol(getenv("PEMAP_BATCH")) : 1000000;
-  char *rows1 = malloc((size_t)batch_cap * ROW), *rows2 = paired ? malloc((size_t)batch_cap * ROW) : NULL;
-  int *len1 = malloc(sizeof(int) * (size_t)batch_cap), *len2 = malloc(sizeof(int) * (size_t)batch_cap);
-  uint32_t *bm1 = malloc(4 * (size_t)batch_cap), *bm2 = malloc(4 * (size_t)batch_cap);
-  int *btype = malloc(sizeof(int) * (size_t)batch_cap);
   uint32_t *maps1 = calloc((size_t)max_reads + 1, 4), *maps2 = calloc((size_t)max_reads + 1, 4);
   if (!maps1 || !maps2) die(" Could not allocate space for mapping position of reads ");
   long mate_counts[9] = {0}, total_reads = 0, total_bases = 0, total_dist = 0, no_dists = 0, tot_pairs = 0;
+  worker_t *ws = calloc((size_t)n_gpus, sizeof(worker_t));
+  for (int g = 0; g < n_gpus; g++) {
+    worker_t *w = &ws[g];
+    w->h = hs[g];
+    w->paired = paired;
+    w->cap = batch_cap;
+    w->rows1 = malloc((size_t)batch_cap * ROW);
+    w->rows2 = paired ? malloc((size_t)batch_cap * ROW) : NULL;
+    w->len1 = malloc(sizeof(int) * (size_t)batch_cap);
+    w->len2 = malloc(sizeof(int) * (size_t)batch_cap);
+    w->bm1 = malloc(4 * (size_t)batch_cap);
+    w->bm2 = malloc(4 * (size_t)batch_cap);
+    w->btype = malloc(sizeof(int) * (size_t)batch_cap);
+    if (!w->rows1 || (paired && !w->rows2) || !w->len1 || !w->len2 || !w->bm1 || !w->bm2 || !w->btype)
+      die(" Could not allocate the batch buffers ");
+    w->maps1 = maps1;
+    w->maps2 = maps2;
+    w->max_dist = max_dist;
+    pthread_mutex_init(&w->mu, NULL);
+    pthread_cond_init(&w->cv, NULL);
+    w->state = 0;
+    if (pthread_create(&w->thread, NULL, worker_main, w)) die(" Could not start a submitting thread ");
+  }
+  long batch_no = 0;
 
   printf("\n About to start mapping everything \n\n");
   for (int fi = 0; fi < n_files; fi++) {
@@ -288,7 +403,11 @@ int main(int argc, char **argv) {
     }
     long current = 0, filled = 0, batch_first = 0;
     int go = s1 != NULL;
+    worker_t *w = &ws[batch_no % n_gpus];
+    worker_wait_idle(w);
     while (go || filled) {
+      char *rows1 = w->rows1, *rows2 = w->rows2;
+      int *len1 = w->len1, *len2 = w->len2;
       const int have = go && s1 && (int)strlen(s1) > 12 && (!paired || s2); /* 663 */
       if (have) {
         const int l1 = (int)strlen(s1), l2 = paired ? (int)strlen(s2) : 0;
@@ -313,38 +432,18 @@ int main(int argc, char **argv) {
       } else
         go = 0;
       if (filled == batch_cap || (!go && filled)) {
-        rc = pemap_map_batch_rows(h, (int)filled, rows1, len1, rows2, paired ? len2 : NULL, ROW, bm1, bm2, btype);
-        if (rc) {
-          printf("\n pemap_map_batch failed: %s \n", pemap_last_error(h));
-          exit(1);
-        }
-        for (long j = 0; j < filled; j++) { /* batch epilogue, 1238-1265 */
-          mate_counts[btype[j]]++;
-          maps1[batch_first + j] = bm1[j];
-          if (bm1[j]) {
-            total_reads++;
-            total_bases += len1[j];
-            if (bm2[j]) {
-              total_reads++;
-              total_bases += len2[j];
-              long test = (long)(uint32_t)(bm1[j] - bm2[j]); /* labs() of an unsigned difference (1250) */
-              maps2[batch_first + j] = bm2[j];
-              if (test < (long)max_dist * 4) {
-                total_dist += test;
-                no_dists++;
-              }
-            }
-          } else if (bm2[j]) {
-            total_reads++;
-            total_bases += len2[j];
-            maps2[batch_first + j] = bm2[j];
-          }
-        }
+        w->filled = filled;
+        w->first = batch_first;
+        worker_submit(w, 1);
         batch_first += filled;
         filled = 0;
-        printf("\n We have read %ld reads and %ld have come back from successful mapping\n\n", current, total_reads);
+        printf("\n We have read %ld reads \n\n", current);
+        batch_no++;
+        w = &ws[batch_no % n_gpus];
+        worker_wait_idle(w); /* its previous batch has been mapped and booked: the buffers are free */
       }
     }
+    for (int g = 0; g < n_gpus; g++) worker_wait_idle(&ws[g]); /* the .mfile arrays are complete (768-774) */
     printf("\n Made it out alive, and have started cleanup \n\n");
     snprintf(path, sizeof path, "%s.mfile", files1[fi]); /* 775-781 */
     FILE *mf = fopen(path, "wb");
@@ -363,6 +462,17 @@ int main(int argc, char **argv) {
     tot_pairs += current;
   }
 
+  for (int g = 0; g < n_gpus; g++) {
+    worker_t *w = &ws[g];
+    worker_wait_idle(w);
+    worker_submit(w, 2);
+    pthread_join(w->thread, NULL);
+    for (int i = 0; i < 9; i++) mate_counts[i] += w->mate_counts[i];
+    total_reads += w->total_reads;
+    total_bases += w->total_bases;
+    total_dist += w->total_dist;
+    no_dists += w->no_dists;
+  }
   const char *pn[9] = {"Unique Mate-Paired", "Unique Mate-Paired with slip", "Unique Single End", "Unique Mis-size",
                        "Non-Unique Mate-Paired", "Non-Unique Mis-size", "Fragment Mismatch", "Non-unique with no map",
                        "Neither Map"}; /* 567-590 */
@@ -385,10 +495,34 @@ int main(int argc, char **argv) {
   const pemap_record *rec;
   const pemap_insertion *ins;
   uint64_t n_rec, n_ins;
+  pemap_insertion *all_ins = NULL; /* insertion strings of every GPU, sorted by site */
+  uint64_t n_all = 0;
+  for (int g = 1; g < n_gpus; g++) { /* every GPU's counters onto GPU 0 over NVLink; its insertion strings to the host */
+    const pemap_record *r2;
+    const pemap_insertion *i2;
+    uint64_t nr2, ni2;
+    rc = pemap_reduce_counts_peer(hs[0], hs[g]);
+    if (!rc) rc = pemap_finish(hs[g], &r2, &nr2, &i2, &ni2);
+    if (rc) {
+      printf("\n reducing GPU %d failed: %s \n", device + g, pemap_last_error(rc ? hs[g] : hs[0]));
+      exit(1);
+    }
+    all_ins = realloc(all_ins, (size_t)(n_all + ni2 + 1) * sizeof(pemap_insertion));
+    memcpy(all_ins + n_all, i2, (size_t)ni2 * sizeof(pemap_insertion));
+    n_all += ni2;
+  }
   rc = pemap_finish(h, &rec, &n_rec, &ins, &n_ins);
   if (rc) {
     printf("\n pemap_finish failed: %s \n", pemap_last_error(h));
     exit(1);
+  }
+  if (n_gpus > 1) {
+    all_ins = realloc(all_ins, (size_t)(n_all + n_ins + 1) * sizeof(pemap_insertion));
+    memcpy(all_ins + n_all, ins, (size_t)n_ins * sizeof(pemap_insertion));
+    n_all += n_ins;
+    qsort(all_ins, (size_t)n_all, sizeof(pemap_insertion), cmp_ins);
+    ins = all_ins;
+    n_ins = n_all;
   }
   gzprintf(indel, "Fragment\tPositions\tReference Base\tTotal Coverage\tReference Reads\tNo Deletions\tNo Insertions\tInsertion Sequence"); /* 819-820 */
   uint32_t *padded = calloc((size_t)sdx.n + 16, 4);
@@ -429,6 +563,6 @@ int main(int argc, char **argv) {
     fprintf(f, "\n");
   }
   fclose(summary);
-  pemap_destroy(h);
+  for (int g = 0; g < n_gpus; g++) pemap_destroy(hs[g]);
   return 0;
 }

@@ -31,10 +31,16 @@ def _normalise_indel(path):
     return "\n".join(lines)
 
 
-@pytest.mark.parametrize("name", ["tiny", "edge9"])
-def test_cli_files_match_reference(name, get_fixture, oracle_built, tmp_path):
+@pytest.mark.parametrize("name,gpus", [("tiny", 1), ("edge9", 1), ("edge9", 2)])
+def test_cli_files_match_reference(name, gpus, get_fixture, oracle_built, tmp_path):
+    """gpus == 2: PEMAP_GPUS=2 with small batches - one submitting thread per GPU, batches alternate between the GPUs,
+    counters summed over NVLink peer memory (pemap_reduce_counts_peer); the files must not change."""
     if not os.path.exists(CLI):
         pytest.fail("C host not built: run __graft_entry__.build()")
+    if gpus > 1:
+        import torch
+        if torch.cuda.device_count() < gpus:
+            pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (gpus, gpus))
     fx = get_fixture(name)
     work = str(tmp_path)
     oracle = ol.Oracle(fx.genome)
@@ -42,6 +48,8 @@ def test_cli_files_match_reference(name, get_fixture, oracle_built, tmp_path):
     oracle.close()
     assert open(os.path.join(work, "g.sdx")).read() == gio.index_meta(name)["sdx"]
     env = dict(os.environ, PEMAP_DEVICE_INDEX="1")
+    if gpus > 1:
+        env.update(PEMAP_GPUS=str(gpus), PEMAP_BATCH="777")
     checked = 0
     for run in fx.runs:
         if not gio.have(name, run.name):
