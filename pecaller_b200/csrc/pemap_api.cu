@@ -232,7 +232,7 @@ int open_device(pemap_ctx* h, int device) {
 }
 
 int alloc_chunk_buffers(pemap_ctx* h) {
-  int chunk = 1 << 17;
+  int chunk = 1 << 19;  // reads (pairs) per pass of the kernel chain: larger chunks shorten the persistent kernels' tails
   if (const char* s = getenv("PEMAP_CHUNK")) chunk = std::max(1024, atoi(s));
   h->chunk = chunk;
   h->stride_cap = PM_DP_MAX;
@@ -467,7 +467,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   const bool paired = h->params.pair_flag && d_r2;
   const bool exact = h->exact || (h->keep & PEMAP_KEEP_DETAIL) || h->params.match_bonus != 1.0;
   CK(cudaMemsetAsync(h->d_cursors, 0, 16, h->stream));
-  CK(cudaMemsetAsync(h->d_cursors + 6, 0, 12, h->stream));
+  CK(cudaMemsetAsync(h->d_cursors + 6, 0, 40, h->stream));  // [6..8] lists, [9..15] work counters of the persistent kernels
   CK(cudaEventRecord(ev[0], h->stream));
   pm::SeedArgs sa;
   sa.pos_index = h->d_pos_index;
@@ -517,6 +517,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   wa.winners = h->d_winners;
   wa.list_mode = 0;
   wa.n_items = h->d_cursors;
+  wa.work = h->d_cursors + 9;
   wa.reads[0] = d_r1;
   wa.reads[1] = d_r2;
   wa.len[0] = d_l1;
@@ -568,6 +569,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     ia.tasks = h->d_tasks;
     ia.results = h->d_ires;
     ia.n_items = h->d_cursors;
+    ia.work = h->d_cursors + 10;
     ia.reads[0] = d_r1;
     ia.reads[1] = d_r2;
     ia.len[0] = d_l1;
@@ -606,6 +608,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     ra.winners = h->d_replay_tasks;
     ra.list_mode = 1;
     ra.n_items = h->d_cursors + 3;
+    ra.work = h->d_cursors + 11;
     dispatch_sw<0>(h, ra, max_len);
     se.read_list = h->d_replay_reads;
     se.n_list = h->d_cursors + 2;
@@ -636,6 +639,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     ta.results = h->d_results;
     ta.winners = h->d_winners;
     ta.n_items = h->d_cursors + 1;
+    ta.work = h->d_cursors + 12;
     ta.exact_winners = h->d_exact_winners;
     ta.exact_cursor = h->d_cursors + 7;
     ta.reads[0] = d_r1;
@@ -652,14 +656,17 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     CK(cudaEventRecord(ev[6], h->stream));
     wa.winners = h->d_exact_winners;
     wa.n_items = h->d_cursors + 7;
+    wa.work = h->d_cursors + 13;
   } else {
     wa.n_items = h->d_cursors + 1;
+    wa.work = h->d_cursors + 13;
     CK(cudaEventRecord(ev[5], h->stream));
     CK(cudaEventRecord(ev[6], h->stream));
   }
   dispatch_sw<2>(h, wa, max_len);  // exact traceback, decision band in shared memory
   wa.winners = h->d_oob_winners;   // walks that left the band (long indels): every lane's decisions in global memory
   wa.n_items = h->d_cursors + 8;
+  wa.work = h->d_cursors + 14;
   dispatch_sw<1>(h, wa, max_len);
   CK(cudaEventRecord(ev[4], h->stream));
   CK(cudaGetLastError());

@@ -91,6 +91,30 @@ __host__ __device__ __forceinline__ int find_chrom(const uint32_t* pos, int n_co
   return first;
 }
 
+// Dynamic work distribution for the persistent sub-warp kernels: the group's lane 0 takes the next item from a global
+// counter and broadcasts it.  Items differ in cost (window length, walk length, tie certification), and with a few
+// items per group a static grid-stride split leaves most of the last wave idle.
+template <int G>
+__device__ __forceinline__ uint32_t next_work_item(uint32_t* counter, unsigned gmask, int gl) {
+  uint32_t v = 0;
+  if (gl == 0) v = atomicAdd(counter, 1u);
+  return __shfl_sync(gmask, v, 0, G);
+}
+
+// Same, for kernels whose groups end every item with a one-lane phase (the traceback walk): the sub-warps of a warp
+// take consecutive items together, so that they stay in lock step through the wavefront (a warp whose sub-warps
+// sit in different phases issues each phase for half of its lanes only).
+// *first = the warp's first item (warp-uniform: the loop ends for the whole warp when it passes the end).
+template <int G>
+__device__ __forceinline__ uint32_t next_work_item_warp(uint32_t* counter, uint32_t* first) {
+  __syncwarp();
+  uint32_t v = 0;
+  if ((threadIdx.x & 31) == 0) v = atomicAdd(counter, 32u / G);
+  v = __shfl_sync(0xFFFFFFFFu, v, 0);
+  *first = v;
+  return v + (threadIdx.x & 31) / G;
+}
+
 // window set-up of map_everything (1052-1058): returns the contig, fills start (real coordinate) and blen
 __host__ __device__ __forceinline__ int candidate_window(const uint32_t* cstart, int n_contigs, uint32_t spot, int len,
                                                           int slop, uint32_t* start, int32_t* blen) {

@@ -32,6 +32,7 @@ struct SwIntArgs {
   const Task* tasks;
   ITaskResult* results;
   const uint32_t* n_items;
+  uint32_t* work;   // zeroed per launch: next pair to score
   const char* reads[2];
   const int* len[2];
   int stride;
@@ -81,13 +82,14 @@ __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
   const int tid = threadIdx.x, grp = tid / G, gl = tid % G;
   const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) / G * G));
   const uint32_t n_items = *a.n_items, n_pairs = (n_items + 1) >> 1;
-  const uint32_t ggid = blockIdx.x * GPB + grp, n_groups = gridDim.x * GPB;
   uint32_t* win = s_win[grp];
   uint32_t* last = s_last[CMM >= 0 ? grp : 0];
   constexpr uint32_t K1 = 0x00010001u, K12 = 0x000C000Cu, NEG72 = 0xFFB8FFB8u;
   constexpr uint32_t BIASP = (PM_IBIAS << 16) | PM_IBIAS;
 
-  for (uint32_t pair = ggid; pair < n_pairs; pair += n_groups) {
+  for (;;) {
+    const uint32_t pair = next_work_item<G>(a.work, gmask, gl);
+    if (pair >= n_pairs) break;
     const uint32_t idA = 2 * pair, idB = (2 * pair + 1 < n_items) ? 2 * pair + 1 : 2 * pair;
     const Task tA = a.tasks[idA], tB = a.tasks[idB];
     const int orA = (int)(tA.rm >> 31), orB = (int)(tB.rm >> 31);

@@ -26,6 +26,7 @@ struct SwArgs {
   const Winner* winners;       // trace kernels: the winners; score kernel with list_mode: the tasks to (re)score
   int list_mode;
   const uint32_t* n_items;     // device counter: number of tasks (score) or winners (trace)
+  uint32_t* work;              // zeroed per launch: next item
   Winner* oob_winners;         // MODE 2: winners whose walk left the shared-memory band
   uint32_t* oob_cursor;
   const char* reads[2];
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
   const int grp = tid / G, gl = tid % G;
   const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) / G * G));
   const uint32_t n_items = *a.n_items;
-  const uint32_t ggid = blockIdx.x * GROUPS_PER_BLOCK + grp, n_groups = gridDim.x * GROUPS_PER_BLOCK;
+  const uint32_t ggid = blockIdx.x * GROUPS_PER_BLOCK + grp;
   const double go = a.p.go, ge = a.p.ge, match = a.p.match, mism = a.p.mism;
   char* win = s_win[grp];
   unsigned long long* band = MODE == 2 ? s_band_d + (size_t)grp * ROWS * PM_BAND_LANES : nullptr;
@@ -65,7 +66,15 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
   PileSink sink = a.sink;
   if (TRACE) sink.pend = a.sink.pend + (size_t)ggid * PM_DP_MAX;
 
-  for (uint32_t item = ggid; item < n_items; item += n_groups) {
+  for (;;) {
+    uint32_t first = 0;
+    const uint32_t item = TRACE ? next_work_item_warp<G>(a.work, &first) : next_work_item<G>(a.work, gmask, gl);
+    if (TRACE) {
+      if (first >= n_items) break;
+      if (item >= n_items) continue;  // the warp's other sub-warp still has an item
+    } else if (item >= n_items) {
+      break;
+    }
     const uint32_t task_id = (TRACE || a.list_mode) ? a.winners[item].task : item;
     const Task tk = a.tasks[task_id];
     const int orient = (int)(tk.rm >> 31);

@@ -30,6 +30,7 @@ struct TraceIntArgs {
   const TaskResult* results;   // maxk / maxi of the winner (written by the selection kernels)
   const Winner* winners;
   const uint32_t* n_items;
+  uint32_t* work;              // zeroed per launch: next winner (pair)
   Winner* exact_winners;       // winners that need the fp64 traceback
   uint32_t* exact_cursor;
   const char* reads[2];
@@ -273,14 +274,18 @@ __global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
   const int tid = threadIdx.x, grp = tid / G, gl = tid % G;
   const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) / G * G));
   const uint32_t n_items = *a.n_items;
-  const uint32_t ggid = blockIdx.x * GPB + grp, n_groups = gridDim.x * GPB;
+  const uint32_t ggid = blockIdx.x * GPB + grp;
   unsigned char* win = s_win[grp];
   unsigned long long* band = s_band_i + (size_t)grp * ROWS * PM_BAND_LANES;
   const int bis = a.p.is_bisulfite;
   PileSink sink = a.sink;
   sink.pend = a.sink.pend + (size_t)ggid * PM_DP_MAX;
 
-  for (uint32_t item = ggid; item < n_items; item += n_groups) {
+  for (;;) {
+    uint32_t first;
+    const uint32_t item = next_work_item_warp<G>(a.work, &first);
+    if (first >= n_items) break;
+    if (item >= n_items) continue;  // the warp's other sub-warp still has an item
     const uint32_t task_id = a.winners[item].task;
     const Task tk = a.tasks[task_id];
     const TaskResult res = a.results[task_id];
@@ -438,7 +443,7 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
   const int tid = threadIdx.x, grp = tid / G, gl = tid % G;
   const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) / G * G));
   const uint32_t n_items = *a.n_items, n_pairs = (n_items + 1) >> 1;
-  const uint32_t ggid = blockIdx.x * GPB + grp, n_groups = gridDim.x * GPB;
+  const uint32_t ggid = blockIdx.x * GPB + grp;
   unsigned char* win = s_win[grp];
   uint32_t* band = s_band16 + (size_t)grp * ROWS * PM_BAND16_LANES * 6;
   const int bis = a.p.is_bisulfite;
@@ -449,7 +454,11 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
   PileSink sink = a.sink;
   sink.pend = a.sink.pend + ((size_t)ggid * 2 + (gl & 1)) * PM_DP_MAX;  // lanes 0 and 1 walk concurrently
 
-  for (uint32_t pair = ggid; pair < n_pairs; pair += n_groups) {
+  for (;;) {
+    uint32_t first;
+    const uint32_t pair = next_work_item_warp<G>(a.work, &first);
+    if (first >= n_pairs) break;
+    if (pair >= n_pairs) continue;  // the warp's other sub-warp still has a pair
     const uint32_t itA = 2 * pair, itB = (2 * pair + 1 < n_items) ? 2 * pair + 1 : 2 * pair;
     const uint32_t idA = a.winners[itA].task, idB = a.winners[itB].task;
     const Task tA = a.tasks[idA], tB = a.tasks[idB];

@@ -75,6 +75,10 @@ def ctx_cache():
 
 def _ctx(cache, fx):
     if fx.name not in cache:
+        for name in list(cache):  # one index (16 GiB pos_index + chunk buffers, ~35 GB of HBM) at a time
+            m, o = cache.pop(name)
+            m.close()
+            o.close()
         cache[fx.name] = (pb.PEMapper.from_genome(fx.genome), ol.Oracle(fx.genome))
     return cache[fx.name]
 
