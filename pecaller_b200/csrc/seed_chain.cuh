@@ -387,23 +387,45 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
           const int off_loop = (loop < total_cuts) ? 16 * loop : len - 16;
           const int na = (int)cnts[loop];
           const uint32_t* anchors = na <= PM_SLIST ? shead[loop] : slists + (size_t)loop * PM_SEG_CAP;
-          for (int i0 = 0; i0 < na && !done; i0 += 32) {
-            const int i = i0 + lane;
-            const bool valid = i < na;
-            const uint32_t av = valid ? anchors[i] : 0u;
+          const int mo = (a.p.idepth - 4 > 2) ? a.p.idepth - 4 : 2;  // max_off (2196)
+          // Two lane mappings with the same result.  Few anchors (the usual case: the exact hit and a chance
+          // neighbour): one anchor at a time, the lanes check the later segments in parallel.  Many anchors
+          // (repeats): 32 anchors at a time, each lane walks the later segments itself.
+          const bool by_segment = na <= PM_SLIST;
+          for (int i0 = 0; i0 < na && !done; i0 += by_segment ? 1 : 32) {
+            unsigned mask;
             int found = 1;
-            if (valid)
-              for (int j = loop + 1; j <= max_depth; j++) {
+            uint32_t av;
+            if (by_segment) {
+              av = anchors[i0];
+              const int j = loop + 1 + lane;
+              bool hit = false;
+              if (j <= max_depth) {
                 const int nj = (int)cnts[j];
-                if (nj == 0) continue;
-                const int d = ((j < total_cuts) ? 16 * j : len - 16) - off_loop;
-                // |(anchor - p) - (offsets[loop] - offsets[j])| < max_off = 12  (2244)
-                const long long c = (long long)av + d;
-                const int mo = (a.p.idepth - 4 > 2) ? a.p.idepth - 4 : 2;
-                found += list_has_in_range(nj <= PM_SLIST ? shead[j] : slists + (size_t)j * PM_SEG_CAP, nj, c - (mo - 1),
-                                           c + (mo - 1)) ? 1 : 0;
+                if (nj) {
+                  const long long c = (long long)av + (((j < total_cuts) ? 16 * j : len - 16) - off_loop);
+                  hit = list_has_in_range(nj <= PM_SLIST ? shead[j] : slists + (size_t)j * PM_SEG_CAP, nj, c - (mo - 1),
+                                          c + (mo - 1));
+                }
               }
-            unsigned mask = __ballot_sync(0xFFFFFFFFu, valid && found >= min_match);
+              found = 1 + __popc(__ballot_sync(0xFFFFFFFFu, hit));
+              mask = found >= min_match ? 1u : 0u;  // lane 0 stands for the anchor
+            } else {
+              const int i = i0 + lane;
+              const bool valid = i < na;
+              av = valid ? anchors[i] : 0u;
+              if (valid)
+                for (int j = loop + 1; j <= max_depth; j++) {
+                  const int nj = (int)cnts[j];
+                  if (nj == 0) continue;
+                  const int d = ((j < total_cuts) ? 16 * j : len - 16) - off_loop;
+                  // |(anchor - p) - (offsets[loop] - offsets[j])| < max_off = 12  (2244)
+                  const long long c = (long long)av + d;
+                  found += list_has_in_range(nj <= PM_SLIST ? shead[j] : slists + (size_t)j * PM_SEG_CAP, nj, c - (mo - 1),
+                                             c + (mo - 1)) ? 1 : 0;
+                }
+              mask = __ballot_sync(0xFFFFFFFFu, valid && found >= min_match);
+            }
             while (mask) {
               const int l = __ffs(mask) - 1;
               mask &= mask - 1;
