@@ -902,8 +902,6 @@ void pemap_default_params(pemap_params* p) {
 
 const char* pemap_last_error(pemap_t* h) { return h ? h->err.c_str() : "NULL handle"; }
 
-static pemap_ctx* g_failed = nullptr;  // keeps the message of a failed init readable through the returned handle
-
 int pemap_init(pemap_t** out, const pemap_index* ix, const pemap_params* p, int device) {
   if (!out) return PEMAP_ERR_ARG;
   pemap_ctx* h = new pemap_ctx();
@@ -1299,7 +1297,6 @@ void pemap_destroy(pemap_t* h) {
     cudaStreamDestroy(h->stream);
   }
   delete h;
-  (void)g_failed;
 }
 
 }  // extern "C"
