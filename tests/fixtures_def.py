@@ -35,6 +35,7 @@ class Fixture:
     genome: list
     names: list
     runs: list = field(default_factory=list)
+    bisulfite: bool = False         # index built in bisulfite mode (index_genome_whole.c:163, 174-175: C coded as T)
 
 
 def _edge_reads(genome, length=100):
@@ -134,4 +135,25 @@ def fx_tiny():
     return fx
 
 
-FIXTURES = {"tiny": fx_tiny, "cfg1": fx_cfg1, "pe150": fx_pe150, "edge9": fx_edge9, "repeat": fx_repeat}
+def _bisulfite_convert(rng, reads, rate=0.9):
+    """Unmethylated C reads as T after bisulfite treatment: convert each C of the read as sequenced with p = rate."""
+    out = reads.copy()
+    hit = (out == ord("C")) & (rng.random(out.shape) < rate)
+    out[hit] = ord("T")
+    return out
+
+
+def fx_bis():
+    """Bisulfite mode: 1 contig x 80 kb indexed with C = T, C->T converted reads, IS_BISULFITE = y."""
+    g = synth.random_genome(60, [80_000])
+    fx = Fixture("bis", g, ["chrB"], bisulfite=True)
+    rng = np.random.Generator(np.random.PCG64(61))
+    se = synth.simulate_reads(62, g, 2500, 100, sub=0.01, ins=0.0005, dele=0.0005)
+    fx.runs.append(RunDef("single", False, _bisulfite_convert(rng, se.reads1), None, 0.85, bisulfite=True))
+    pe = synth.simulate_reads(63, g, 1200, 100, paired=True, sub=0.01)
+    fx.runs.append(RunDef("pairs", True, _bisulfite_convert(rng, pe.reads1), _bisulfite_convert(rng, pe.reads2), 0.85,
+                          bisulfite=True))
+    return fx
+
+
+FIXTURES = {"bis": fx_bis, "tiny": fx_tiny, "cfg1": fx_cfg1, "pe150": fx_pe150, "edge9": fx_edge9, "repeat": fx_repeat}

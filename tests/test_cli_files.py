@@ -31,7 +31,7 @@ def _normalise_indel(path):
     return "\n".join(lines)
 
 
-@pytest.mark.parametrize("name,gpus", [("tiny", 1), ("edge9", 1), ("edge9", 2)])
+@pytest.mark.parametrize("name,gpus", [("tiny", 1), ("edge9", 1), ("bis", 1), ("edge9", 2)])
 def test_cli_files_match_reference(name, gpus, get_fixture, oracle_built, tmp_path):
     """gpus == 2: PEMAP_GPUS=2 with small batches - one submitting thread per GPU, batches alternate between the GPUs,
     counters summed over NVLink peer memory (pemap_reduce_counts_peer); the files must not change."""

@@ -16,7 +16,8 @@ pytestmark = pytest.mark.gpu
 def _run_both(mapper, oracle, run, n=None, threads=16):
     r1 = run.reads1[:n]
     r2 = run.reads2[:n] if run.paired else None
-    kw = dict(min_align=run.min_align, pair_flag=int(run.paired), min_dist=run.min_dist, max_dist=run.max_dist)
+    kw = dict(min_align=run.min_align, pair_flag=int(run.paired), min_dist=run.min_dist, max_dist=run.max_dist,
+              is_bisulfite=int(run.bisulfite))
     oracle.reset()
     oracle.set_params(**kw)
     mapper.reset_counts()
@@ -79,11 +80,13 @@ def _ctx(cache, fx):
             m, o = cache.pop(name)
             m.close()
             o.close()
-        cache[fx.name] = (pb.PEMapper.from_genome(fx.genome), ol.Oracle(fx.genome))
+        bis = int(getattr(fx, "bisulfite", False))  # baked into the index (index_genome_whole.c:174-175)
+        cache[fx.name] = (pb.PEMapper.from_genome(fx.genome, pb.default_params(is_bisulfite=bis)),
+                          ol.Oracle(fx.genome, ol.default_params(is_bisulfite=bis)))
     return cache[fx.name]
 
 
-@pytest.mark.parametrize("name", ["tiny", "edge9", "cfg1", "pe150", "repeat"])
+@pytest.mark.parametrize("name", ["tiny", "edge9", "cfg1", "pe150", "repeat", "bis"])
 def test_cuda_matches_oracle_and_reference(name, get_fixture, ctx_cache, oracle_built):
     fx = get_fixture(name)
     mapper, oracle = _ctx(ctx_cache, fx)

@@ -8,13 +8,14 @@ import pytest
 import golden_io as gio
 import oracle_lib as ol
 
-FAST = ["tiny", "edge9"]
+FAST = ["tiny", "edge9", "bis"]
 ALL = ["tiny", "edge9", "cfg1", "pe150", "repeat"]
 
 
 def _check_fixture(fx):
     assert gio.have(fx.name), "golden vectors for %s missing (tools/make_golden.py)" % fx.name
-    o = ol.Oracle(fx.genome)
+    bis = int(getattr(fx, "bisulfite", False))
+    o = ol.Oracle(fx.genome, ol.default_params(is_bisulfite=bis))
     meta = gio.index_meta(fx.name)
     # index_genome_whole parity: .mdx byte for byte, .sdx text
     assert hashlib.sha256(o.mers().tobytes()).hexdigest() == meta["mdx_sha256"]
@@ -25,7 +26,8 @@ def _check_fixture(fx):
         pass  # the 16 GiB .idx stream is checked by tools/pin_index.py (minutes), not here
     for run in fx.runs:
         o.reset()
-        o.set_params(min_align=run.min_align, pair_flag=int(run.paired), min_dist=run.min_dist, max_dist=run.max_dist)
+        o.set_params(min_align=run.min_align, pair_flag=int(run.paired), min_dist=run.min_dist, max_dist=run.max_dist,
+                     is_bisulfite=bis)
         m1, m2, ty = o.map_batch(run.reads1, run.reads2, nthreads=8)
         g1 = gio.mfile(fx.name, run.name, 1)
         assert np.array_equal(g1, m1), "%s/%s: .mfile of mate 1 differs" % (fx.name, run.name)

@@ -52,7 +52,7 @@ def build_index(work, fx):
     if not os.path.exists(os.path.join(work, "g.sdx")):
         synth.write_fasta(fa, fx.genome, fx.names)
         t = time.time()
-        stdin = "S\n%d\ng.fa\ng\nn\n" % (len(fx.genome) + 1)
+        stdin = "S\n%d\ng.fa\ng\n%s\n" % (len(fx.genome) + 1, "y" if getattr(fx, "bisulfite", False) else "n")
         subprocess.run([os.path.join(REF, "index_genome_whole")], input=stdin.encode(), cwd=work,
                        stdout=subprocess.DEVNULL, check=True)
         print("  index_genome_whole: %.0f s" % (time.time() - t), flush=True)
