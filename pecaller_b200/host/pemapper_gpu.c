@@ -5,6 +5,12 @@
  *
  *   pemapper_gpu out sdx s|sa file1 is_bisulfite min_match max_threads max_reads
  *   pemapper_gpu out sdx p|pa file1 file2 max_dist min_dist is_bisulfite min_match max_threads max_reads
+ * and, with two more arguments, those of pemapper_tsw (src/pemapper_tsw.c main(), tsw:213-335):
+ *   pemapper_gpu out sdx s|sa file1 ... max_reads trim_from_start trim_from_end
+ *   pemapper_gpu out sdx p|pa file1 file2 ... max_reads trim_from_start trim_from_end
+ * In that form every read is trimmed (tsw:693-704, 792-802), a second column of the array file names the sample
+ * of each fastq, and whenever the sample changes the outputs are written and the counters zeroed
+ * (dump_output, tsw:636-675, 849-965) - pemap_finish + pemap_reset_counts.
  *
  * max_threads is accepted and ignored: the reader thread fills batches, one submitting thread per GPU maps them.
  * Environment:
@@ -93,7 +99,8 @@ static char *next_sequence(reader *r) {
   return found ? s : NULL;
 }
 
-static int read_name_list(const char *path, char (*names)[NAME_MAX_LEN]) { /* 250-267 */
+/* 250-267; outs (may be NULL): second column = sample / output name of the file (tsw:266-280) */
+static int read_name_list(const char *path, char (*names)[NAME_MAX_LEN], char (*outs)[NAME_MAX_LEN]) {
   FILE *f = fopen(path, "r");
   if (!f) {
     printf("\n Can not open file %s for reading\n", path);
@@ -104,7 +111,10 @@ static int read_name_list(const char *path, char (*names)[NAME_MAX_LEN]) { /* 25
   while (n < MAX_FILES && fgets(line, NAME_MAX_LEN - 1, f)) {
     char *tok = strtok(line, "\t \n");
     if (!tok || strlen(tok) <= 2) break;
-    strcpy(names[n++], tok);
+    strcpy(names[n], tok);
+    tok = strtok(NULL, "\t \n");
+    if (outs) strcpy(outs[n], tok ? tok : "");
+    n++;
   }
   fclose(f);
   return n;
@@ -244,6 +254,172 @@ static int cmp_ins(const void *a, const void *b) {
   return strcmp(x->seq, y->seq);
 }
 
+/* tsw:693-704, 792-802: skip trim_from_start characters, drop trim_from_end from the end (never below length 0) */
+static char *trim_read(char *s, int trim_start, int trim_end) {
+  if (!s || (trim_start == 0 && trim_end == 0)) return s;
+  size_t n = strlen(s);
+  s += (size_t)trim_start <= n ? (size_t)trim_start : n; /* the reference would run past a short line; we stop at its end */
+  long len = (long)strlen(s) - trim_end;
+  if (len < 0) len = 0;
+  s[len] = '\0';
+  return s;
+}
+
+/* ---- outputs: the writer loop of main() (819-900) and, for the tsw form, dump_output (tsw:849-965) ---- */
+typedef struct {
+  gzFile pile, indel;
+  FILE *summary;
+  pemap_t **hs;
+  int n_gpus, device, paired, tsw;
+  worker_t *ws;
+  const sdx_t *sdx;
+  const char *genome;
+  uint64_t genome_size;
+  long mate_counts[9], total_reads, total_bases, total_dist, no_dists, tot_pairs;
+} out_t;
+
+static void open_outputs(out_t *o, const char *base) {
+  char path[4300];
+  snprintf(path, sizeof path, "%s.pileup.gz", base);
+  o->pile = gzopen(path, "wb");
+  if (!o->pile) die(" Can not open the pileup file for writing ");
+  gzbuffer(o->pile, 33554432);
+  snprintf(path, sizeof path, "%s.indel.txt.gz", base);
+  o->indel = gzopen(path, "w");
+  if (!o->indel) die(" Can not open the indel file for writing ");
+  gzbuffer(o->indel, 33554432);
+  snprintf(path, sizeof path, "%s.summary.txt", base);
+  o->summary = fopen(path, "w");
+  if (!o->summary) die(" Can not open the summary file for writing ");
+}
+
+static void write_summary(FILE *f, const out_t *o, const char **names, double avg_len, double avg_depth, double avg_dist) {
+  const char *bars = "\n================================================================";
+  fprintf(f, "%s\n================= Summary ======================================%s%s", bars, bars, bars);
+  if (o->total_bases <= 0)
+    fprintf(f, "\n\nTotal Number of Mapping reads of Any Kind\t0\tWith average Length\t0\tAverage Depth\t0\tAverage Insert Size\t0");
+  else
+    fprintf(f, "\n\nTotal Number of Mapping reads of Any Kind\t%ld\tWith average Length\t%g\tAverage Depth\t%g\tAverage Insert Size\t%g",
+            o->total_reads, avg_len, avg_depth, avg_dist);
+  fprintf(f, "\n\nMapping Type\tCount\tFraction");
+  fprintf(f, "\nAll\t%ld\t1", o->tot_pairs);
+  for (int i = 0; i < 9; i++)
+    if (names[i]) fprintf(f, "\n%s\t%ld\t%g", names[i], o->mate_counts[i], (double)o->mate_counts[i] / (double)o->tot_pairs);
+  fprintf(f, "\n");
+}
+
+/* Collect the workers' statistics, write pileup / indel / summary of what has been mapped since the last call and
+   (tsw form) zero the counters for the next sample.  Returns 1 when nothing mapped (790-808 / tsw:855-873). */
+static int dump_output(out_t *o) {
+  const char *pn[9] = {"Unique Mate-Paired", "Unique Mate-Paired with slip", "Unique Single End", "Unique Mis-size",
+                       "Non-Unique Mate-Paired", "Non-Unique Mis-size", "Fragment Mismatch", "Non-unique with no map",
+                       "Neither Map"}; /* 567-590 */
+  const char *sn[9] = {NULL, NULL, "Unique Mapping", NULL, NULL, NULL, NULL, "Non-Unique Mapping, discarded",
+                       "No mapping reaches threshold"};
+  const char **names = o->paired ? pn : sn;
+  for (int g = 0; g < o->n_gpus; g++) {
+    worker_t *w = &o->ws[g];
+    worker_wait_idle(w);
+    for (int i = 0; i < 9; i++) {
+      o->mate_counts[i] += w->mate_counts[i];
+      w->mate_counts[i] = 0;
+    }
+    o->total_reads += w->total_reads;
+    o->total_bases += w->total_bases;
+    o->total_dist += w->total_dist;
+    o->no_dists += w->no_dists;
+    w->total_reads = w->total_bases = w->total_dist = w->no_dists = 0;
+  }
+  if (o->total_bases <= 0) { /* nothing mapped: summary only, and (tsw quirk) nothing is reset */
+    write_summary(o->summary, o, names, 0, 0, 0);
+    fclose(o->summary);
+    return 1;
+  }
+
+  pemap_t *h = o->hs[0];
+  const pemap_record *rec;
+  const pemap_insertion *ins;
+  uint64_t n_rec, n_ins;
+  pemap_insertion *all_ins = NULL; /* insertion strings of every GPU, sorted by site */
+  uint64_t n_all = 0;
+  int rc;
+  for (int g = 1; g < o->n_gpus; g++) { /* every GPU's counters onto GPU 0 over NVLink; its insertion strings to the host */
+    const pemap_record *r2;
+    const pemap_insertion *i2;
+    uint64_t nr2, ni2;
+    rc = pemap_reduce_counts_peer(o->hs[0], o->hs[g]);
+    if (rc) {
+      printf("\n reducing GPU %d failed: %s \n", o->device + g, pemap_last_error(o->hs[0]));
+      exit(1);
+    }
+    rc = pemap_finish(o->hs[g], &r2, &nr2, &i2, &ni2);
+    if (rc) {
+      printf("\n pemap_finish failed on GPU %d: %s \n", o->device + g, pemap_last_error(o->hs[g]));
+      exit(1);
+    }
+    all_ins = realloc(all_ins, (size_t)(n_all + ni2 + 1) * sizeof(pemap_insertion));
+    memcpy(all_ins + n_all, i2, (size_t)ni2 * sizeof(pemap_insertion));
+    n_all += ni2;
+  }
+  rc = pemap_finish(h, &rec, &n_rec, &ins, &n_ins);
+  if (rc) {
+    printf("\n pemap_finish failed: %s \n", pemap_last_error(h));
+    exit(1);
+  }
+  if (o->n_gpus > 1) {
+    all_ins = realloc(all_ins, (size_t)(n_all + n_ins + 1) * sizeof(pemap_insertion));
+    memcpy(all_ins + n_all, ins, (size_t)n_ins * sizeof(pemap_insertion));
+    n_all += n_ins;
+    qsort(all_ins, (size_t)n_all, sizeof(pemap_insertion), cmp_ins);
+    ins = all_ins;
+    n_ins = n_all;
+  }
+  const sdx_t *sdx = o->sdx;
+  gzprintf(o->indel, "Fragment\tPositions\tReference Base\tTotal Coverage\tReference Reads\tNo Deletions\tNo Insertions\tInsertion Sequence"); /* 819-820 */
+  uint32_t *padded = calloc((size_t)sdx->n + 16, 4);
+  for (int i = 0; i <= sdx->n; i++) padded[i] = sdx->starts[i] + 15u * (uint32_t)i; /* 821-822 */
+  uint64_t q = 0;
+  for (uint64_t k = 0; k < n_rec; k++) { /* 828-864 */
+    gzwrite(o->pile, &rec[k].pos, 4);
+    gzwrite(o->pile, rec[k].c, 12);
+    if (rec[k].c[5] > 0) {
+      const uint32_t pos = rec[k].pos;
+      const char ref = o->genome[pos];
+      const int tot = rec[k].c[0] + rec[k].c[1] + rec[k].c[2] + rec[k].c[3] + rec[k].c[4] + rec[k].c[5];
+      const int ref_reads = ref == 'A' ? rec[k].c[0] : ref == 'C' ? rec[k].c[1] : ref == 'G' ? rec[k].c[2] : rec[k].c[3];
+      const int which = find_contig(padded, sdx->n, pos);
+      gzprintf(o->indel, "\n%s\t%d\t%c\t%d\t%d\t%d\t%d", sdx->names[which], (int)(1 + pos - padded[which]), ref, tot,
+               ref_reads, rec[k].c[4], rec[k].c[5]);
+      while (q < n_ins && ins[q].pos < pos) q++;
+      for (; q < n_ins && ins[q].pos == pos; q++) gzprintf(o->indel, "\t%s", ins[q].seq);
+    }
+  }
+  free(padded);
+  free(all_ins);
+  gzclose(o->pile);
+  gzclose(o->indel);
+
+  double avg_len = (double)o->total_bases, avg_dist = (double)o->total_dist; /* 811-817, 868 */
+  if (o->total_reads > 0) avg_len /= (double)o->total_reads;
+  if (o->no_dists > 0) avg_dist /= (double)o->no_dists;
+  const double avg_depth = (double)o->total_bases / (double)o->genome_size;
+  if (!o->tsw) write_summary(stdout, o, names, avg_len, avg_depth, avg_dist); /* 870-883: pemapper also prints it */
+  write_summary(o->summary, o, names, avg_len, avg_depth, avg_dist);
+  fclose(o->summary);
+  if (o->tsw) { /* tsw:932, 957-962: ready for the next sample */
+    for (int g = 0; g < o->n_gpus; g++) {
+      rc = pemap_reset_counts(o->hs[g]);
+      if (rc) {
+        printf("\n pemap_reset_counts failed: %s \n", pemap_last_error(o->hs[g]));
+        exit(1);
+      }
+    }
+    o->total_reads = o->total_bases = o->total_dist = o->no_dists = 0;
+    for (int i = 0; i < 9; i++) o->mate_counts[i] = 0;
+  }
+  return 0;
+}
+
 int main(int argc, char **argv) {
   if (argc < 4) die("Usage: pemapper_gpu out_file sdx_file [s,sa,p,pa] ... (same arguments as pemapper)");
   const char mode = (char)toupper(argv[3][0]), arr = (char)toupper(argv[3][1]);
@@ -251,16 +427,28 @@ int main(int argc, char **argv) {
   double min_align;
   long max_reads;
   const char *in1, *in2 = NULL;
+  int tsw = 0, trim_start = 0, trim_end = 0;
   if (mode == 'S') { /* 233-280 */
-    if (argc != 9) die("Usage: pemapper_gpu out_file sdx_file [s,sa] file1 is_bisulfite[y,n] min_match_percentage max_threads max_reads");
+    if (argc != 9 && argc != 11)
+      die("Usage: pemapper_gpu out_file sdx_file [s,sa] file1 is_bisulfite[y,n] min_match_percentage max_threads max_reads [trim_from_start trim_from_end]");
+    if (argc == 11) {
+      tsw = 1;
+      trim_start = atoi(argv[9]);
+      trim_end = atoi(argv[10]);
+    }
     paired = 0;
     in1 = argv[4];
     bisulfite = strchr(argv[5], 'Y') || strchr(argv[5], 'y');
     min_align = atof(argv[6]);
     max_reads = atoi(argv[8]);
   } else if (mode == 'P') { /* 281-358 */
-    if (argc != 12)
-      die("Usage: pemapper_gpu out_file sdx_file [p,pa] file1 file2 max_dist min_dist is_bisulfite[y,n] min_match_percentage max_threads max_reads");
+    if (argc != 12 && argc != 14)
+      die("Usage: pemapper_gpu out_file sdx_file [p,pa] file1 file2 max_dist min_dist is_bisulfite[y,n] min_match_percentage max_threads max_reads [trim_from_start trim_from_end]");
+    if (argc == 14) {
+      tsw = 1;
+      trim_start = atoi(argv[12]);
+      trim_end = atoi(argv[13]);
+    }
     paired = 1;
     in1 = argv[4];
     in2 = argv[5];
@@ -273,11 +461,11 @@ int main(int argc, char **argv) {
     die("Usage: pemapper_gpu out_file sdx_file paired_or_single_or_array[p,s,pa,ps] ...");
     return 1;
   }
-  static char files1[MAX_FILES][NAME_MAX_LEN], files2[MAX_FILES][NAME_MAX_LEN];
+  static char files1[MAX_FILES][NAME_MAX_LEN], files2[MAX_FILES][NAME_MAX_LEN], out_names[MAX_FILES][NAME_MAX_LEN];
   int n_files = 1;
   if (arr == 'A') {
-    n_files = read_name_list(in1, files1);
-    if (paired && read_name_list(in2, files2) != n_files) die(" Mismatch in number of files in the two arrays ");
+    n_files = read_name_list(in1, files1, tsw ? out_names : NULL);
+    if (paired && read_name_list(in2, files2, NULL) != n_files) die(" Mismatch in number of files in the two arrays ");
   } else {
     strcpy(files1[0], in1);
     if (paired) strcpy(files2[0], in2);
@@ -285,17 +473,9 @@ int main(int argc, char **argv) {
 
   char path[4300], base[1024], sdxbase[1024];
   strcpy(base, argv[1]);
-  snprintf(path, sizeof path, "%s.pileup.gz", base);
-  gzFile pile = gzopen(path, "wb");
-  if (!pile) die(" Can not open the pileup file for writing ");
-  gzbuffer(pile, 33554432);
-  snprintf(path, sizeof path, "%s.indel.txt.gz", base);
-  gzFile indel = gzopen(path, "w");
-  if (!indel) die(" Can not open the indel file for writing ");
-  gzbuffer(indel, 33554432);
-  snprintf(path, sizeof path, "%s.summary.txt", base);
-  FILE *summary = fopen(path, "w");
-  if (!summary) die(" Can not open the summary file for writing ");
+  out_t out;
+  memset(&out, 0, sizeof out);
+  if (!tsw) open_outputs(&out, base); /* 374-393; the tsw form opens them per sample (tsw:636-675) */
 
   sdx_t sdx;
   load_sdx(argv[2], &sdx);
@@ -359,12 +539,11 @@ int main(int argc, char **argv) {
     free(mers);
   }
   if (rc) exit(1);
-  pemap_t *h = hs[0];
 
   const long batch_cap = getenv("PEMAP_BATCH") ? atol(getenv("PEMAP_BATCH")) : 1000000;
   uint32_t *maps1 = calloc((size_t)max_reads + 1, 4), *maps2 = calloc((size_t)max_reads + 1, 4);
   if (!maps1 || !maps2) die(" Could not allocate space for mapping position of reads ");
-  long mate_counts[9] = {0}, total_reads = 0, total_bases = 0, total_dist = 0, no_dists = 0, tot_pairs = 0;
+  long tot_pairs = 0;
   worker_t *ws = calloc((size_t)n_gpus, sizeof(worker_t));
   for (int g = 0; g < n_gpus; g++) {
     worker_t *w = &ws[g];
@@ -389,17 +568,46 @@ int main(int argc, char **argv) {
     if (pthread_create(&w->thread, NULL, worker_main, w)) die(" Could not start a submitting thread ");
   }
   long batch_no = 0;
+  out.hs = hs;
+  out.n_gpus = n_gpus;
+  out.device = device;
+  out.paired = paired;
+  out.tsw = tsw;
+  out.ws = ws;
+  out.sdx = &sdx;
+  out.genome = genome;
+  out.genome_size = genome_size;
+  int open_flag = 1;
 
   printf("\n About to start mapping everything \n\n");
   for (int fi = 0; fi < n_files; fi++) {
     reader r1, r2;
     reader_open(&r1, files1[fi]);
     if (paired) reader_open(&r2, files2[fi]);
+    if (tsw) { /* tsw:636-675: a new sample name closes the previous sample's outputs and opens its own */
+      if (out_names[fi][0] != '\0') {
+        if (strcmp(base, out_names[fi]) != 0) {
+          open_flag = 1;
+          if (fi > 0) {
+            for (int g = 0; g < n_gpus; g++) worker_wait_idle(&ws[g]);
+            out.tot_pairs = tot_pairs;
+            dump_output(&out);
+            tot_pairs = 0;
+          }
+        } else if (fi > 0)
+          open_flag = 0;
+      }
+      if (open_flag) {
+        open_flag = 0;
+        if (out_names[fi][0] != '\0') strcpy(base, out_names[fi]);
+        open_outputs(&out, base);
+      }
+    }
     char *s1 = reader_line(&r1), *s2 = NULL;
-    s1 = reader_line(&r1);
+    s1 = trim_read(reader_line(&r1), trim_start, trim_end);
     if (paired) {
       s2 = reader_line(&r2);
-      s2 = reader_line(&r2);
+      s2 = trim_read(reader_line(&r2), trim_start, trim_end);
     }
     long current = 0, filled = 0, batch_first = 0;
     int go = s1 != NULL;
@@ -422,10 +630,10 @@ int main(int argc, char **argv) {
         current++;
         if (current >= max_reads) go = 0;
         else {
-          s1 = next_sequence(&r1);
+          s1 = trim_read(next_sequence(&r1), trim_start, trim_end);
           if (!s1) go = 0;
           if (paired && go) {
-            s2 = next_sequence(&r2);
+            s2 = trim_read(next_sequence(&r2), trim_start, trim_end);
             if (!s2) go = 0;
           }
         }
@@ -462,107 +670,13 @@ int main(int argc, char **argv) {
     tot_pairs += current;
   }
 
+  for (int g = 0; g < n_gpus; g++) worker_wait_idle(&ws[g]);
+  out.tot_pairs = tot_pairs;
+  const int nothing = dump_output(&out); /* 786-900 / tsw:847 */
   for (int g = 0; g < n_gpus; g++) {
-    worker_t *w = &ws[g];
-    worker_wait_idle(w);
-    worker_submit(w, 2);
-    pthread_join(w->thread, NULL);
-    for (int i = 0; i < 9; i++) mate_counts[i] += w->mate_counts[i];
-    total_reads += w->total_reads;
-    total_bases += w->total_bases;
-    total_dist += w->total_dist;
-    no_dists += w->no_dists;
+    worker_submit(&ws[g], 2);
+    pthread_join(ws[g].thread, NULL);
   }
-  const char *pn[9] = {"Unique Mate-Paired", "Unique Mate-Paired with slip", "Unique Single End", "Unique Mis-size",
-                       "Non-Unique Mate-Paired", "Non-Unique Mis-size", "Fragment Mismatch", "Non-unique with no map",
-                       "Neither Map"}; /* 567-590 */
-  const char *sn[9] = {NULL, NULL, "Unique Mapping", NULL, NULL, NULL, NULL, "Non-Unique Mapping, discarded",
-                       "No mapping reaches threshold"};
-  const char **names = paired ? pn : sn;
-  const char *bars = "\n================================================================";
-  if (total_bases <= 0) { /* 790-808 */
-    fprintf(summary, "%s\n================= Summary ======================================%s%s", bars, bars, bars);
-    fprintf(summary, "\n\nTotal Number of Mapping reads of Any Kind\t0\tWith average Length\t0\tAverage Depth\t0\tAverage Insert Size\t0");
-    fprintf(summary, "\n\nMapping Type\tCount\tFraction");
-    fprintf(summary, "\nAll\t%ld\t1", tot_pairs);
-    for (int i = 0; i < 9; i++)
-      if (names[i]) fprintf(summary, "\n%s\t%ld\t%g", names[i], mate_counts[i], (double)mate_counts[i] / (double)tot_pairs);
-    fprintf(summary, "\n");
-    fclose(summary);
-    return 1;
-  }
-
-  const pemap_record *rec;
-  const pemap_insertion *ins;
-  uint64_t n_rec, n_ins;
-  pemap_insertion *all_ins = NULL; /* insertion strings of every GPU, sorted by site */
-  uint64_t n_all = 0;
-  for (int g = 1; g < n_gpus; g++) { /* every GPU's counters onto GPU 0 over NVLink; its insertion strings to the host */
-    const pemap_record *r2;
-    const pemap_insertion *i2;
-    uint64_t nr2, ni2;
-    rc = pemap_reduce_counts_peer(hs[0], hs[g]);
-    if (!rc) rc = pemap_finish(hs[g], &r2, &nr2, &i2, &ni2);
-    if (rc) {
-      printf("\n reducing GPU %d failed: %s \n", device + g, pemap_last_error(rc ? hs[g] : hs[0]));
-      exit(1);
-    }
-    all_ins = realloc(all_ins, (size_t)(n_all + ni2 + 1) * sizeof(pemap_insertion));
-    memcpy(all_ins + n_all, i2, (size_t)ni2 * sizeof(pemap_insertion));
-    n_all += ni2;
-  }
-  rc = pemap_finish(h, &rec, &n_rec, &ins, &n_ins);
-  if (rc) {
-    printf("\n pemap_finish failed: %s \n", pemap_last_error(h));
-    exit(1);
-  }
-  if (n_gpus > 1) {
-    all_ins = realloc(all_ins, (size_t)(n_all + n_ins + 1) * sizeof(pemap_insertion));
-    memcpy(all_ins + n_all, ins, (size_t)n_ins * sizeof(pemap_insertion));
-    n_all += n_ins;
-    qsort(all_ins, (size_t)n_all, sizeof(pemap_insertion), cmp_ins);
-    ins = all_ins;
-    n_ins = n_all;
-  }
-  gzprintf(indel, "Fragment\tPositions\tReference Base\tTotal Coverage\tReference Reads\tNo Deletions\tNo Insertions\tInsertion Sequence"); /* 819-820 */
-  uint32_t *padded = calloc((size_t)sdx.n + 16, 4);
-  for (int i = 0; i <= sdx.n; i++) padded[i] = sdx.starts[i] + 15u * (uint32_t)i; /* 821-822 */
-  uint64_t q = 0;
-  for (uint64_t k = 0; k < n_rec; k++) { /* 828-864 */
-    gzwrite(pile, &rec[k].pos, 4);
-    gzwrite(pile, rec[k].c, 12);
-    if (rec[k].c[5] > 0) {
-      const uint32_t pos = rec[k].pos;
-      const char ref = genome[pos];
-      const int tot = rec[k].c[0] + rec[k].c[1] + rec[k].c[2] + rec[k].c[3] + rec[k].c[4] + rec[k].c[5];
-      const int ref_reads = ref == 'A' ? rec[k].c[0] : ref == 'C' ? rec[k].c[1] : ref == 'G' ? rec[k].c[2] : rec[k].c[3];
-      const int which = find_contig(padded, sdx.n, pos);
-      gzprintf(indel, "\n%s\t%d\t%c\t%d\t%d\t%d\t%d", sdx.names[which], (int)(1 + pos - padded[which]), ref, tot, ref_reads,
-               rec[k].c[4], rec[k].c[5]);
-      while (q < n_ins && ins[q].pos < pos) q++;
-      for (; q < n_ins && ins[q].pos == pos; q++) gzprintf(indel, "\t%s", ins[q].seq);
-    }
-  }
-  gzclose(pile);
-  gzclose(indel);
-
-  double avg_len = (double)total_bases, avg_dist = (double)total_dist; /* 811-817, 868 */
-  if (total_reads > 0) avg_len /= (double)total_reads;
-  if (no_dists > 0) avg_dist /= (double)no_dists;
-  const double avg_depth = (double)total_bases / (double)genome_size;
-  FILE *outs[2] = {stdout, summary};
-  for (int o = 0; o < 2; o++) { /* 870-898 */
-    FILE *f = outs[o];
-    fprintf(f, "%s\n================= Summary ======================================%s%s", bars, bars, bars);
-    fprintf(f, "\n\nTotal Number of Mapping reads of Any Kind\t%ld\tWith average Length\t%g\tAverage Depth\t%g\tAverage Insert Size\t%g",
-            total_reads, avg_len, avg_depth, avg_dist);
-    fprintf(f, "\n\nMapping Type\tCount\tFraction");
-    fprintf(f, "\nAll\t%ld\t1", tot_pairs);
-    for (int i = 0; i < 9; i++)
-      if (names[i]) fprintf(f, "\n%s\t%ld\t%g", names[i], mate_counts[i], (double)mate_counts[i] / (double)tot_pairs);
-    fprintf(f, "\n");
-  }
-  fclose(summary);
   for (int g = 0; g < n_gpus; g++) pemap_destroy(hs[g]);
-  return 0;
+  return (nothing && !tsw) ? 1 : 0;
 }

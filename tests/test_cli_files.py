@@ -79,3 +79,49 @@ def test_cli_files_match_reference(name, gpus, get_fixture, oracle_built, tmp_pa
         assert _normalise_indel(os.path.join(work, run.name + ".indel.txt.gz")) == gold_indel, tag + ": .indel.txt.gz"
         checked += 1
     assert checked > 0
+
+
+def test_cli_tsw_form_matches_reference(get_fixture, oracle_built, tmp_path):
+    """pemapper_tsw form: array files with a sample column, read trimming, outputs written and counters
+    zeroed whenever the sample changes - against the files of the unmodified reference pemapper_tsw
+    (tests/golden/tsw, tools/make_golden_tsw.py)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_golden_tsw import tsw_runs
+    gold = os.path.join(gio.GOLD, "tsw")
+    fx = get_fixture("tiny")
+    work = str(tmp_path)
+    oracle = ol.Oracle(fx.genome)
+    oracle.write_index(os.path.join(work, "g"), fx.names, with_idx=False)
+    oracle.close()
+    env = dict(os.environ, PEMAP_DEVICE_INDEX="1", PEMAP_BATCH="333")
+    for run in tsw_runs(fx):
+        r1, r2 = run["reads"]
+        with open(os.path.join(work, run["name"] + ".arr1"), "w") as a1:
+            for f1, f2, samp, (lo, hi) in run["files"]:
+                synth.write_fastq(os.path.join(work, f1), r1[lo:hi])
+                a1.write("%s\t%s\n" % (f1, samp))
+        if r2 is not None:
+            with open(os.path.join(work, run["name"] + ".arr2"), "w") as a2:
+                for f1, f2, samp, (lo, hi) in run["files"]:
+                    synth.write_fastq(os.path.join(work, f2), r2[lo:hi])
+                    a2.write("%s\n" % f2)
+        import json
+        argv = json.load(open(os.path.join(gold, run["name"] + ".json")))["argv"]
+        r = subprocess.run([CLI] + argv, cwd=work, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        for samp in sorted({f[2] for f in run["files"]}):
+            tag = "%s/%s" % (run["name"], samp)
+            raw = gzip.open(os.path.join(work, samp + ".pileup.gz"), "rb").read()
+            want = gzip.open(os.path.join(gold, "%s.%s.pileup.bin.gz" % (run["name"], samp)), "rb").read()
+            assert raw == want, tag + ": .pileup.gz"
+            assert open(os.path.join(work, samp + ".summary.txt")).read() == \
+                open(os.path.join(gold, "%s.%s.summary.txt" % (run["name"], samp))).read(), tag + ": .summary.txt"
+            assert _normalise_indel(os.path.join(work, samp + ".indel.txt.gz")) == \
+                gzip.open(os.path.join(gold, "%s.%s.indel.norm.txt.gz" % (run["name"], samp)), "rt").read(), tag + ": indel"
+        for f1, f2, samp, (lo, hi) in run["files"]:
+            for fq in (f1, f2):
+                if fq:
+                    got = np.fromfile(os.path.join(work, fq + ".mfile"), dtype=np.uint32)
+                    want = np.frombuffer(gzip.open(os.path.join(gold, "%s.%s.mfile.gz" % (run["name"], fq))).read(), dtype=np.uint32)
+                    assert np.array_equal(got, want), "%s: %s.mfile" % (run["name"], fq)
