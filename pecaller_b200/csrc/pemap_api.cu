@@ -356,7 +356,8 @@ int upload_cstart(pemap_ctx* h, const uint32_t* cs, int n_contigs) {
 
 int check_contigs(pemap_ctx* h, int n) {
   if (n < 1) return fail(h, PEMAP_ERR_ARG, "no contigs");
-  if (n >= 2 && n <= 7)
+  // PEMAP_INDEX_ONLY=1 (set by index_genome_gpu): the handle is only used to build and read back the index
+  if (n >= 2 && n <= 7 && !(getenv("PEMAP_INDEX_ONLY") && atoi(getenv("PEMAP_INDEX_ONLY"))))
     return fail(h, PEMAP_ERR_UNSUPPORTED,
                 "2..7 contigs: the reference's find_chrom (pemapper.c:2168-2186) starts its bisection at index 7 and "
                 "reads past contig_starts; its result is undefined there (SURVEY.md section 7-C). Use 1 or >= 8 contigs.");

@@ -125,3 +125,34 @@ def test_cli_tsw_form_matches_reference(get_fixture, oracle_built, tmp_path):
                     got = np.fromfile(os.path.join(work, fq + ".mfile"), dtype=np.uint32)
                     want = np.frombuffer(gzip.open(os.path.join(gold, "%s.%s.mfile.gz" % (run["name"], fq))).read(), dtype=np.uint32)
                     assert np.array_equal(got, want), "%s: %s.mfile" % (run["name"], fq)
+
+
+def test_index_genome_gpu_files_match_reference(get_fixture, tmp_path):
+    """index_genome_gpu (device-built index written as .sdx/.seq/.idx/.mdx) against the files of the unmodified
+    index_genome_whole: .sdx text, sha256 of .mdx and of the inflated .seq and .idx (16 GiB stream) - SURVEY 8f-2."""
+    tool = os.path.join(ROOT, "pecaller_b200", "host", "index_genome_gpu")
+    if not os.path.exists(tool):
+        pytest.fail("index_genome_gpu not built: run __graft_entry__.build()")
+    for name, full_idx in (("edge9", False), ("tiny", True)):
+        fx = get_fixture(name)
+        meta = gio.index_meta(name)
+        work = str(tmp_path / name)
+        os.makedirs(work)
+        synth.write_fasta(os.path.join(work, "g.fa"), fx.genome, fx.names)
+        env = dict(os.environ, PEMAP_INDEX_SKIP_IDX="0" if full_idx else "1")
+        r = subprocess.run([tool, "g.fa", "g", "n"], cwd=work, env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert open(os.path.join(work, "g.sdx")).read() == meta["sdx"], name + ": .sdx"
+        assert hashlib.sha256(open(os.path.join(work, "g.mdx"), "rb").read()).hexdigest() == meta["mdx_sha256"], name + ": .mdx"
+        assert hashlib.sha256(gzip.open(os.path.join(work, "g.seq"), "rb").read()).hexdigest() == meta["seq_sha256"], name + ": .seq"
+        if full_idx and "idx_sha256" in meta:
+            h = hashlib.sha256()
+            n = 0
+            with gzip.open(os.path.join(work, "g.idx"), "rb") as f:
+                while True:
+                    b = f.read(1 << 26)
+                    if not b:
+                        break
+                    h.update(b)
+                    n += len(b)
+            assert n == meta["idx_bytes"] and h.hexdigest() == meta["idx_sha256"], name + ": inflated .idx"

@@ -111,6 +111,25 @@ def test_cuda_matches_oracle_and_reference(name, get_fixture, ctx_cache, oracle_
                 assert counts[nm] == got[code]
 
 
+@pytest.mark.parametrize("name", ["tiny", "bis"])
+def test_device_index_equals_reference_idx_stream(name, get_fixture):
+    """The device index builder against the reference index_genome_whole's FILES: sha256 of the whole pos_index
+    (2^32+1 words = the inflated .idx, 16 GiB) and of mers (= .mdx), normal and bisulfite index."""
+    meta = gio.index_meta(name)
+    if "idx_sha256" not in meta:
+        pytest.skip("reference .idx stream not hashed for %s" % name)
+    fx = get_fixture(name)
+    mapper = pb.PEMapper.from_genome(fx.genome, pb.default_params(is_bisulfite=int(getattr(fx, "bisulfite", False))))
+    assert hashlib.sha256(mapper.read_mers().tobytes()).hexdigest() == meta["mdx_sha256"]
+    h = hashlib.sha256()
+    total = (1 << 32) + 1
+    step = 1 << 28
+    for first in range(0, total, step):
+        h.update(mapper.read_pos_index(first, min(step, total - first)).tobytes())
+    mapper.close()
+    assert h.hexdigest() == meta["idx_sha256"]
+
+
 def test_pointer_entry_and_chunking(get_fixture, ctx_cache, oracle_built, monkeypatch):
     """pemap_map_batch (char** form of PTHREAD_DATA_NODE) == pemap_map_batch_rows; results independent of batching."""
     fx = get_fixture("tiny")
