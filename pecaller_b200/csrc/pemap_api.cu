@@ -91,6 +91,11 @@ struct pemap_ctx {
   pm::Winner* d_replay_tasks = nullptr;
   int band_half = PM_BAND_LANES / 2;  // PEMAP_BAND_HALF=0/1 narrows the traceback band (tests of the hand-over path)
   int trace32 = 0;
+  void* d_flagq = nullptr;      // packed decision flags between k_trace_dp16 and k_trace_walk16
+  size_t flagq_bytes = 0;
+  int* d_pair_dmid = nullptr;
+  void* d_pair_codes = nullptr;  // one-hot base codes of every winner pair (window rows, read columns)
+  size_t pair_codes_bytes = 0;
   int exact = 0;  // 1: fp64 kernels for everything (PEMAP_EXACT=1, PEMAP_KEEP_DETAIL, match_bonus != 1)
   uint32_t* d_cand_base = nullptr;
   uint32_t* d_cand_n = nullptr;
@@ -397,8 +402,30 @@ void dispatch_sw(pemap_ctx* h, const pm::SwArgs& a, int max_len) {
   h->stats.launches++;
 }
 
+// flag scratch of the packed integer traceback: one record per winner pair, sized for a chunk whose read-mates all have gaps
+int ensure_flag_scratch(pemap_ctx* h, size_t bytes_per_pair, size_t code_bytes) {
+  const size_t pairs = (size_t)h->chunk + 1;  // 2 * chunk read-mates / 2
+  const size_t need = pairs * bytes_per_pair, need_codes = pairs * code_bytes;
+  if (h->flagq_bytes < need) {
+    if (h->d_flagq) cudaFree(h->d_flagq);
+    h->d_flagq = nullptr;
+    h->flagq_bytes = 0;
+    CK(cudaMalloc(&h->d_flagq, need));
+    h->flagq_bytes = need;
+  }
+  if (h->pair_codes_bytes < need_codes) {
+    if (h->d_pair_codes) cudaFree(h->d_pair_codes);
+    h->d_pair_codes = nullptr;
+    h->pair_codes_bytes = 0;
+    CK(cudaMalloc(&h->d_pair_codes, need_codes));
+    h->pair_codes_bytes = need_codes;
+  }
+  if (!h->d_pair_dmid) CK(cudaMalloc(&h->d_pair_dmid, pairs * sizeof(int)));
+  return PEMAP_OK;
+}
+
 template <int G, int WD>
-void launch_trace_int(pemap_ctx* h, const pm::TraceIntArgs& a) {
+int launch_trace_int(pemap_ctx* h, pm::TraceIntArgs& a) {
   if (h->trace32) {  // one winner per sub-warp, 32-bit integers (PEMAP_TRACE32=1; kept as a cross-check)
     const size_t dyn = pm::trace_band_bytes<G, WD>();
     static int grids32[kMaxDev] = {};
@@ -408,24 +435,45 @@ void launch_trace_int(pemap_ctx* h, const pm::TraceIntArgs& a) {
       grid32 = one_wave_grid(h, pm::k_trace_i32<G, WD>, 128, dyn);
     }
     pm::k_trace_i32<G, WD><<<grid32, 128, dyn, h->stream>>>(a);
-    return;
+    h->stats.launches++;
+    return PEMAP_OK;
   }
-  const size_t dyn = pm::trace16_band_bytes<G, WD>();
-  static int grids16[kMaxDev] = {};
-  int& grid16 = grids16[h->device % kMaxDev];
-  if (!grid16) {
-    cudaFuncSetAttribute(pm::k_trace_i16<G, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    grid16 = one_wave_grid(h, pm::k_trace_i16<G, WD>, 128, dyn);
+  int rc = ensure_flag_scratch(h, pm::trace_flag_bytes_per_pair<G, WD>(), (size_t)pm::trace_code_bytes<G, WD>());
+  if (rc) return rc;
+  a.flagq = reinterpret_cast<uint2*>(h->d_flagq);
+  a.pair_codes = reinterpret_cast<unsigned char*>(h->d_pair_codes);
+  a.pair_dmid = h->d_pair_dmid;
+  const size_t dyn_dp = pm::trace_dp16_smem<G, WD>(), dyn_wk = pm::trace_walk16_smem<G, WD>();
+  static int grids_dp[kMaxDev] = {}, grids_wk[kMaxDev] = {};
+  int& grid_dp = grids_dp[h->device % kMaxDev];
+  int& grid_wk = grids_wk[h->device % kMaxDev];
+  if (!grid_dp) {
+    cudaFuncSetAttribute(pm::k_trace_dp16<G, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_dp);
+    cudaFuncSetAttribute(pm::k_trace_walk16<G, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_wk);
+    grid_dp = one_wave_grid(h, pm::k_trace_dp16<G, WD>, 128, dyn_dp);
+    {  // 4 walkers per CTA; the segment scratch (d_pend) holds 16 walkers per sw_blocks entry
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_trace_walk16<G, WD>, 128, dyn_wk) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+      }
+      grid_wk = std::min(h->sw_blocks * 4, per_sm * h->sm_count);
+    }
+    if (getenv("PEMAP_VERBOSE"))
+      fprintf(stderr, "pemap: k_trace_dp16<%d,%d> grid %d (%zu B dyn smem), k_trace_walk16 grid %d (%zu B)\n", G, WD, grid_dp,
+              dyn_dp, grid_wk, dyn_wk);
   }
-  pm::k_trace_i16<G, WD><<<grid16, 128, dyn, h->stream>>>(a);
+  pm::k_trace_dp16<G, WD><<<grid_dp, 128, dyn_dp, h->stream>>>(a);
+  pm::k_trace_walk16<G, WD><<<grid_wk, 128, dyn_wk, h->stream>>>(a);
+  h->stats.launches += 2;
+  return PEMAP_OK;
 }
 
-void dispatch_trace_int(pemap_ctx* h, const pm::TraceIntArgs& a, int max_len) {
-  if (max_len <= 112) launch_trace_int<16, 7>(h, a);
-  else if (max_len <= 160) launch_trace_int<16, 10>(h, a);
-  else if (max_len <= 256) launch_trace_int<32, 8>(h, a);
-  else launch_trace_int<32, 10>(h, a);
-  h->stats.launches++;
+int dispatch_trace_int(pemap_ctx* h, pm::TraceIntArgs& a, int max_len) {
+  if (max_len <= 112) return launch_trace_int<16, 7>(h, a);
+  if (max_len <= 160) return launch_trace_int<16, 10>(h, a);
+  if (max_len <= 256) return launch_trace_int<32, 8>(h, a);
+  return launch_trace_int<32, 10>(h, a);
 }
 
 template <int G, int WD, int CMM>
@@ -653,7 +701,14 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     ta.band_half = h->band_half;
     ta.counters = h->d_counters;
     ta.p = sa.p;
-    dispatch_trace_int(h, ta, max_len);
+    ta.work_walk = h->d_cursors + 15;
+    ta.flagq = nullptr;
+    ta.pair_dmid = nullptr;
+    ta.pair_codes = nullptr;
+    {
+      const int trc = dispatch_trace_int(h, ta, max_len);
+      if (trc) return trc;
+    }
     CK(cudaEventRecord(ev[6], h->stream));
     wa.winners = h->d_exact_winners;
     wa.n_items = h->d_cursors + 7;
@@ -1278,7 +1333,7 @@ void pemap_destroy(pemap_t* h) {
                    h->d_tasks, h->d_results, h->d_cursors,
                    h->d_cand_base, h->d_cand_n, h->d_winners, h->d_det_best, h->d_det_orient,
                    h->d_det_score, h->d_seed_scratch, h->d_dirs, h->d_pend, h->d_counters, h->d_ires, h->d_replay_reads,
-                   h->d_replay_tasks, h->d_diag_winners, h->d_exact_winners, h->d_oob_winners};
+                   h->d_replay_tasks, h->d_diag_winners, h->d_exact_winners, h->d_oob_winners, h->d_flagq, h->d_pair_dmid, h->d_pair_codes};
     for (void* p : dev)
       if (p) cudaFree(p);
     for (auto& sl : h->slots) {

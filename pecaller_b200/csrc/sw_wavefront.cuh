@@ -46,7 +46,7 @@ __device__ __forceinline__ char seq_char(const char* read, int len, int orient, 
 }
 
 template <int G, int WD, int MODE>
-__global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
+__global__ void __launch_bounds__(128, MODE == 2 ? 4 : 1) k_sw_fp64(SwArgs a) {
   constexpr bool TRACE = MODE != 0;
   constexpr int GROUPS_PER_BLOCK = 128 / G;
   constexpr int ROWS = (G * WD + 24 < PM_DP_MAX) ? G * WD + 24 : PM_DP_MAX;
@@ -66,12 +66,18 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
   PileSink sink = a.sink;
   if (TRACE) sink.pend = a.sink.pend + (size_t)ggid * PM_DP_MAX;
 
+  // TRACE: the sub-warps of a warp take consecutive winners and run the loops below with warp-uniform trip counts and
+  // full-mask shuffles (width G), so that they stay in lock step through the wavefront; a sub-warp without a winner
+  // runs empty rows.
+  constexpr unsigned FULL = 0xFFFFFFFFu;
   for (;;) {
     uint32_t first = 0;
-    const uint32_t item = TRACE ? next_work_item_warp<G>(a.work, &first) : next_work_item<G>(a.work, gmask, gl);
+    uint32_t item = TRACE ? next_work_item_warp<G>(a.work, &first) : next_work_item<G>(a.work, gmask, gl);
+    bool have = true;
     if (TRACE) {
       if (first >= n_items) break;
-      if (item >= n_items) continue;  // the warp's other sub-warp still has an item
+      have = item < n_items;
+      if (!have) item = first;
     } else if (item >= n_items) {
       break;
     }
@@ -89,8 +95,11 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
     res.maxk = 0;
     if (TRACE) res = a.results[task_id];
     // the walk never consults rows below the winning cell
-    const int nn = TRACE ? (res.maxi < tk.blen ? res.maxi : tk.blen) : tk.blen;
+    const int nn = !have ? 0 : TRACE ? (res.maxi < tk.blen ? res.maxi : tk.blen) : tk.blen;
     const int dend = res.maxi - mm;
+    const unsigned wmask = TRACE ? FULL : gmask;
+    int steps = nn > 0 ? nn + G - 1 : 0;
+    if (TRACE && G < 32) steps = max(steps, __shfl_xor_sync(FULL, steps, 16));
 
     __syncwarp(gmask);
     const int bis = a.p.is_bisulfite;
@@ -131,11 +140,10 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
     double out_s0 = 0.0, out_s2 = 0.0, out_m = 0.0;
     __syncwarp(gmask);
 
-    const int steps = nn > 0 ? nn + G - 1 : 0;
     for (int s = 0; s < steps; s++) {
-      double in_s0 = __shfl_up_sync(gmask, out_s0, 1, G);
-      double in_s2 = __shfl_up_sync(gmask, out_s2, 1, G);
-      double in_m = __shfl_up_sync(gmask, out_m, 1, G);
+      double in_s0 = __shfl_up_sync(wmask, out_s0, 1, G);
+      double in_s2 = __shfl_up_sync(wmask, out_s2, 1, G);
+      double in_m = __shfl_up_sync(wmask, out_m, 1, G);
       if (gl == 0) {  // column 0: S0[i][0] = 0, S2[i][0] = -go, M[i-1][0] = max(0, 0, -go) = 0 (2062-2081)
         in_s0 = 0.0;
         in_s2 = -1.0 * go;
@@ -196,25 +204,30 @@ __global__ void __launch_bounds__(128) k_sw_fp64(SwArgs a) {
       }
     } else {
       __syncwarp(gmask);
-      if (gl == 0 && nn > 0) {
-        // smith_waterman_backtrack (1752-1965) over the stored decisions
-        if (MODE == 1) {
+      // smith_waterman_backtrack (1752-1965) over the stored decisions
+      if (MODE == 1) {
+        if (gl == 0 && have && nn > 0) {
           FullCell<G, WD, 4> cell;
           cell.dirs = dirs;
           walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink, s_q[grp], 0);
           atomicAdd(&a.counters->tb_cells, (unsigned long long)nn * (unsigned long long)mm);
-        } else {
-          BandCell<WD, 4> cell;
-          cell.band = band;
-          cell.dend = dend;
-          cell.half = a.band_half;
-          if (walk_path<false, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink, s_q[grp], 0) == PM_WALK_OK) {
-            walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink, s_q[grp], 0);
-            atomicAdd(&a.counters->tb_cells, (unsigned long long)nn * (unsigned long long)mm);
-          } else {
-            const uint32_t w = atomicAdd(a.oob_cursor, 1u);
-            a.oob_winners[w] = a.winners[item];
-          }
+        }
+      } else if (have && nn > 0) {  // the whole group walks (coop_walk, trace_walk.cuh); the path segments go to the pend scratch
+        BandCell<WD, 4> cell;
+        cell.band = band;
+        cell.dend = dend;
+        cell.half = a.band_half;
+        uint2* segs = reinterpret_cast<uint2*>(sink.pend);
+        int nseg = 0;
+        NoTie nt;
+        int rc = coop_walk<G>(cell, nt, gmask, (tid & 31) / G * G, gl, res.maxk, res.maxi, mm, 0, segs, &nseg);
+        if (rc == PM_WALK_OK && nseg < 0) rc = PM_WALK_OOB;  // more segments than the scratch holds
+        if (rc == PM_WALK_OK) {
+          coop_apply<G>(segs, nseg, gmask, gl, read, mm, orient, tk.wstart, sink, s_q[grp], 0);
+          if (gl == 0) atomicAdd(&a.counters->tb_cells, (unsigned long long)nn * (unsigned long long)mm);
+        } else if (gl == 0) {
+          const uint32_t w = atomicAdd(a.oob_cursor, 1u);
+          a.oob_winners[w] = a.winners[item];
         }
       }
       __syncwarp(gmask);

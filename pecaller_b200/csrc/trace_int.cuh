@@ -40,6 +40,10 @@ struct TraceIntArgs {
   PileSink sink;               // sink.pend: per group PM_DP_MAX bytes
   SeedCounters* counters;
   int band_half;               // lanes kept on each side of the end-diagonal lane (PM_BAND_LANES / 2)
+  uint2* flagq;                // k_trace_dp16 -> k_trace_walk16: packed decision flags, [pair][winner][band row][lane]
+  unsigned char* pair_codes;   // one-hot codes of every pair's windows and oriented reads (low nibble first winner)
+  int* pair_dmid;              // band position of every winner pair (+1024), bit 16 / 17: a base outside ACGTN
+  uint32_t* work_walk;         // zeroed per launch: next winner of the walk kernel
   DevParams p;
 };
 
@@ -396,70 +400,105 @@ __global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_trace_i16: the same traceback with TWO winners packed per lane (s16x2, biased by PM_TBIAS like sw_int16.cuh)
-// and the decision flags extracted with SWAR compares: for halves a, b in [0, 2^15), (a + 0x8000 - b) has bit 15
-// set iff a >= b, and neither half borrows from the other.  Six flag words are accumulated per lane and row,
-// one bit per cell and half:
+// Packed integer traceback: k_trace_dp16 + k_trace_walk16.
+//
+// TWO winners are packed per lane (s16x2, biased by PM_TBIAS like sw_int16.cuh) and the decision flags are extracted
+// with SWAR compares: for halves a, b in [0, 2^15), (a + 0x8000 - b) has bit 15 set iff a >= b, and neither half
+// borrows from the other.  Six flags per cell and half:
 //     F0  S1 > S0 (or X tie)      F1  S2 > max(S0,S1)     F2  X1     F3  X2
 //     F4  S1 == S0 (or X tie)     F5  S2 == max(S0,S1)
-// (F0 and F4 both set cannot happen otherwise and marks the cell like A == 3 above.)  Only the PM_BAND16_LANES
-// lanes nearest the two winners' end diagonals keep their words, in shared memory; lane 0 walks the first winner
-// and lane 1 the second, with the same walker and tie certification as k_trace_i32.
+// (F0 and F4 both set cannot happen otherwise and marks the cell like A == 3 above.)
+//
+// Only the cells near the winners' end diagonal are ever consulted by the walk: lane l (columns WD*l+1 .. WD*l+WD)
+// is "in the band" for the nb = (half+1)*WD rows starting at r0(l) = WD*l - WD/2 + dmid + 1, and at any step of the
+// wavefront only one or two lanes of a group are.  Computing the flags inside the wavefront makes all G lanes pay
+// for them (3/4 of the instructions of a row), so k_trace_dp16 splits the work:
+//   1. main pass - the plain scoring recurrence (10 instructions per packed cell) over the whole matrix; a lane
+//      entering its band rows parks its column state (S0, S1, M of the row above: 3*WD words) and, for every band
+//      row, the three words that arrive from its left neighbour (S0, S2 of the row, M of the row above);
+//   2. band pass - every lane recomputes ITS OWN band rows from the parked inputs, now with the flags: no lane
+//      depends on another one any more, all G lanes are busy, and the flags cost nb rows per lane instead of
+//      nn + G - 1.  The values are the same integers, so the flags are the ones a single pass would produce.
+// Shared memory per group: [2*WD + ceil(WD/4)][G] uint4: band row r of lane l holds {l_s0, l_s2, diag, top-state
+// word r}; the last WD top-state words sit in the extra quads.  The packed flags of a band row,
+// {A: F0|F1<<WD|F2<<2WD, A: F3|F4<<WD|F5<<2WD, B: ..., B: ...}, go to global memory ([pair][row][lane], one
+// coalesced line per row and group) for the walk kernel.
+//
+// The walk is a different kind of program (branchy, latency-bound, few registers), and one kernel holding both
+// phases overflowed the instruction caches (44 % of its stall samples were instruction fetch).  k_trace_walk16
+// gives G/2 lanes to every winner: they stage the winner's flag words in shared memory and walk cooperatively
+// (trace_walk.cuh), with the tie certification above.
 // ---------------------------------------------------------------------------------------------------
 #define PM_TBIAS 1024
-#define PM_BAND16_LANES 2   // the lane of the end-diagonal column and its nearer neighbour: >= WD/2 columns each side
 
 template <int G, int WD>
-__host__ __device__ constexpr size_t trace16_band_bytes() {
-  return (size_t)(128 / G) * trace_rows<G, WD>() * PM_BAND16_LANES * 6 * 4;
-}
+__host__ __device__ constexpr int defer_quads() { return 2 * WD + (WD + 3) / 4; }
+template <int G, int WD>
+__host__ __device__ constexpr size_t trace_dp16_smem() { return (size_t)(128 / G) * defer_quads<G, WD>() * G * 16; }
+template <int G, int WD>
+__host__ __device__ constexpr int trace_code_bytes() { return (trace_rows<G, WD>() + G * WD + 15) / 16 * 16; }
+template <int G, int WD>
+__host__ __device__ constexpr size_t trace_walk16_smem() { return (size_t)4 * (2 * WD * G * 8 + trace_code_bytes<G, WD>()); }
+template <int G, int WD>
+__host__ __device__ constexpr size_t trace_flag_bytes_per_pair() { return (size_t)2 * WD * G * 16; }
 
-template <int WD>
-struct PackedBandCell {
-  const uint32_t* band;  // [rows][PM_BAND16_LANES][6]
-  int dmid, half, hi;    // hi: 0 = low halves (first winner), 1 = high halves; half = 0 keeps one lane (tests)
+// accessor over one winner's flag words: [band row][lane] uint2
+template <int G, int WD>
+struct LaneBandCell {
+  const uint2* fl;
+  int dmid, nb;          // nb = band rows per lane = (half + 1) * WD
   __device__ __forceinline__ int operator()(int pi, int pj) const {
     const int l = (pj - 1) / WD, c = (pj - 1) - l * WD;
-    const int slot = l - (band_center_lane<WD>(pi + WD / 2, dmid) - half);
-    if (slot < 0 || slot > half) return -1;
-    const uint32_t* w = band + ((pi - 1) * PM_BAND16_LANES + slot) * 6;
-    const int bit = 16 - WD + c + 16 * hi;
-    const uint2 w01 = *reinterpret_cast<const uint2*>(w), w23 = *reinterpret_cast<const uint2*>(w + 2),
-                w45 = *reinterpret_cast<const uint2*>(w + 4);
-    const int f0 = (w01.x >> bit) & 1, f1 = (w01.y >> bit) & 1, f2 = (w23.x >> bit) & 1, f3 = (w23.y >> bit) & 1,
-              f4 = (w45.x >> bit) & 1, f5 = (w45.y >> bit) & 1;
+    const int r = pi - (WD * l - WD / 2 + dmid + 1);
+    if (r < 0 || r >= nb) return -1;
+    const uint2 w = fl[r * G + l];
+    const int f0 = (w.x >> c) & 1, f1 = (w.x >> (WD + c)) & 1, f2 = (w.x >> (2 * WD + c)) & 1;
+    const int f3 = (w.y >> c) & 1, f4 = (w.y >> (WD + c)) & 1, f5 = (w.y >> (2 * WD + c)) & 1;
     if (f0 & f4) return 3;  // an X decision compared equal integers: undecidable here
     return (f1 ? 2 : f0) | (f2 << 2) | (f3 << 3) | (f4 << 4) | (f5 << 5);
   }
 };
 
+struct IntTie {
+  static constexpr bool kTrack = true;
+  TieCtx t;
+  __device__ __forceinline__ bool match(int i, int j) const { return cells_match(t, i, j); }
+  template <class Cell>
+  __device__ __forceinline__ bool resolve(const Cell& cell, int pi, int pj, int r36) const {
+    return resolve_tie(cell, t, pi, pj, r36);
+  }
+};
+
 template <int G, int WD>
-__global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
+__global__ void __launch_bounds__(128) k_trace_dp16(TraceIntArgs a) {
   constexpr int GPB = 128 / G;
   constexpr int ROWS = trace_rows<G, WD>();
-  extern __shared__ uint32_t s_band16[];  // [GPB][ROWS][PM_BAND16_LANES][6]
-  __shared__ unsigned char s_win[GPB][ROWS];  // one-hot window codes: low nibble first winner, high nibble second
-  __shared__ unsigned char s_q16[GPB][ROWS];  // one-hot codes of the two oriented reads, same packing
+  constexpr int QUADS = defer_quads<G, WD>();
+  extern __shared__ uint4 s_park[];           // [GPB][QUADS][G]
+  constexpr int CB = trace_code_bytes<G, WD>();
+  __shared__ __align__(16) unsigned char s_codes[GPB][CB];  // one-hot codes, low nibble first winner, high nibble second:
+                                                            // [0, ROWS) window rows, [ROWS, ROWS + G*WD) read columns
   const int tid = threadIdx.x, grp = tid / G, gl = tid % G;
-  const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) / G * G));
   const uint32_t n_items = *a.n_items, n_pairs = (n_items + 1) >> 1;
-  const uint32_t ggid = blockIdx.x * GPB + grp;
-  unsigned char* win = s_win[grp];
-  uint32_t* band = s_band16 + (size_t)grp * ROWS * PM_BAND16_LANES * 6;
+  unsigned char* win = s_codes[grp];
+  unsigned char* qcodes = s_codes[grp] + ROWS;
+  uint4* quads = s_park + (size_t)grp * QUADS * G;
   const int bis = a.p.is_bisulfite;
   const int half = a.band_half < 1 ? a.band_half : 1;  // lanes kept = half + 1
+  const int nb = (half + 1) * WD;                      // band rows per lane
   constexpr uint32_t K1 = 0x00010001u, K12 = 0x000C000Cu, NEG72 = 0xFFB8FFB8u, H = 0x80008000u;
   constexpr uint32_t BIASP = (PM_TBIAS << 16) | PM_TBIAS;
   constexpr uint32_t HX = H + 70u * K1;  // x = S + 70 >= S0  <=>  S - ge > S0 - go
-  PileSink sink = a.sink;
-  sink.pend = a.sink.pend + ((size_t)ggid * 2 + (gl & 1)) * PM_DP_MAX;  // lanes 0 and 1 walk concurrently
+  constexpr unsigned FULL = 0xFFFFFFFFu;
 
+  // The sub-warps of a warp take consecutive pairs and run every loop below with warp-uniform trip counts and
+  // full-mask shuffles (width G), so that they stay in lock step: a sub-warp without a pair runs empty rows.
   for (;;) {
     uint32_t first;
     const uint32_t pair = next_work_item_warp<G>(a.work, &first);
     if (first >= n_pairs) break;
-    if (pair >= n_pairs) continue;  // the warp's other sub-warp still has a pair
-    const uint32_t itA = 2 * pair, itB = (2 * pair + 1 < n_items) ? 2 * pair + 1 : 2 * pair;
+    const bool have = pair < n_pairs;
+    const uint32_t itA = have ? 2 * pair : 0, itB = have ? ((2 * pair + 1 < n_items) ? 2 * pair + 1 : 2 * pair) : 0;
     const uint32_t idA = a.winners[itA].task, idB = a.winners[itB].task;
     const Task tA = a.tasks[idA], tB = a.tasks[idB];
     const TaskResult rA = a.results[idA], rB = a.results[idB];
@@ -468,13 +507,16 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
     const int mmA = ((rmA & 1u) ? a.len[1] : a.len[0])[rmA >> 1], mmB = ((rmB & 1u) ? a.len[1] : a.len[0])[rmB >> 1];
     const char* readA = ((rmA & 1u) ? a.reads[1] : a.reads[0]) + (size_t)(rmA >> 1) * a.stride;
     const char* readB = ((rmB & 1u) ? a.reads[1] : a.reads[0]) + (size_t)(rmB >> 1) * a.stride;
-    const int nnA = rA.maxi < tA.blen ? rA.maxi : tA.blen, nnB = rB.maxi < tB.blen ? rB.maxi : tB.blen;
+    const int nnA = have ? (rA.maxi < tA.blen ? rA.maxi : tA.blen) : 0;  // rows below the winning cell are never consulted
+    const int nnB = have ? (rB.maxi < tB.blen ? rB.maxi : tB.blen) : 0;
     const int nn = nnA > nnB ? nnA : nnB;
     const int dmid = ((rA.maxi - mmA) + (rB.maxi - mmB)) >> 1;  // one band for both winners
+    int nn_w = nn;
+    if (G < 32) nn_w = max(nn_w, __shfl_xor_sync(FULL, nn_w, 16));
 
-    __syncwarp(gmask);
-    bool badA = false, badB = false;
-    for (int i = gl; i < nn; i += G) {
+    __syncwarp();
+    bool badA = false, badB = false;  // a base outside ACGTN: the walk kernel hands such winners to the fp64 path
+    for (int i = gl; i < nn_w; i += G) {
       uint32_t cA = 0, cB = 0;
       if (i < nnA) {
         const char ch = a.genome[(size_t)tA.wstart + i];
@@ -486,7 +528,7 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
         cB = ch == 'A' ? 1u : ch == 'C' ? (bis ? 10u : 2u) : ch == 'G' ? 4u : ch == 'T' ? 8u : (ch == 'N' || ch == 'n') ? 15u : 0u;
         badB |= (cB == 0u);
       }
-      win[i] = (unsigned char)(cA | (cB << 4));
+      if (i < nn) win[i] = (unsigned char)(cA | (cB << 4));
     }
     uint32_t q[WD], s0u[WD], s1u[WD], mu[WD];
     const int jbase = gl * WD;
@@ -505,22 +547,32 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
         badB |= (cB == 0u);
       }
       q[c] = cA | (cB << 16);
-      s_q16[grp][j0] = (unsigned char)(cA | (cB << 4));
+      qcodes[j0] = (unsigned char)(cA | (cB << 4));
       const uint32_t b = (uint32_t)(PM_TBIAS - 72 - j0);  // S*[0][j] = -(72 + j - 1), j = j0 + 1 (2073-2081)
       s0u[c] = b | (b << 16);
       s1u[c] = s0u[c];
       mu[c] = s0u[c] - K12;  // mu holds max(S0,S1,S2) - 12
     }
-    badA = __any_sync(gmask, badA);
-    badB = __any_sync(gmask, badB);
+    {
+      const unsigned gm = (G == 32) ? FULL : (((1u << G) - 1u) << ((tid & 31) / G * G));
+      badA = (__ballot_sync(FULL, badA) & gm) != 0u;
+      badB = (__ballot_sync(FULL, badB) & gm) != 0u;
+    }
     uint32_t out_s0 = 0, out_s2 = 0, out_m = 0;
-    __syncwarp(gmask);
+    __syncwarp();
+    if (have) {  // the codes travel with the flags
+      uint4* dst = reinterpret_cast<uint4*>(a.pair_codes + (size_t)pair * CB);
+      const uint4* srcq = reinterpret_cast<const uint4*>(s_codes[grp]);
+      for (int x = gl; x < CB / 16; x += G) dst[x] = srcq[x];
+    }
 
-    const int steps = nn > 0 ? nn + G - 1 : 0;
-    for (int s = 0; s < steps; s++) {
-      uint32_t l_s0 = __shfl_up_sync(gmask, out_s0, 1, G);
-      uint32_t l_s2 = __shfl_up_sync(gmask, out_s2, 1, G);
-      uint32_t diag = __shfl_up_sync(gmask, out_m, 1, G);
+    const int r0 = WD * gl - WD / 2 + dmid + 1;  // first band row of this lane
+    // ---- main pass: values only
+    const int steps_w = nn_w > 0 ? nn_w + G - 1 : 0;
+    for (int s = 0; s < steps_w; s++) {
+      uint32_t l_s0 = __shfl_up_sync(FULL, out_s0, 1, G);
+      uint32_t l_s2 = __shfl_up_sync(FULL, out_s2, 1, G);
+      uint32_t diag = __shfl_up_sync(FULL, out_m, 1, G);
       if (gl == 0) {  // column 0: S0 = 0, S2 = -72, M(row above) - 12 = -12 (2062-2081)
         l_s0 = BIASP;
         l_s2 = BIASP - 0x00480048u;
@@ -528,29 +580,30 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
       }
       const int i = s - gl + 1;
       if (i >= 1 && i <= nn) {
+        const unsigned r = (unsigned)(i - r0);
+        if (r < (unsigned)nb) {
+          uint32_t* slot = reinterpret_cast<uint32_t*>(&quads[r * G + gl]);
+          if (r == 0u && i >= 2) {  // entering the band: park the column state of row i - 1
+#pragma unroll
+            for (int c = 0; c < WD; c++) {
+              reinterpret_cast<uint32_t*>(&quads[c * G + gl])[3] = s0u[c];
+              reinterpret_cast<uint32_t*>(&quads[(WD + c) * G + gl])[3] = s1u[c];
+              reinterpret_cast<uint32_t*>(&quads[(2 * WD + c / 4) * G + gl])[c & 3] = mu[c];
+            }
+          }
+          *reinterpret_cast<uint2*>(slot) = make_uint2(l_s0, l_s2);
+          slot[2] = diag;
+        }
         const uint32_t rb = win[i - 1];
         const uint32_t rc = (rb & 15u) | ((rb >> 4) << 16);
-        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
 #pragma unroll
         for (int c = 0; c < WD; c++) {
           const uint32_t s2 = __viaddmax_s16x2(l_s0, NEG72, l_s2 - K1);      // 1710 / 1720
           const uint32_t s1 = __viaddmax_s16x2(s0u[c], NEG72, s1u[c] - K1);  // 1711 / 1721
           const uint32_t m01 = __vminu2(q[c] & rc, K1);                      // 1 where the bases match
-          const uint32_t s0 = m01 * 48u + diag;                              // (M - 12) + 48 or + 0
+          const uint32_t s0 = m01 * 48u + diag;                              // (M - 12) + 48 or + 0 (1713 / 1723)
           diag = mu[c];
-          const uint32_t x01 = __vmaxs2(s0, s1);
-          const uint32_t m = __vmaxs2(x01, s2);
-          // SWAR decisions, bit 15 of each half
-          const uint32_t g = s0 + H - s1, g2 = s1 + H - s0;                  // S0 >= S1, S1 >= S0
-          const uint32_t hh = x01 + H - s2, h2 = s2 + H - x01;               // max01 >= S2, S2 >= max01
-          const uint32_t w1 = s1 + HX - s0, w2 = s2 + HX - s0;               // X1, X2
-          const uint32_t tx = ((w1 + K1) & ~w1) | ((w2 + K1) & ~w2);         // S1 + 71 == S0 or S2 + 71 == S0
-          a0 = (a0 >> 1) | ((~g | tx) & H);
-          a1 = (a1 >> 1) | (~hh & H);
-          a2 = (a2 >> 1) | (w1 & H);
-          a3 = (a3 >> 1) | (w2 & H);
-          a4 = (a4 >> 1) | (((g & g2) | tx) & H);
-          a5 = (a5 >> 1) | (hh & h2 & H);
+          const uint32_t m = __vmaxs2(__vmaxs2(s0, s1), s2);
           s0u[c] = s0;
           s1u[c] = s1;
           mu[c] = m - K12;
@@ -560,46 +613,159 @@ __global__ void __launch_bounds__(128) k_trace_i16(TraceIntArgs a) {
         out_s0 = l_s0;
         out_s2 = l_s2;
         out_m = diag;
-        const int slot = gl - (band_center_lane<WD>(i + WD / 2, dmid) - half);
-        if (slot >= 0 && slot <= half) {
-          uint32_t* w = band + ((i - 1) * PM_BAND16_LANES + slot) * 6;
-          *reinterpret_cast<uint2*>(w) = make_uint2(a0, a1);
-          *reinterpret_cast<uint2*>(w + 2) = make_uint2(a2, a3);
-          *reinterpret_cast<uint2*>(w + 4) = make_uint2(a4, a5);
+      }
+    }
+    __syncwarp();
+    // ---- band pass: this lane's band rows again, with the flags
+    {
+#pragma unroll
+      for (int c = 0; c < WD; c++) {
+        if (r0 >= 2) {
+          s0u[c] = reinterpret_cast<const uint32_t*>(&quads[c * G + gl])[3];
+          s1u[c] = reinterpret_cast<const uint32_t*>(&quads[(WD + c) * G + gl])[3];
+          mu[c] = reinterpret_cast<const uint32_t*>(&quads[(2 * WD + c / 4) * G + gl])[c & 3];
+        } else {  // the band starts at row 1: row 0 borders (2073-2081)
+          const uint32_t b = (uint32_t)(PM_TBIAS - 72 - (jbase + c));
+          s0u[c] = b | (b << 16);
+          s1u[c] = s0u[c];
+          mu[c] = s0u[c] - K12;
+        }
+      }
+      uint2* outA = a.flagq + (size_t)pair * (2 * 2 * WD * G);  // [winner][band row][lane]
+      uint2* outB = outA + 2 * WD * G;
+      for (int r = 0; r < nb; r++) {  // warp-uniform trip count; rows outside 1 .. nn are never consulted
+        const int i = r0 + r;
+        if (i >= 1 && i <= nn) {
+          const uint4 in = quads[r * G + gl];
+          uint32_t l_s0 = in.x, l_s2 = in.y, diag = in.z;
+          const uint32_t rb = win[i - 1];
+          const uint32_t rc = (rb & 15u) | ((rb >> 4) << 16);
+          uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+#pragma unroll
+          for (int c = 0; c < WD; c++) {
+            const uint32_t s2 = __viaddmax_s16x2(l_s0, NEG72, l_s2 - K1);      // 1710 / 1720
+            const uint32_t s1 = __viaddmax_s16x2(s0u[c], NEG72, s1u[c] - K1);  // 1711 / 1721
+            const uint32_t m01 = __vminu2(q[c] & rc, K1);                      // 1 where the bases match
+            const uint32_t s0 = m01 * 48u + diag;                              // (M - 12) + 48 or + 0
+            diag = mu[c];
+            const uint32_t x01 = __vmaxs2(s0, s1);
+            const uint32_t m = __vmaxs2(x01, s2);
+            // SWAR decisions, bit 15 of each half
+            const uint32_t g = s0 + H - s1, g2 = s1 + H - s0;                  // S0 >= S1, S1 >= S0
+            const uint32_t hh = x01 + H - s2, h2 = s2 + H - x01;               // max01 >= S2, S2 >= max01
+            const uint32_t w1 = s1 + HX - s0, w2 = s2 + HX - s0;               // X1, X2
+            const uint32_t tx = ((w1 + K1) & ~w1) | ((w2 + K1) & ~w2);         // S1 + 71 == S0 or S2 + 71 == S0
+            a0 = (a0 >> 1) | ((~g | tx) & H);
+            a1 = (a1 >> 1) | (~hh & H);
+            a2 = (a2 >> 1) | (w1 & H);
+            a3 = (a3 >> 1) | (w2 & H);
+            a4 = (a4 >> 1) | (((g & g2) | tx) & H);
+            a5 = (a5 >> 1) | (hh & h2 & H);
+            s0u[c] = s0;
+            s1u[c] = s1;
+            mu[c] = m - K12;
+            l_s0 = s0;
+            l_s2 = s2;
+          }
+          // flags sit in bits 16-WD .. 15 (first winner) and 32-WD .. 31 (second) of a0 .. a5
+          constexpr uint32_t FM = (1u << WD) - 1u;
+          const uint32_t wa0 = ((a0 >> (16 - WD)) & FM) | (((a1 >> (16 - WD)) & FM) << WD) | (((a2 >> (16 - WD)) & FM) << (2 * WD));
+          const uint32_t wa1 = ((a3 >> (16 - WD)) & FM) | (((a4 >> (16 - WD)) & FM) << WD) | (((a5 >> (16 - WD)) & FM) << (2 * WD));
+          const uint32_t wb0 = (a0 >> (32 - WD)) | ((a1 >> (32 - WD)) << WD) | ((a2 >> (32 - WD)) << (2 * WD));
+          const uint32_t wb1 = (a3 >> (32 - WD)) | ((a4 >> (32 - WD)) << WD) | ((a5 >> (32 - WD)) << (2 * WD));
+          outA[r * G + gl] = make_uint2(wa0, wa1);
+          outB[r * G + gl] = make_uint2(wb0, wb1);
         }
       }
     }
-    __syncwarp(gmask);
-
-    if (gl < 2 && nn > 0 && (gl == 0 || itB != itA)) {
-      const bool second = gl == 1;
-      const Task& tk = second ? tB : tA;
-      const TaskResult& res = second ? rB : rA;
-      const char* read = second ? readB : readA;
-      const int mm = second ? mmB : mmA, orient = second ? orB : orA, nnw = second ? nnB : nnA;
-      const bool bad = second ? badB : badA;
-      PackedBandCell<WD> cell;
-      cell.band = band;
-      cell.dmid = dmid;
-      cell.half = half;
-      cell.hi = second ? 1 : 0;
-      // the tie certification reads one-hot window codes: give it this winner's half through a byte view
-      TieCtx tc;
-      tc.win = win;
-      tc.qcode = s_q16[grp];
-      tc.shift = second ? 4 : 0;
-      const int r36 = (int)lrint(res.score * 36.0);
-      int rc = (bad || nnw <= 0) ? PM_WALK_TIE : walk_check_int(cell, tc, res.maxk, res.maxi, mm, r36);
-      atomicAdd(&a.counters->tb_cells_int, (unsigned long long)nnw * (unsigned long long)mm);
-      if (rc == PM_WALK_OK) {
-        walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink, tc.qcode, tc.shift);
-      } else {
-        const uint32_t w = atomicAdd(a.exact_cursor, 1u);
-        a.exact_winners[w] = a.winners[second ? itB : itA];
-        atomicAdd(&a.counters->exact_traced, 1ull);
-      }
+    if (have && gl == 0) {
+      a.pair_dmid[pair] = (dmid + 1024) | (badA ? (1 << 16) : 0) | (badB ? (1 << 17) : 0);
+      atomicAdd(&a.counters->tb_cells_int, (unsigned long long)nnA * (unsigned long long)mmA +
+                                               (itB != itA ? (unsigned long long)nnB * (unsigned long long)mmB : 0ull));
     }
-    __syncwarp(gmask);
+    __syncwarp();
+  }
+}
+
+// one winner per warp: stage its flag words and base codes, walk, apply or hand over to the exact kernel
+template <int G, int WD>
+__global__ void __launch_bounds__(128) k_trace_walk16(TraceIntArgs a) {
+  constexpr int NL = 32;
+  constexpr int WPB = 4;
+  constexpr int ROWS = trace_rows<G, WD>();
+  constexpr int CB = trace_code_bytes<G, WD>();
+  constexpr int FLW = 2 * WD * G;             // flag words (uint2) of one winner
+  extern __shared__ uint4 s_walk[];           // [WPB]{FLW uint2, CB bytes}
+  const int tid = threadIdx.x, wk = tid / NL, sl = tid % NL;
+  constexpr unsigned smask = 0xFFFFFFFFu;
+  const uint32_t n_items = *a.n_items;
+  const uint32_t gwk = blockIdx.x * WPB + wk;
+  const int half = a.band_half < 1 ? a.band_half : 1;
+  const int nb = (half + 1) * WD;
+  uint4* mine = s_walk + (size_t)wk * ((FLW * 8 + CB) / 16);
+  uint2* fl = reinterpret_cast<uint2*>(mine);
+  unsigned char* codes = reinterpret_cast<unsigned char*>(mine + FLW * 8 / 16);
+  PileSink sink = a.sink;
+  sink.pend = a.sink.pend + (size_t)gwk * PM_DP_MAX;   // the walker's path segments
+  uint2* segs = reinterpret_cast<uint2*>(sink.pend);
+
+  // winners are taken 8 at a time: one atomic per winner on a single address serialises in L2
+  uint32_t next_item = 0, batch_left = 0;
+  for (;;) {
+    if (batch_left == 0u) {
+      uint32_t v = 0;
+      if (sl == 0) v = atomicAdd(a.work_walk, 8u);
+      next_item = __shfl_sync(smask, v, 0);
+      batch_left = 8u;
+    }
+    const uint32_t item = next_item++;
+    batch_left--;
+    if (item >= n_items) break;
+    const uint32_t pair = item >> 1;
+    const int hi = (int)(item & 1u);
+    const uint32_t task_id = a.winners[item].task;
+    const Task tk = a.tasks[task_id];
+    const TaskResult res = a.results[task_id];
+    const int orient = (int)(tk.rm >> 31);
+    const uint32_t rm = tk.rm & 0x7FFFFFFFu;
+    const int mm = ((rm & 1u) ? a.len[1] : a.len[0])[rm >> 1];
+    const char* read = ((rm & 1u) ? a.reads[1] : a.reads[0]) + (size_t)(rm >> 1) * a.stride;
+    const int nn = res.maxi < tk.blen ? res.maxi : tk.blen;
+    const int pd = a.pair_dmid[pair];
+    const int dmid = (pd & 0xFFFF) - 1024;
+    const bool bad = (pd >> (16 + hi)) & 1;  // bases outside ACGTN: the scoring kernel sent such reads to the fp64 path already
+
+    __syncwarp();
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(a.flagq + ((size_t)pair * 2 + hi) * FLW);
+      for (int x = sl; x < nb * G / 2; x += NL) mine[x] = __ldg(src + x);
+      const uint4* csrc = reinterpret_cast<const uint4*>(a.pair_codes + (size_t)pair * CB);
+      for (int x = sl; x < CB / 16; x += NL) mine[FLW * 8 / 16 + x] = __ldg(csrc + x);
+    }
+    __syncwarp();
+
+    int rc = PM_WALK_TIE, nseg = 0;
+    if (!bad && nn > 0) {
+      LaneBandCell<G, WD> cell;
+      cell.fl = fl;
+      cell.dmid = dmid;
+      cell.nb = nb;
+      IntTie tie;
+      tie.t.win = codes;
+      tie.t.qcode = codes + ROWS;
+      tie.t.shift = 4 * hi;
+      const int r36 = (int)lrint(res.score * 36.0);
+      rc = coop_walk<NL>(cell, tie, smask, 0, sl, res.maxk, res.maxi, mm, r36, segs, &nseg);
+      if (rc == PM_WALK_OK && nseg < 0) rc = PM_WALK_TIE;  // more segments than the scratch holds: exact kernel
+    }
+    if (rc == PM_WALK_OK) {
+      coop_apply<NL>(segs, nseg, smask, sl, read, mm, orient, tk.wstart, sink, codes + ROWS, 4 * hi);
+    } else if (sl == 0) {
+      const uint32_t w = atomicAdd(a.exact_cursor, 1u);
+      a.exact_winners[w] = a.winners[item];
+      atomicAdd(&a.counters->exact_traced, 1ull);
+    }
+    __syncwarp();
   }
 }
 

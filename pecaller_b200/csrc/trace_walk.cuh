@@ -120,6 +120,173 @@ __device__ __forceinline__ int walk_path(const Cell& cell, int k, int i, int j, 
   return PM_WALK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cooperative walk.  The serial walk above is a chain of ~2 * len dependent shared-memory look-ups on one lane;
+// most of it is a state-0 diagonal.  Here NL consecutive lanes own one winner: in state 0 lane t looks at the cell
+// t steps down the diagonal, a ballot finds the first cell that is not a plain "stay in state 0" decision, and the
+// walk jumps there in one iteration.  Gap steps and cells that need the tie certification are handled one at a
+// time, exactly as walk_path / walk_check_int do.  Nothing is applied during the walk: the path is recorded as
+// segments (type, i, j, length) and, once the whole walk is known to be decidable here, applied by all NL lanes
+// (coop_apply).  Every lane of the walker carries the same (k, i, j): control flow is uniform within the walker.
+// ---------------------------------------------------------------------------------------------------
+#define PM_WALK_SEGS 40   // recorded segments per walker: PM_DP_MAX bytes of scratch / 8
+
+// sink_insertion for an insertion whose characters are read columns j_lo .. j_lo + n - 1 (0-based, ascending):
+// the un-reversed buffer of 1892-1893
+__device__ __forceinline__ void sink_insertion_direct(const PileSink& s, uint32_t site, const char* read, int mm,
+                                                      int orient, int j_lo, int n) {
+  unsigned long long need = 8ull + (unsigned long long)((n + 3) & ~3);
+  unsigned long long off = atomicAdd(s.ins_cursor, need);
+  if (off + need <= s.ins_cap) {
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(s.ins_buf + off);
+    hdr[0] = site;
+    hdr[1] = (uint32_t)n;
+    unsigned char* dst = s.ins_buf + off + 8;
+    for (int m = 0; m < n; m++) dst[m] = (unsigned char)oriented_char(read, mm, orient, j_lo + m);
+  }
+  atomicAdd(&s.counts[(size_t)site * 6 + 5], 1u);  // no_ins++ (1903 / 1952)
+}
+
+struct NoTie {  // the fp64 kernels: every decision bit is the reference's own double comparison
+  static constexpr bool kTrack = false;
+  __device__ __forceinline__ bool match(int, int) const { return false; }
+  template <class Cell>
+  __device__ __forceinline__ bool resolve(const Cell&, int, int, int) const { return true; }
+};
+
+// Tie: kTrack (follow the rational value r36 of the path), match(i, j), resolve(cell, pi, pj, r36).
+// smask: the walker's lanes within the warp, base: its first lane, sl: this lane's index in the walker.
+// segs: PM_WALK_SEGS records written by lane 0 of the walker; *n_segs = number written, or -1 when the path has more
+// segments than that (the caller then applies it with the serial walk_path<true>).
+template <int NL, class Cell, class Tie>
+__device__ int coop_walk(const Cell& cell, const Tie& tie, unsigned smask, int base, int sl, int k, int i, int j, int r36,
+                         uint2* segs, int* n_segs) {
+  int nseg = 0, ot = -1, oi = 0, oj = 0, ol = 0;  // ot..ol: the open segment
+  bool over = false;
+  auto flush = [&]() {
+    if (ot >= 0) {
+      if (nseg < PM_WALK_SEGS) {
+        if (sl == 0) segs[nseg] = make_uint2((unsigned)oi | ((unsigned)oj << 16), (unsigned)ol | ((unsigned)ot << 16));
+        nseg++;
+      } else {
+        over = true;
+      }
+    }
+  };
+  auto add = [&](int type, int si, int sj, int len) {
+    if (type == ot) { ol += len; return; }   // consecutive steps of one type are contiguous
+    flush();
+    ot = type; oi = si; oj = sj; ol = len;
+  };
+  while (i > 0 && j > 0) {
+    if (k == 0) {
+      // iteration t of the serial walk would stand at (i - t, j - t) in state 0 and consult cell (i-t-1, j-t-1)
+      const int ci = i - sl, cj = j - sl;
+      int c = 0;
+      bool clean = false, mt = false;
+      if (Tie::kTrack && ci > 0 && cj > 0) mt = tie.match(ci, cj);
+      if (ci > 1 && cj > 1) {
+        c = cell(ci - 1, cj - 1);
+        clean = c >= 0 && (c & 0x33) == 0;     // stays in state 0, no equal integers involved
+      }
+      const unsigned dirty = (__ballot_sync(smask, !clean) >> base) & ((NL == 32) ? 0xFFFFFFFFu : ((1u << NL) - 1u));
+      const unsigned mbits = Tie::kTrack ? (__ballot_sync(smask, mt) >> base) : 0u;
+      const int ts = dirty ? __ffs((int)dirty) - 1 : NL;   // iterations 0 .. ts-1 are plain diagonal steps
+      if (Tie::kTrack) {
+        const int nm = __popc(mbits & ((ts >= 32) ? 0xFFFFFFFFu : ((1u << ts) - 1u)));
+        r36 -= 36 * nm - 12 * (ts - nm);
+      }
+      if (ts > 0) add(0, i, j, ts);
+      i -= ts;
+      j -= ts;
+      if (ts < NL) {  // the iteration at (i, j): its cell is the one lane ts looked at
+        const int cc = __shfl_sync(smask, c, base + ts);
+        if (Tie::kTrack) r36 -= ((mbits >> ts) & 1u) ? 36 : -12;   // value of M[i-1][j-1]
+        int pk = 0;
+        if (i > 1 && j > 1) {
+          if (cc < 0) return PM_WALK_OOB;
+          if ((cc & 3) == 3) return PM_WALK_TIE;
+          if (Tie::kTrack && (cc & 48)) {
+            const int t5 = ((cc & 3) == 2) ? 4 : ((1 << (cc & 3)) | ((cc & 16) ? 3 : 0) | ((cc & 32) ? 4 : 0));  // top_set
+            if (t5 & (t5 - 1)) {
+              int ok = 1;
+              if (sl == 0) ok = tie.resolve(cell, i - 1, j - 1, r36) ? 1 : 0;
+              ok = __shfl_sync(smask, ok, base);
+              if (!ok) return PM_WALK_TIE;
+            }
+          }
+          pk = cc & 3;
+        }
+        add(0, i, j, 1);
+        i--;
+        j--;
+        k = pk;
+      }
+    } else if (k == 2) {
+      const int pj = j - 1;
+      int pk = 0;
+      if (pj > 0) {
+        const int c = cell(i, pj);
+        if (c < 0) return PM_WALK_OOB;
+        if ((c & 3) == 3) return PM_WALK_TIE;
+        pk = (c & 8) ? 2 : 0;
+      }
+      if (Tie::kTrack) r36 += pk == 2 ? 1 : 72;
+      add(2, i, j, 1);
+      j = pj;
+      k = pk;
+    } else {
+      const int pi = i - 1;
+      int pk = 0;
+      if (pi > 0) {
+        const int c = cell(pi, j);
+        if (c < 0) return PM_WALK_OOB;
+        if ((c & 3) == 3) return PM_WALK_TIE;
+        pk = (c & 4) ? 1 : 0;
+      }
+      if (Tie::kTrack) r36 += pk == 1 ? 1 : 72;
+      add(1, i, j, 1);
+      i = pi;
+      k = pk;
+    }
+  }
+  flush();
+  *n_segs = over ? -1 : nseg;
+  return PM_WALK_OK;
+}
+
+// the pileup increments of a recorded path (1846-1958), by all NL lanes of the walker
+template <int NL>
+__device__ void coop_apply(const uint2* segs, int nseg, unsigned smask, int sl, const char* read, int mm, int orient,
+                           uint32_t wstart, const PileSink& sink, const unsigned char* qcode, int qshift) {
+  __syncwarp(smask);
+  int pend_n = 0, pend_j = 0, pend_i = 0;
+  for (int s = 0; s < nseg; s++) {
+    const uint2 sg = segs[s];
+    const int si = (int)(sg.x & 0xFFFFu), sj = (int)(sg.x >> 16), len = (int)(sg.y & 0xFFFFu), type = (int)(sg.y >> 16);
+    if (type == 2) {  // insertion: read columns sj-1 down to sj-len wait for the next consumed reference base (1910-1911)
+      pend_n = len;
+      pend_j = sj;
+      pend_i = si;
+      continue;
+    }
+    if (pend_n > 0 && sl == 0) sink_insertion_direct(sink, wstart + (uint32_t)(si - 1), read, mm, orient, pend_j - pend_n, pend_n);
+    pend_n = 0;
+    for (int u = sl; u < len; u += NL) {
+      const size_t site = (size_t)wstart + (size_t)(si - 1 - u);
+      if (type == 0) {  // 1846-1858
+        const int col = code_column((qcode[sj - 1 - u] >> qshift) & 15u);
+        if (col >= 0) atomicAdd(&sink.counts[site * 6 + col], 1u);
+      } else {
+        atomicAdd(&sink.counts[site * 6 + 4], 1u);  // 1868
+      }
+    }
+  }
+  // the walk ended inside an insertion: attached to the row it stood on (1918-1958)
+  if (pend_n > 0 && sl == 0) sink_insertion_direct(sink, wstart + (uint32_t)(pend_i - 1), read, mm, orient, pend_j - pend_n, pend_n);
+  __syncwarp(smask);
+}
+
 // accessor over the shared-memory band store of one group: rows x PM_BAND_LANES 64-bit words
 // (half = lanes kept on each side of the centre lane, <= PM_BAND_LANES / 2; smaller values only exist to test the
 // out-of-band hand-over)
