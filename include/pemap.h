@@ -99,6 +99,7 @@ typedef struct pemap_stats {
   uint64_t exact_traced;    /* winners whose integer traceback met a rational tie and was redone in fp64 */
   double ms_tb_diag, ms_tb_int, ms_tb_fp64; /* ms_traceback split: pure-diagonal pileup, integer traceback, fp64 traceback */
   uint64_t tb_cells_int;    /* cells recomputed by the integer traceback kernel */
+  uint64_t sw_cells_certified; /* part of sw_cells whose candidates were decided by the ungapped-diagonal certificate, no DP */
 } pemap_stats;
 
 typedef struct pemap_ctx pemap_t;

@@ -91,6 +91,8 @@ struct pemap_ctx {
   pm::Winner* d_replay_tasks = nullptr;
   int band_half = PM_BAND_LANES / 2;  // PEMAP_BAND_HALF=0/1 narrows the traceback band (tests of the hand-over path)
   int trace32 = 0;
+  uint32_t* d_sw_list = nullptr;  // tasks left for the DP scoring kernel by k_diag_certify
+  int certify = 1;                // PEMAP_CERTIFY=0: score every candidate with the DP (cross-check)
   void* d_flagq = nullptr;      // packed decision flags between k_trace_dp16 and k_trace_walk16
   size_t flagq_bytes = 0;
   int* d_pair_dmid = nullptr;
@@ -259,7 +261,9 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   h->task_cap = (uint32_t)std::min<size_t>(2 * n * PM_MAX_HITS, 0x7FFFFFFFull);
   CK(cudaMalloc(&h->d_tasks, (size_t)h->task_cap * sizeof(pm::Task)));
   CK(cudaMalloc(&h->d_results, (size_t)h->task_cap * sizeof(pm::TaskResult)));
-  CK(cudaMalloc(&h->d_cursors, 64));
+  CK(cudaMalloc(&h->d_cursors, 128));
+  CK(cudaMalloc(&h->d_sw_list, (size_t)h->task_cap * 4));
+  if (const char* s = getenv("PEMAP_CERTIFY")) h->certify = atoi(s) != 0;
   CK(cudaMalloc(&h->d_ires, (size_t)h->task_cap * sizeof(pm::ITaskResult)));
   CK(cudaMalloc(&h->d_replay_reads, n * 4));
   CK(cudaMalloc(&h->d_replay_tasks, (size_t)h->task_cap * sizeof(pm::Winner)));
@@ -516,7 +520,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   const bool paired = h->params.pair_flag && d_r2;
   const bool exact = h->exact || (h->keep & PEMAP_KEEP_DETAIL) || h->params.match_bonus != 1.0;
   CK(cudaMemsetAsync(h->d_cursors, 0, 16, h->stream));
-  CK(cudaMemsetAsync(h->d_cursors + 6, 0, 40, h->stream));  // [6..8] lists, [9..15] work counters of the persistent kernels
+  CK(cudaMemsetAsync(h->d_cursors + 6, 0, 44, h->stream));  // [6..8] lists, [9..15] work counters of the persistent kernels, [16] DP list
   CK(cudaEventRecord(ev[0], h->stream));
   pm::SeedArgs sa;
   sa.pos_index = h->d_pos_index;
@@ -627,6 +631,27 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     ia.genome = h->d_genome;
     ia.lane_mm = -1;
     ia.p = sa.p;
+    ia.list = nullptr;
+    if (h->certify) {  // candidates decided by their ungapped diagonals alone skip the DP
+      pm::CertifyArgs ca;
+      ca.tasks = h->d_tasks;
+      ca.results = h->d_ires;
+      ca.n_items = h->d_cursors;
+      ca.list = h->d_sw_list;
+      ca.list_cursor = h->d_cursors + 16;
+      ca.reads[0] = d_r1;
+      ca.reads[1] = d_r2;
+      ca.len[0] = d_l1;
+      ca.len[1] = d_l2;
+      ca.stride = stride;
+      ca.genome = h->d_genome;
+      ca.cells_certified = &h->d_counters->sw_cells_certified;
+      ca.p = sa.p;
+      pm::k_diag_certify<4><<<h->sm_count * 16, 128, 0, h->stream>>>(ca);
+      h->stats.launches++;
+      ia.list = h->d_sw_list;
+      ia.n_items = h->d_cursors + 16;
+    }
     dispatch_sw_int(h, ia, max_len, uniform_len);
     CK(cudaEventRecord(ev[2], h->stream));
     pm::SelectIntArgs si;
@@ -810,6 +835,7 @@ int fetch_counters(pemap_ctx* h) {
   h->stats.diag_traced = c.diag_traced;
   h->stats.exact_traced = c.exact_traced;
   h->stats.tb_cells_int = c.tb_cells_int;
+  h->stats.sw_cells_certified = c.sw_cells_certified;
   return PEMAP_OK;
 }
 
@@ -1333,7 +1359,7 @@ void pemap_destroy(pemap_t* h) {
                    h->d_tasks, h->d_results, h->d_cursors,
                    h->d_cand_base, h->d_cand_n, h->d_winners, h->d_det_best, h->d_det_orient,
                    h->d_det_score, h->d_seed_scratch, h->d_dirs, h->d_pend, h->d_counters, h->d_ires, h->d_replay_reads,
-                   h->d_replay_tasks, h->d_diag_winners, h->d_exact_winners, h->d_oob_winners, h->d_flagq, h->d_pair_dmid, h->d_pair_codes};
+                   h->d_replay_tasks, h->d_diag_winners, h->d_exact_winners, h->d_oob_winners, h->d_flagq, h->d_pair_dmid, h->d_pair_codes, h->d_sw_list};
     for (void* p : dev)
       if (p) cudaFree(p);
     for (auto& sl : h->slots) {

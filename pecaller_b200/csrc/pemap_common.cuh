@@ -42,7 +42,8 @@ struct Winner {
 };
 
 struct SeedCounters {  // device-side statistics, accumulated with atomics once per warp
-  unsigned long long lookups, mer_positions, candidates, sw_cells, tb_cells, replayed, diag_traced, exact_traced, tb_cells_int;
+  unsigned long long lookups, mer_positions, candidates, sw_cells, tb_cells, replayed, diag_traced, exact_traced, tb_cells_int,
+      sw_cells_certified;  // cells of the candidates k_diag_certify resolved without the DP
 };
 
 __host__ __device__ __forceinline__ double dmax(double a, double b) { return (a > b) ? a : b; }  // maxim(), pemapper.c:36

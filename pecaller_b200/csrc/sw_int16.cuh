@@ -31,7 +31,8 @@ struct ITaskResult {
 struct SwIntArgs {
   const Task* tasks;
   ITaskResult* results;
-  const uint32_t* n_items;
+  const uint32_t* n_items;   // number of tasks to score (entries of `list` when it is set)
+  const uint32_t* list;      // task ids left over by k_diag_certify, or nullptr: every task
   uint32_t* work;   // zeroed per launch: next pair to score
   const char* reads[2];
   const int* len[2];
@@ -90,7 +91,11 @@ __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
   for (;;) {
     const uint32_t pair = next_work_item<G>(a.work, gmask, gl);
     if (pair >= n_pairs) break;
-    const uint32_t idA = 2 * pair, idB = (2 * pair + 1 < n_items) ? 2 * pair + 1 : 2 * pair;
+    uint32_t idA = 2 * pair, idB = (2 * pair + 1 < n_items) ? 2 * pair + 1 : 2 * pair;
+    if (a.list) {
+      idA = a.list[idA];
+      idB = a.list[idB];
+    }
     const Task tA = a.tasks[idA], tB = a.tasks[idB];
     const int orA = (int)(tA.rm >> 31), orB = (int)(tB.rm >> 31);
     const uint32_t rmA = tA.rm & 0x7FFFFFFFu, rmB = tB.rm & 0x7FFFFFFFu;
@@ -252,6 +257,142 @@ __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
       a.results[idB] = r;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_diag_certify: candidates whose result follows from their ungapped diagonals alone skip the DP.
+//
+// In units of 1/36 every DP value of column j is either the sum of one whole diagonal started at column 0
+// (S0[i-j][0] = 0: the free start of the semi-global alignment) or the value of a path with a gap or a row-0 border
+// start, and those are <= 36 j - 72 (induction over 1710-1713 with the borders 2062-2081: every read base adds at
+// most +36 and the first gap or border costs at least 72).  A diagonal with at most one mismatch scores
+// >= 36 j - 48 at every column, i.e. 24 above anything with a gap.  So if, among the K + 1 = nn - mm + 1 whole
+// diagonals of the window, EXACTLY ONE has <= 1 mismatches (say offset o, m mismatches) then, with no rounding
+// involved anywhere:
+//   * on that diagonal S0[j+o][j] is its prefix sum and S1, S2 are at least 24 below it: the traceback from its
+//     last cell is the pure state-0 diagonal decided by strict inequalities (the `flags & 4` of k_sw_i16);
+//   * the last-column scan (1717-1742) has a unique maximum 36 mm - 48 m at (k, i) = (0, o + mm): every other
+//     whole diagonal has >= 2 mismatches (<= 36 mm - 96) and everything else is <= 36 mm - 72.
+// That is the ITaskResult k_sw_i16 would write.  Anything else (no such diagonal, two of them, a character outside
+// ACGT, a window shorter than the read) goes on the list of tasks k_sw_i16 scores.
+// One warp per task, 32 consecutive tasks per warp: lane o tries the first 8 columns of diagonal o, the surviving
+// diagonals are counted in full by all lanes; the left-over tasks of a warp cost one atomic.
+// ---------------------------------------------------------------------------------------------------
+
+struct CertifyArgs {
+  const Task* tasks;
+  ITaskResult* results;
+  const uint32_t* n_items;
+  uint32_t* list;          // tasks that need the DP
+  uint32_t* list_cursor;
+  const char* reads[2];
+  const int* len[2];
+  int stride;
+  const char* genome;
+  unsigned long long* cells_certified;  // sum of nn * mm over the certified tasks
+  DevParams p;
+};
+
+__device__ __forceinline__ bool is_acgt(unsigned ch) {
+  return (ch & 0xE0u) == 0x40u && ((0x0010008Au >> (ch & 31u)) & 1u);  // 'A' 0x41, 'C' 0x43, 'G' 0x47, 'T' 0x54
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_diag_certify(CertifyArgs a) {
+  __shared__ unsigned char s_w[WARPS][PM_DP_MAX + 32];
+  __shared__ unsigned char s_r[WARPS][PM_DP_MAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n_items = *a.n_items;
+  const uint32_t gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
+  unsigned char* w = s_w[warp];
+  unsigned char* q = s_r[warp];
+  const bool bis = a.p.is_bisulfite != 0;
+  unsigned long long cells = 0;
+
+  for (uint32_t t0 = gw * 32u; t0 < n_items; t0 += nw * 32u) {
+    bool mine_needs_dp = false;   // lane t: does task t0 + t need the DP ?
+    const uint32_t t_end = (n_items - t0 < 32u) ? n_items - t0 : 32u;
+    for (uint32_t t = 0; t < t_end; t++) {
+      const uint32_t id = t0 + t;
+      const Task tk = a.tasks[id];
+      const int orient = (int)(tk.rm >> 31);
+      const uint32_t rm = tk.rm & 0x7FFFFFFFu;
+      const int mm = a.len[rm & 1][rm >> 1];
+      const char* read = a.reads[rm & 1] + (size_t)(rm >> 1) * a.stride;
+      const int nn = tk.blen;
+      const int K = nn - mm;                       // whole diagonals: offsets 0 .. K
+      bool ok = K >= 0 && K < 32 && mm >= 8 && nn <= PM_DP_MAX;
+      __syncwarp();
+      if (ok) {
+        bool good = true;
+        for (int i = lane; i < nn; i += 32) {
+          const unsigned ch = (unsigned char)a.genome[(size_t)tk.wstart + i];
+          good &= is_acgt(ch);
+          w[i] = (unsigned char)ch;
+        }
+        for (int j = lane; j < mm; j += 32) {      // the oriented read (reverse strand = reverse_transcribe, 2303-2337)
+          unsigned ch = (unsigned char)read[orient ? mm - 1 - j : j];
+          good &= is_acgt(ch);
+          if (orient) ch ^= (ch & 2u) ? 0x04u : 0x15u;   // A <-> T, C <-> G
+          q[j] = (unsigned char)ch;
+        }
+        ok = __all_sync(0xFFFFFFFFu, good);
+      }
+      __syncwarp();
+      int o_star = -1, m_star = 0;
+      if (ok) {
+        // first 8 columns of diagonal `lane`
+        int mis = 2;
+        if (lane <= K) {
+          mis = 0;
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const unsigned rc = w[lane + j], qc = q[j];
+            mis += !(rc == qc || (bis && rc == 'C' && qc == 'T'));
+          }
+        }
+        unsigned cand = __ballot_sync(0xFFFFFFFFu, mis < 2);
+        int n_good = 0;
+        while (cand) {                              // usually one survivor: count it in full
+          const int o = __ffs((int)cand) - 1;
+          cand &= cand - 1u;
+          int m = 0;
+          for (int j = lane; j < mm; j += 32) {
+            const unsigned rc = w[o + j], qc = q[j];
+            m += !(rc == qc || (bis && rc == 'C' && qc == 'T'));
+          }
+          m = __reduce_add_sync(0xFFFFFFFFu, m);
+          if (m < 2) {
+            n_good++;
+            o_star = o;
+            m_star = m;
+          }
+        }
+        ok = n_good == 1;
+      }
+      if (ok) {
+        if (lane == 0) {
+          ITaskResult r;
+          r.score36 = 36 * mm - 48 * m_star;
+          r.maxi = (uint16_t)(o_star + mm);
+          r.maxk = 0;
+          r.flags = 4;
+          a.results[id] = r;
+          cells += (unsigned long long)nn * (unsigned long long)mm;
+        }
+      } else if (lane == (int)t) {
+        mine_needs_dp = true;
+      }
+    }
+    const unsigned need = __ballot_sync(0xFFFFFFFFu, mine_needs_dp);
+    if (need) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(a.list_cursor, (uint32_t)__popc(need));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (mine_needs_dp) a.list[base + __popc(need & ((1u << lane) - 1u))] = t0 + (uint32_t)lane;
+    }
+  }
+  if (lane == 0 && cells) atomicAdd(a.cells_certified, cells);
 }
 
 // ---------------------------------------------------------------------------------------------------

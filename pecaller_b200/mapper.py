@@ -48,7 +48,7 @@ class Stats(C.Structure):
                 ("ms_traceback", C.c_double), ("ms_total", C.c_double), ("launches", C.c_uint64),
                 ("diag_traced", C.c_uint64), ("exact_traced", C.c_uint64),
                 ("ms_tb_diag", C.c_double), ("ms_tb_int", C.c_double), ("ms_tb_fp64", C.c_double),
-                ("tb_cells_int", C.c_uint64)]
+                ("tb_cells_int", C.c_uint64), ("sw_cells_certified", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
