@@ -267,12 +267,12 @@ __global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
 // start, and those are <= 36 j - 72 (induction over 1710-1713 with the borders 2062-2081: every read base adds at
 // most +36 and the first gap or border costs at least 72).  A diagonal with at most one mismatch scores
 // >= 36 j - 48 at every column, i.e. 24 above anything with a gap.  So if, among the K + 1 = nn - mm + 1 whole
-// diagonals of the window, EXACTLY ONE has <= 1 mismatches (say offset o, m mismatches) then, with no rounding
-// involved anywhere:
+// diagonals of the window, EXACTLY ONE has <= 2 mismatches (say offset o, m mismatches; for m = 2 with the extra
+// condition spelled out in the kernel) then, with no rounding involved anywhere:
 //   * on that diagonal S0[j+o][j] is its prefix sum and S1, S2 are at least 24 below it: the traceback from its
 //     last cell is the pure state-0 diagonal decided by strict inequalities (the `flags & 4` of k_sw_i16);
 //   * the last-column scan (1717-1742) has a unique maximum 36 mm - 48 m at (k, i) = (0, o + mm): every other
-//     whole diagonal has >= 2 mismatches (<= 36 mm - 96) and everything else is <= 36 mm - 72.
+//     whole diagonal has >= 3 mismatches (<= 36 mm - 144) and everything else is below it too.
 // That is the ITaskResult k_sw_i16 would write.  Anything else (no such diagonal, two of them, a character outside
 // ACGT, a window shorter than the read) goes on the list of tasks k_sw_i16 scores.
 // One warp per task, 32 consecutive tasks per warp: lane o tries the first 8 columns of diagonal o, the surviving
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_diag_certify(CertifyArgs a) {
       const char* read = a.reads[rm & 1] + (size_t)(rm >> 1) * a.stride;
       const int nn = tk.blen;
       const int K = nn - mm;                       // whole diagonals: offsets 0 .. K
-      bool ok = K >= 0 && K < 32 && mm >= 8 && nn <= PM_DP_MAX;
+      bool ok = K >= 0 && K < 32 && mm >= 16 && nn <= PM_DP_MAX;
       __syncwarp();
       if (ok) {
         bool good = true;
@@ -341,34 +341,56 @@ __global__ void __launch_bounds__(WARPS * 32) k_diag_certify(CertifyArgs a) {
       __syncwarp();
       int o_star = -1, m_star = 0;
       if (ok) {
-        // first 8 columns of diagonal `lane`
-        int mis = 2;
+        // first and last 8 columns of diagonal `lane`: mismatches, leading and trailing runs of matches
+        int mis = 3, pre = 0, suf = 0;
         if (lane <= K) {
           mis = 0;
+          bool run = true, runs = true;
 #pragma unroll
           for (int j = 0; j < 8; j++) {
             const unsigned rc = w[lane + j], qc = q[j];
-            mis += !(rc == qc || (bis && rc == 'C' && qc == 'T'));
+            const bool mt = rc == qc || (bis && rc == 'C' && qc == 'T');
+            mis += !mt;
+            run = run && mt;
+            pre += run;
+            const unsigned rs = w[lane + mm - 1 - j], qs = q[mm - 1 - j];
+            runs = runs && (rs == qs || (bis && rs == 'C' && qs == 'T'));
+            suf += runs;
           }
         }
-        unsigned cand = __ballot_sync(0xFFFFFFFFu, mis < 2);
-        int n_good = 0;
+        unsigned cand = __ballot_sync(0xFFFFFFFFu, mis < 3);
+        int n_good = 0, p1 = 0;
         while (cand) {                              // usually one survivor: count it in full
           const int o = __ffs((int)cand) - 1;
           cand &= cand - 1u;
-          int m = 0;
+          int m = 0, first = mm + 1;                // first = 1-based column of the first mismatch
           for (int j = lane; j < mm; j += 32) {
             const unsigned rc = w[o + j], qc = q[j];
-            m += !(rc == qc || (bis && rc == 'C' && qc == 'T'));
+            if (!(rc == qc || (bis && rc == 'C' && qc == 'T'))) {
+              m++;
+              first = min(first, j + 1);
+            }
           }
           m = __reduce_add_sync(0xFFFFFFFFu, m);
-          if (m < 2) {
+          if (m < 3) {
             n_good++;
             o_star = o;
             m_star = m;
+            p1 = __reduce_min_sync(0xFFFFFFFFu, first);
           }
         }
         ok = n_good == 1;
+        if (ok && m_star == 2) {
+          // two mismatches score 36 mm - 96: a path with one gap and no mismatch (<= 36 * matched - 72) could reach that.
+          // Such a path is a run of matches from column 1 on one diagonal and a run of matches up to its last column on
+          // another; with A / B the longest leading / trailing runs of the OTHER diagonals it cannot reach any cell of
+          // this diagonal or the last column with as much when A <= p1, B <= mm - p1 and A + B <= mm - 1 (p1 = column
+          // of the first mismatch); two gaps, or a gap and a mismatch, cost >= 120.  tools/certify_bruteforce.py checks
+          // both rules against the full DP.
+          const bool other = lane <= K && lane != o_star;
+          const int A = __reduce_max_sync(0xFFFFFFFFu, other ? pre : 0), B = __reduce_max_sync(0xFFFFFFFFu, other ? suf : 0);
+          ok = A < 8 && B < 8 && A <= p1 && B <= mm - p1 && A + B <= mm - 1;   // a run of 8 may be longer: leave it to the DP
+        }
       }
       if (ok) {
         if (lane == 0) {
