@@ -546,21 +546,26 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   sa.p = h->dp;
   sa.p.pair_flag = paired ? 1 : 0;
   const int work = paired ? 2 * n : n;
-  static int seed_waves[kMaxDev][2] = {};  // one resident wave of the persistent seed kernel, per device and variant
-  const int sv = h->d_filter ? 1 : 0;
+  static int seed_waves[kMaxDev][4] = {};  // one resident wave of the persistent seed kernel, per device and variant
+  const int sv = h->d_filter ? std::min(3, std::max(1, h->filter_k)) : 0;  // bits per k-mer of the filter, 0 = none
   int* seed_wave = seed_waves[h->device % kMaxDev];
   if (!seed_wave[sv]) {
     int per_sm = 0;
-    cudaError_t oe = sv ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_seed_chain<kSeedWarps, true>, kSeedWarps * 32, 0)
-                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_seed_chain<kSeedWarps, false>, kSeedWarps * 32, 0);
+    cudaError_t oe =
+        sv == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_seed_chain<kSeedWarps, 0>, kSeedWarps * 32, 0)
+        : sv == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_seed_chain<kSeedWarps, 1>, kSeedWarps * 32, 0)
+        : sv == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_seed_chain<kSeedWarps, 2>, kSeedWarps * 32, 0)
+                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_seed_chain<kSeedWarps, 3>, kSeedWarps * 32, 0);
     if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
     cudaGetLastError();
     seed_wave[sv] = std::min(h->seed_blocks, per_sm * h->sm_count);
     if (getenv("PEMAP_VERBOSE")) fprintf(stderr, "pemap: seed kernel %d CTAs per SM\n", per_sm);
   }
   const int seed_grid = std::min(seed_wave[sv], (work + kSeedWarps - 1) / kSeedWarps);
-  if (h->d_filter) pm::k_seed_chain<kSeedWarps, true><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
-  else pm::k_seed_chain<kSeedWarps, false><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
+  if (sv == 0) pm::k_seed_chain<kSeedWarps, 0><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
+  else if (sv == 1) pm::k_seed_chain<kSeedWarps, 1><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
+  else if (sv == 2) pm::k_seed_chain<kSeedWarps, 2><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
+  else pm::k_seed_chain<kSeedWarps, 3><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
   h->stats.launches++;
   CK(cudaEventRecord(ev[1], h->stream));
 

@@ -212,11 +212,18 @@ __device__ __forceinline__ bool list_has_in_range(const uint32_t* lst, int n, lo
   return a < n && (long long)lst[a] <= hi;
 }
 
-template <int WARPS, bool FILT>
+// FK = bits per k-mer of the Bloom filter (1..3), 0 = no filter
+template <int WARPS, int FK>
 __global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
+  constexpr bool FILT = FK > 0;
   __shared__ SeedWarpSmem smem[WARPS];
   __shared__ SeedQueueSmem qsmem[FILT ? WARPS : 1];
+  __shared__ uint32_t s_xm[64];   // FILT: xor mask of variant v (kmer_variant), so that the lookup loop has no divisions
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (FILT) {
+    if (threadIdx.x < 64) s_xm[threadIdx.x] = (threadIdx.x > 0 && threadIdx.x < PM_KV) ? kmer_variant(0u, (int)threadIdx.x) : 0u;
+    __syncthreads();
+  }
   SeedWarpSmem& sm = smem[warp];
   const int gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
   uint32_t* lists = a.scratch + (size_t)gw * (2 * PM_MAX_SEG * PM_SEG_CAP);
@@ -273,20 +280,34 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
       if (FILT) {
         SeedQueueSmem& qs = qsmem[warp];
         int qn = 0;  // warp-uniform queue length
+        // lookup q = 32 * step + lane is variant vq of (strand, segment) sq: both advance without a division
+        int sq = 0, vq = lane;
+        const int nss = 2 * nseg;
         for (int q0 = 0; q0 < L; q0 += 32 * PM_SEED_UNROLL) {
           uint32_t codes[PM_SEED_UNROLL], fw[PM_SEED_UNROLL], fm[PM_SEED_UNROLL];
+          int ssu[PM_SEED_UNROLL];
 #pragma unroll
           for (int u = 0; u < PM_SEED_UNROLL; u++) {
-            const int q = q0 + u * 32 + lane;
             fw[u] = 0;
             fm[u] = 1;
             codes[u] = 0;
-            if (q < L) {
-              const int ss = q / PM_KV, v = q - ss * PM_KV;
-              codes[u] = kmer_variant(sm.kcode[ss], v);
-              uint32_t word;
-              filter_slot(codes[u], a.filter_shift, a.filter_k, &word, &fm[u]);
-              fw[u] = a.filter[word];  // L2-resident (persisting window)
+            ssu[u] = sq;
+            if (sq < nss) {
+              codes[u] = sm.kcode[sq] ^ s_xm[vq];
+              uint32_t x = codes[u] * 0x9E3779B1u;   // filter_slot with the number of bits fixed at compile time
+              x ^= x >> 15;
+              x *= 0x85EBCA77u;
+              x ^= x >> 13;
+              uint32_t m = 1u << (x & 31u);
+              if (FK > 1) m |= 1u << ((x >> 5) & 31u);
+              if (FK > 2) m |= 1u << ((x >> 10) & 31u);
+              fm[u] = m;
+              fw[u] = a.filter[x >> a.filter_shift];  // L2-resident (persisting window)
+            }
+            vq += 32;
+            if (vq >= PM_KV) {
+              vq -= PM_KV;
+              sq++;
             }
           }
 #pragma unroll
@@ -296,7 +317,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
             if (pass) {
               const int at = qn + __popc(bal & ((1u << lane) - 1u));
               qs.code[at] = codes[u];
-              qs.ss[at] = (uint8_t)((q0 + u * 32 + lane) / PM_KV);
+              qs.ss[at] = (uint8_t)ssu[u];
             }
             qn += __popc(bal);
           }

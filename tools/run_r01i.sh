@@ -1,3 +1,3 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_j.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_j.log
-tail -n 4 gpurun_out/pytest_j.log
-PEMAP_VERBOSE=1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_j.json 2> gpurun_out/bench_j.err
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_k.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_k.log
+tail -n 4 gpurun_out/pytest_k.log
+PEMAP_VERBOSE=1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_k.json 2> gpurun_out/bench_k.err
