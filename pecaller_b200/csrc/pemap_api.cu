@@ -78,6 +78,9 @@ struct pemap_ctx {
     bool paired = false, direct = false;
   } slots[2];
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaStream_t s_aux = nullptr;            // the pure-diagonal pileup runs beside the integer traceback
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int diag_overlap = 1;                    // PEMAP_DIAG_OVERLAP=0: k_apply_diag on the compute stream
   pm::Task* d_tasks = nullptr;
   pm::TaskResult* d_results = nullptr;
   uint32_t task_cap = 0;
@@ -230,6 +233,10 @@ int open_device(pemap_ctx* h, int device) {
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  if (const char* s = getenv("PEMAP_DIAG_OVERLAP")) h->diag_overlap = atoi(s) != 0;
   for (auto& sl : h->slots) {
     for (auto& ev : sl.ev) CK(cudaEventCreate(&ev));
     CK(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
@@ -519,6 +526,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
               int max_len, int uniform_len, uint32_t* d_m1, uint32_t* d_m2, int* d_type, cudaEvent_t* ev) {
   const bool paired = h->params.pair_flag && d_r2;
   const bool exact = h->exact || (h->keep & PEMAP_KEEP_DETAIL) || h->params.match_bonus != 1.0;
+  bool forked = false;
   CK(cudaMemsetAsync(h->d_cursors, 0, 16, h->stream));
   CK(cudaMemsetAsync(h->d_cursors + 6, 0, 44, h->stream));  // [6..8] lists, [9..15] work counters of the persistent kernels, [16] DP list
   CK(cudaEventRecord(ev[0], h->stream));
@@ -709,7 +717,17 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     da.stride = stride;
     da.counts = h->d_counts;
     da.counters = h->d_counters;
-    pm::k_apply_diag<<<h->sm_count * 8, 256, 0, h->stream>>>(da);
+    // k_apply_diag is bound by L2 atomics and leaves the ALUs idle; the integer traceback is the opposite.  Two CTAs
+    // per SM on a side stream leave room for the traceback kernels' resident waves; joined before ev[4].
+    forked = h->diag_overlap != 0;
+    if (forked) {
+      CK(cudaEventRecord(h->ev_fork, h->stream));
+      CK(cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0));
+      pm::k_apply_diag<<<h->sm_count * 2, 256, 0, h->s_aux>>>(da);
+      CK(cudaEventRecord(h->ev_join, h->s_aux));
+    } else {
+      pm::k_apply_diag<<<h->sm_count * 8, 256, 0, h->stream>>>(da);
+    }
     h->stats.launches++;
     CK(cudaEventRecord(ev[5], h->stream));
     // the other winners: integer traceback; the ones with a rational tie on their path fall through to fp64
@@ -754,6 +772,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   wa.n_items = h->d_cursors + 8;
   wa.work = h->d_cursors + 14;
   dispatch_sw<1>(h, wa, max_len);
+  if (forked) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   CK(cudaEventRecord(ev[4], h->stream));
   CK(cudaGetLastError());
   return PEMAP_OK;
@@ -1381,6 +1400,9 @@ void pemap_destroy(pemap_t* h) {
     }
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    if (h->s_aux) cudaStreamDestroy(h->s_aux);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     cudaStreamDestroy(h->stream);
   }
   delete h;

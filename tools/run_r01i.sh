@@ -1,3 +1,4 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_k.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_k.log
-tail -n 4 gpurun_out/pytest_k.log
-PEMAP_VERBOSE=1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_k.json 2> gpurun_out/bench_k.err
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_l.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_l.log
+tail -n 4 gpurun_out/pytest_l.log
+PEMAP_VERBOSE=1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_l.json 2> gpurun_out/bench_l.err
+PEMAP_DIAG_OVERLAP=0 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_l0.json 2> gpurun_out/bench_l0.err
