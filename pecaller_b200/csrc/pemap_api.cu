@@ -1378,6 +1378,17 @@ void pemap_destroy(pemap_t* h) {
   if (h->stream) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+#ifdef PM_TIE_DEBUG
+    {
+      unsigned long long why[32];
+      if (cudaMemcpyFromSymbol(why, pm::g_tie_why, sizeof(why)) == cudaSuccess) {
+        fprintf(stderr, "pemap tie debug:");
+        for (int i = 0; i < 32; i++)
+          if (why[i]) fprintf(stderr, " [%d]=%llu", i, i >= 16 ? why[i] / 32 : why[i]);
+        fprintf(stderr, "\n");
+      }
+    }
+#endif
     if (h->d_filter) cudaCtxResetPersistingL2Cache();  // give the persisting carve-out back
     void* dev[] = {h->d_filter, h->d_pos_index, h->d_mers, h->d_genome, h->d_cstart, h->d_border, h->d_counts, h->d_ins, h->d_ins_cursor,
                    h->d_tasks, h->d_results, h->d_cursors,

@@ -10,6 +10,14 @@
 #define PM_MAX_HITS 200      // max_hits (pemapper.c:162)
 #define PM_DP_MAX 320        // padded read columns / window rows a DP kernel can be instantiated for
 
+// -DPM_TIE_DEBUG: count why winners leave the integer traceback for the fp64 kernel (printed by pemap_destroy)
+#ifdef PM_TIE_DEBUG
+namespace pm { __device__ unsigned long long g_tie_why[32]; }
+#define PM_WHY(x) atomicAdd(&pm::g_tie_why[x], 1ull)
+#else
+#define PM_WHY(x)
+#endif
+
 namespace pm {
 
 struct DevParams {

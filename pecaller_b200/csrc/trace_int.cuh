@@ -129,17 +129,17 @@ __device__ __forceinline__ bool chain_step(const Cell& cell, const TieCtx& t, Ch
   if (p.k == 0) {
     const bool match = cells_match(t, p.i, p.j);
     const int prev = p.r - (match ? 36 : -12);          // M[i-1][j-1]
-    if (!chain_book(p, prev, match ? 0 : 1, b0)) return false;
+    if (!chain_book(p, prev, match ? 0 : 1, b0)) { PM_WHY(match ? 11 : 1); return false; }
     p.i--; p.j--; p.r = prev;
     if (p.i == 0 || p.j == 0) { p.k = 0; return true; } // M of a border cell: every state there is handled above
     const int c = cell(p.i, p.j);
-    if (c < 0 || (c & 3) == 3) return false;
+    if (c < 0 || (c & 3) == 3) { PM_WHY(2); return false; }
     const int ts = top_set(c);
     if (ts & (ts - 1)) {                                // shared maximum: certify it later
       bool seen = false;
       for (int q = 0; q < wl_n; q++) seen |= (wl_i[q] == p.i && wl_j[q] == p.j);
       if (!seen) {
-        if (wl_n >= PM_TIE_LIST) return false;
+        if (wl_n >= PM_TIE_LIST) { PM_WHY(3); return false; }
         wl_i[wl_n] = p.i; wl_j[wl_n] = p.j; wl_n++;
       }
     }
@@ -152,22 +152,22 @@ __device__ __forceinline__ bool chain_step(const Cell& cell, const TieCtx& t, Ch
     // from a border cell: opening from S0 = 0 (column 0) is exact; everything else involves a rounded value
     if (p.k == 2 && pj == 0) {                          // S2[i][1] = max(0 - go, -go - ge) = -go, exact
       const int prev = p.r + 72;
-      if (!chain_book(p, prev, 0, b0)) return false;
+      if (!chain_book(p, prev, 0, b0)) { PM_WHY(4); return false; }
       p.i = pi; p.j = pj; p.k = 0; p.r = prev;
       return true;
     }
-    return false;
+    { PM_WHY(5); return false; }
   }
   const int c = cell(pi, pj);
-  if (c < 0 || (c & 3) == 3) return false;
+  if (c < 0 || (c & 3) == 3 || (c & (p.k == 1 ? 64 : 128))) { PM_WHY(2); return false; }
   if (c & (p.k == 1 ? 4 : 8)) {                         // extension: - 1/36 rounds; the gap state continues
     const int prev = p.r + 1;
-    if (!chain_book(p, prev, 2, b0)) return false;
+    if (!chain_book(p, prev, 2, b0)) { PM_WHY(6); return false; }
     p.i = pi; p.j = pj; p.r = prev;
     return true;
   }
   const int prev = p.r + 72;                            // opening: - 2.0
-  if (!chain_book(p, prev, 0, b0)) return false;
+  if (!chain_book(p, prev, 0, b0)) { PM_WHY(7); return false; }
   p.i = pi; p.j = pj; p.k = 0; p.r = prev;
   return true;
 }
@@ -187,7 +187,7 @@ __device__ bool resolve_tie(const Cell& cell, const TieCtx& t, int i, int j, int
   wl_i[0] = i; wl_j[0] = j; wl_r[0] = r36;
   for (int w = 0; w < wl_n; w++) {
     const int c = cell(wl_i[w], wl_j[w]);
-    if (c < 0 || (c & 3) == 3) return false;
+    if (c < 0 || (c & 3) == 3) { PM_WHY(2); return false; }
     const int ts = top_set(c);
     const int first = __ffs(ts) - 1;
     const int b0 = binade36(wl_r[w]);
@@ -208,13 +208,13 @@ __device__ bool resolve_tie(const Cell& cell, const TieCtx& t, int i, int j, int
         if (joined) {
           if (A.exact && B.exact) break;
           if (A.same && B.same && A.sig == B.sig && A.n_round == B.n_round) break;
-          return false;
+          { PM_WHY(8); return false; }
         }
         if (A.end && B.end) {
           if (A.end == 1 && B.end == 1 && A.exact && B.exact) break;  // two exact constants plus integers
-          return false;
+          { PM_WHY(9); return false; }
         }
-        if (--budget < 0) return false;
+        if (--budget < 0) { PM_WHY(10); return false; }
         // advance the one farther from the origin (the only one that can still reach the other)
         const bool stepA = !A.end && (B.end || A.i + A.j > B.i + B.j || (A.i + A.j == B.i + B.j && A.i >= B.i));
         ChainPos& p = stepA ? A : B;
@@ -405,9 +405,11 @@ __global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
 // TWO winners are packed per lane (s16x2, biased by PM_TBIAS like sw_int16.cuh) and the decision flags are extracted
 // with SWAR compares: for halves a, b in [0, 2^15), (a + 0x8000 - b) has bit 15 set iff a >= b, and neither half
 // borrows from the other.  Six flags per cell and half:
-//     F0  S1 > S0 (or X tie)      F1  S2 > max(S0,S1)     F2  X1     F3  X2
-//     F4  S1 == S0 (or X tie)     F5  S2 == max(S0,S1)
-// (F0 and F4 both set cannot happen otherwise and marks the cell like A == 3 above.)
+//     F0  S1 > S0                 F1  S2 > max(S0,S1)     F2  X1     F3  X2
+//     F4  S1 == S0, or X1 tie     F5  S2 == max(S0,S1), or X2 tie
+// (S1 >= S0 implies X1, so F4 without F2 is free to mean "S1 - ge == S0 - go"; likewise F5 without F3 for X2.  The
+// accessor turns them into bits 6 / 7; the A decision of such a cell stays usable, unlike with the A == 3 mark of
+// k_trace_i32.)
 //
 // Only the cells near the winners' end diagonal are ever consulted by the walk: lane l (columns WD*l+1 .. WD*l+WD)
 // is "in the band" for the nb = (half+1)*WD rows starting at r0(l) = WD*l - WD/2 + dmid + 1, and at any step of the
@@ -454,8 +456,10 @@ struct LaneBandCell {
     const uint2 w = fl[r * G + l];
     const int f0 = (w.x >> c) & 1, f1 = (w.x >> (WD + c)) & 1, f2 = (w.x >> (2 * WD + c)) & 1;
     const int f3 = (w.y >> c) & 1, f4 = (w.y >> (WD + c)) & 1, f5 = (w.y >> (2 * WD + c)) & 1;
-    if (f0 & f4) return 3;  // an X decision compared equal integers: undecidable here
-    return (f1 ? 2 : f0) | (f2 << 2) | (f3 << 3) | (f4 << 4) | (f5 << 5);
+    // S1 >= S0 implies X1 and S2 >= max(S0,S1) implies X2, so "equal" without the X flag is free to mark an X tie:
+    // bits 6 / 7 = the X1 / X2 comparison met equal integers (only a walk that ENTERS the cell in a gap state cares)
+    return (f1 ? 2 : f0) | (f2 << 2) | (f3 << 3) | ((f4 & f2) << 4) | ((f5 & f3) << 5) | ((f4 & ~f2 & 1) << 6) |
+           ((f5 & ~f3 & 1) << 7);
   }
 };
 
@@ -654,13 +658,13 @@ __global__ void __launch_bounds__(128) k_trace_dp16(TraceIntArgs a) {
             const uint32_t g = s0 + H - s1, g2 = s1 + H - s0;                  // S0 >= S1, S1 >= S0
             const uint32_t hh = x01 + H - s2, h2 = s2 + H - x01;               // max01 >= S2, S2 >= max01
             const uint32_t w1 = s1 + HX - s0, w2 = s2 + HX - s0;               // X1, X2
-            const uint32_t tx = ((w1 + K1) & ~w1) | ((w2 + K1) & ~w2);         // S1 + 71 == S0 or S2 + 71 == S0
-            a0 = (a0 >> 1) | ((~g | tx) & H);
+            const uint32_t tx1 = (w1 + K1) & ~w1, tx2 = (w2 + K1) & ~w2;       // S1 + 71 == S0, S2 + 71 == S0
+            a0 = (a0 >> 1) | (~g & H);
             a1 = (a1 >> 1) | (~hh & H);
             a2 = (a2 >> 1) | (w1 & H);
             a3 = (a3 >> 1) | (w2 & H);
-            a4 = (a4 >> 1) | (((g & g2) | tx) & H);
-            a5 = (a5 >> 1) | (hh & h2 & H);
+            a4 = (a4 >> 1) | (((g & g2) | tx1) & H);
+            a5 = (a5 >> 1) | (((hh & h2) | tx2) & H);
             s0u[c] = s0;
             s1u[c] = s1;
             mu[c] = m - K12;

@@ -204,15 +204,15 @@ __device__ int coop_walk(const Cell& cell, const Tie& tie, unsigned smask, int b
         if (Tie::kTrack) r36 -= ((mbits >> ts) & 1u) ? 36 : -12;   // value of M[i-1][j-1]
         int pk = 0;
         if (i > 1 && j > 1) {
-          if (cc < 0) return PM_WALK_OOB;
-          if ((cc & 3) == 3) return PM_WALK_TIE;
+          if (cc < 0) { PM_WHY(16); return PM_WALK_OOB; }
+          if ((cc & 3) == 3) { PM_WHY(17); return PM_WALK_TIE; }
           if (Tie::kTrack && (cc & 48)) {
             const int t5 = ((cc & 3) == 2) ? 4 : ((1 << (cc & 3)) | ((cc & 16) ? 3 : 0) | ((cc & 32) ? 4 : 0));  // top_set
             if (t5 & (t5 - 1)) {
               int ok = 1;
               if (sl == 0) ok = tie.resolve(cell, i - 1, j - 1, r36) ? 1 : 0;
               ok = __shfl_sync(smask, ok, base);
-              if (!ok) return PM_WALK_TIE;
+              if (!ok) { PM_WHY(18); return PM_WALK_TIE; }
             }
           }
           pk = cc & 3;
@@ -227,8 +227,8 @@ __device__ int coop_walk(const Cell& cell, const Tie& tie, unsigned smask, int b
       int pk = 0;
       if (pj > 0) {
         const int c = cell(i, pj);
-        if (c < 0) return PM_WALK_OOB;
-        if ((c & 3) == 3) return PM_WALK_TIE;
+        if (c < 0) { PM_WHY(16); return PM_WALK_OOB; }
+        if ((c & 3) == 3 || (c & 128)) { PM_WHY(19); return PM_WALK_TIE; }   // the X2 comparison met equal integers
         pk = (c & 8) ? 2 : 0;
       }
       if (Tie::kTrack) r36 += pk == 2 ? 1 : 72;
@@ -240,8 +240,8 @@ __device__ int coop_walk(const Cell& cell, const Tie& tie, unsigned smask, int b
       int pk = 0;
       if (pi > 0) {
         const int c = cell(pi, j);
-        if (c < 0) return PM_WALK_OOB;
-        if ((c & 3) == 3) return PM_WALK_TIE;
+        if (c < 0) { PM_WHY(16); return PM_WALK_OOB; }
+        if ((c & 3) == 3 || (c & 64)) { PM_WHY(20); return PM_WALK_TIE; }    // the X1 comparison met equal integers
         pk = (c & 4) ? 1 : 0;
       }
       if (Tie::kTrack) r36 += pk == 1 ? 1 : 72;

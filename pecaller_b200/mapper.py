@@ -68,7 +68,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("PEMAP_LIB") or _build.LIB  # PEMAP_LIB: an instrumented build (e.g. -DPM_TIE_DEBUG)
     if not os.path.exists(path):
         if not build_if_missing:
             raise PemapError("CUDA library %s is missing; run __graft_entry__.build()" % path)
