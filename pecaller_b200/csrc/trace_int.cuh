@@ -77,6 +77,7 @@ struct ChainPos {
   int end;          // 0 walking, 1 ended on an exact constant (column 0), 2 ended on the row-0 border cell (0, j)
   bool exact;       // every operation so far was an exact double addition (rule 1)
   bool same;        // every value so far lies strictly inside the binade of the tied value (rule 2)
+  bool pure;        // every operation so far was +-1.0 or -2.0, whatever the binades (rule 3)
   unsigned sig;     // the rounding operations so far, in order: base-3 digits 1 = mismatch (-1/3), 2 = extension (-1/36)
   int n_round;
 };
@@ -109,13 +110,14 @@ __device__ __forceinline__ int top_set(int c) {
 __device__ __forceinline__ bool chain_book(ChainPos& p, int prev, int digit, int b0) {
   if (digit) {
     p.exact = false;
+    p.pure = false;
     if (++p.n_round > PM_TIE_ROUNDS) p.same = false;
     p.sig = p.sig * 3u + (unsigned)digit;
   } else if (!exact_step(prev, p.r)) {
     p.exact = false;
   }
   if (binade36(prev) != b0 || on_boundary36(prev)) p.same = false;
-  return p.exact || p.same;
+  return p.exact || p.same || p.pure;
 }
 
 // One backward step of a value's history.  Returns false when neither certificate can hold any more (see
@@ -125,7 +127,7 @@ template <class Cell>
 __device__ __forceinline__ bool chain_step(const Cell& cell, const TieCtx& t, ChainPos& p, int b0, int* wl_i, int* wl_j,
                                            int& wl_n) {
   if (p.j == 0) { p.end = 1; return true; }             // S0[i][0] = S1[i][0] = 0, S2[i][0] = -go: exact constants
-  if (p.i == 0) { p.end = 2; return true; }             // S*[0][j] = -(go + (j-1) ge): one rounded constant per column
+  if (p.i == 0) { p.end = 2; p.pure = false; return true; }  // S*[0][j] = -(go + (j-1) ge): one rounded constant per column
   if (p.k == 0) {
     const bool match = cells_match(t, p.i, p.j);
     const int prev = p.r - (match ? 36 : -12);          // M[i-1][j-1]
@@ -173,21 +175,30 @@ __device__ __forceinline__ bool chain_step(const Cell& cell, const TieCtx& t, Ch
 }
 
 // Are the doubles of the states sharing the maximum of cell (i, j), of rational value r36 / 36, provably equal?
-// The tied values are traced back in lock step until their histories join.  Two certificates:
+// The tied values are traced back in lock step until their histories join.  Three certificates:
 //  rule 1  both histories consist of exact double additions only (+-1.0, -2.0, never into a higher binade): both
 //          values are the common ancestor (or an exact border constant) plus the same integer;
 //  rule 2  both histories apply the same rounded constants (-1/3, -1/36) in the same order, merely interleaved
 //          differently with integer additions, and every value involved lies strictly inside one binade: there
 //          fl(y + c) - (y + c) depends only on y modulo the (common) ulp, which integer shifts leave alone (they are
-//          even multiples of the ulp, so round-half-even is preserved too); by induction the two values are equal.
+//          even multiples of the ulp, so round-half-even is preserved too); by induction the two values are equal;
+//  rule 3  both histories consist of +-1.0 / -2.0 only, in any binade, and so does EVERYTHING below the point where
+//          they join, down to an exact column-0 constant (0 or -2.0): then every value involved is an integer-valued
+//          double and every operation on it is exact.  The part below the join is the rest of the walk itself, so
+//          the certificate is conditional (return value 2) and the walker gives the winner up if a later step is a
+//          mismatch, a gap extension or a start on a rounded row-0 border.  Ties near the start of the read, where
+//          the binades of rule 1 are a few cells wide, are the typical case.
+// Returns 0 (cannot certify), 1 (equal doubles) or 2 (equal doubles provided the rest of the walk is all-integer;
+// only when allow_cond).
 template <class Cell>
-__device__ bool resolve_tie(const Cell& cell, const TieCtx& t, int i, int j, int r36) {
+__device__ int resolve_tie(const Cell& cell, const TieCtx& t, int i, int j, int r36, bool allow_cond) {
   int wl_i[PM_TIE_LIST], wl_j[PM_TIE_LIST], wl_r[PM_TIE_LIST];
   int wl_n = 1, budget = PM_TIE_BUDGET;
+  bool cond = false;
   wl_i[0] = i; wl_j[0] = j; wl_r[0] = r36;
   for (int w = 0; w < wl_n; w++) {
     const int c = cell(wl_i[w], wl_j[w]);
-    if (c < 0 || (c & 3) == 3) { PM_WHY(2); return false; }
+    if (c < 0 || (c & 3) == 3) { PM_WHY(2); return 0; }
     const int ts = top_set(c);
     const int first = __ffs(ts) - 1;
     const int b0 = binade36(wl_r[w]);
@@ -199,6 +210,7 @@ __device__ bool resolve_tie(const Cell& cell, const TieCtx& t, int i, int j, int
       A.i = B.i = wl_i[w]; A.j = B.j = wl_j[w]; A.r = B.r = wl_r[w];
       A.k = first; B.k = other; A.end = B.end = 0;
       A.exact = B.exact = true;
+      A.pure = B.pure = true;
       A.same = B.same = b0_ok;
       A.sig = B.sig = 0u;
       A.n_round = B.n_round = 0;
@@ -208,23 +220,28 @@ __device__ bool resolve_tie(const Cell& cell, const TieCtx& t, int i, int j, int
         if (joined) {
           if (A.exact && B.exact) break;
           if (A.same && B.same && A.sig == B.sig && A.n_round == B.n_round) break;
-          { PM_WHY(8); return false; }
+          if (allow_cond && A.pure && B.pure && !A.end) {  // rule 3: the walker checks the part below the join
+            cond = true;
+            break;
+          }
+          { PM_WHY(8); return 0; }
         }
         if (A.end && B.end) {
-          if (A.end == 1 && B.end == 1 && A.exact && B.exact) break;  // two exact constants plus integers
-          { PM_WHY(9); return false; }
+          // two exact column-0 constants plus integers: whole histories of integer-valued doubles
+          if (A.end == 1 && B.end == 1 && ((A.exact && B.exact) || (A.pure && B.pure))) break;
+          { PM_WHY(9); return 0; }
         }
-        if (--budget < 0) { PM_WHY(10); return false; }
+        if (--budget < 0) { PM_WHY(10); return 0; }
         // advance the one farther from the origin (the only one that can still reach the other)
         const bool stepA = !A.end && (B.end || A.i + A.j > B.i + B.j || (A.i + A.j == B.i + B.j && A.i >= B.i));
         ChainPos& p = stepA ? A : B;
         const int n0 = wl_n;
-        if (!chain_step(cell, t, p, b0, wl_i, wl_j, wl_n)) return false;
+        if (!chain_step(cell, t, p, b0, wl_i, wl_j, wl_n)) return 0;
         if (wl_n > n0) wl_r[n0] = p.r;                 // value of the shared maximum just queued
       }
     }
   }
-  return true;
+  return cond ? 2 : 1;
 }
 
 // dry walk of the integer kernel: like walk_path<false> but tracks the rational value along the path so that A ties
@@ -240,7 +257,7 @@ __device__ int walk_check_int(const Cell& cell, const TieCtx& t, int k, int i, i
         const int c = cell(pi, pj);
         if (c < 0) return PM_WALK_OOB;
         if ((c & 3) == 3) return PM_WALK_TIE;
-        if ((c & 48) && (top_set(c) & (top_set(c) - 1)) && !resolve_tie(cell, t, pi, pj, r36)) return PM_WALK_TIE;
+        if ((c & 48) && (top_set(c) & (top_set(c) - 1)) && !resolve_tie(cell, t, pi, pj, r36, false)) return PM_WALK_TIE;
         pk = c & 3;
       }
     } else if (k == 2) {
@@ -468,8 +485,8 @@ struct IntTie {
   TieCtx t;
   __device__ __forceinline__ bool match(int i, int j) const { return cells_match(t, i, j); }
   template <class Cell>
-  __device__ __forceinline__ bool resolve(const Cell& cell, int pi, int pj, int r36) const {
-    return resolve_tie(cell, t, pi, pj, r36);
+  __device__ __forceinline__ int resolve(const Cell& cell, int pi, int pj, int r36) const {
+    return resolve_tie(cell, t, pi, pj, r36, true);
   }
 };
 

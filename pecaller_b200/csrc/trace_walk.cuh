@@ -151,10 +151,12 @@ struct NoTie {  // the fp64 kernels: every decision bit is the reference's own d
   static constexpr bool kTrack = false;
   __device__ __forceinline__ bool match(int, int) const { return false; }
   template <class Cell>
-  __device__ __forceinline__ bool resolve(const Cell&, int, int, int) const { return true; }
+  __device__ __forceinline__ int resolve(const Cell&, int, int, int) const { return 1; }
 };
 
-// Tie: kTrack (follow the rational value r36 of the path), match(i, j), resolve(cell, pi, pj, r36).
+// Tie: kTrack (follow the rational value r36 of the path), match(i, j), resolve(cell, pi, pj, r36) -> 0 (undecidable
+// here), 1 (decided), 2 (decided provided every later step of the walk is an exact integer operation: a match or a
+// gap opening, ending on a column-0 border; trace_int.cuh rule 3).
 // smask: the walker's lanes within the warp, base: its first lane, sl: this lane's index in the walker.
 // segs: PM_WALK_SEGS records written by lane 0 of the walker; *n_segs = number written, or -1 when the path has more
 // segments than that (the caller then applies it with the serial walk_path<true>).
@@ -163,6 +165,7 @@ __device__ int coop_walk(const Cell& cell, const Tie& tie, unsigned smask, int b
                          uint2* segs, int* n_segs) {
   int nseg = 0, ot = -1, oi = 0, oj = 0, ol = 0;  // ot..ol: the open segment
   bool over = false;
+  bool need_pure = false;  // a conditional certificate is outstanding
   auto flush = [&]() {
     if (ot >= 0) {
       if (nseg < PM_WALK_SEGS) {
@@ -194,6 +197,7 @@ __device__ int coop_walk(const Cell& cell, const Tie& tie, unsigned smask, int b
       const int ts = dirty ? __ffs((int)dirty) - 1 : NL;   // iterations 0 .. ts-1 are plain diagonal steps
       if (Tie::kTrack) {
         const int nm = __popc(mbits & ((ts >= 32) ? 0xFFFFFFFFu : ((1u << ts) - 1u)));
+        if (need_pure && nm != ts) { PM_WHY(21); return PM_WALK_TIE; }   // a mismatch below a conditional certificate
         r36 -= 36 * nm - 12 * (ts - nm);
       }
       if (ts > 0) add(0, i, j, ts);
@@ -201,7 +205,10 @@ __device__ int coop_walk(const Cell& cell, const Tie& tie, unsigned smask, int b
       j -= ts;
       if (ts < NL) {  // the iteration at (i, j): its cell is the one lane ts looked at
         const int cc = __shfl_sync(smask, c, base + ts);
-        if (Tie::kTrack) r36 -= ((mbits >> ts) & 1u) ? 36 : -12;   // value of M[i-1][j-1]
+        if (Tie::kTrack) {
+          if (need_pure && !((mbits >> ts) & 1u)) { PM_WHY(21); return PM_WALK_TIE; }
+          r36 -= ((mbits >> ts) & 1u) ? 36 : -12;   // value of M[i-1][j-1]
+        }
         int pk = 0;
         if (i > 1 && j > 1) {
           if (cc < 0) { PM_WHY(16); return PM_WALK_OOB; }
@@ -210,9 +217,10 @@ __device__ int coop_walk(const Cell& cell, const Tie& tie, unsigned smask, int b
             const int t5 = ((cc & 3) == 2) ? 4 : ((1 << (cc & 3)) | ((cc & 16) ? 3 : 0) | ((cc & 32) ? 4 : 0));  // top_set
             if (t5 & (t5 - 1)) {
               int ok = 1;
-              if (sl == 0) ok = tie.resolve(cell, i - 1, j - 1, r36) ? 1 : 0;
+              if (sl == 0) ok = tie.resolve(cell, i - 1, j - 1, r36);
               ok = __shfl_sync(smask, ok, base);
               if (!ok) { PM_WHY(18); return PM_WALK_TIE; }
+              if (ok == 2) need_pure = true;
             }
           }
           pk = cc & 3;
@@ -231,7 +239,10 @@ __device__ int coop_walk(const Cell& cell, const Tie& tie, unsigned smask, int b
         if ((c & 3) == 3 || (c & 128)) { PM_WHY(19); return PM_WALK_TIE; }   // the X2 comparison met equal integers
         pk = (c & 8) ? 2 : 0;
       }
-      if (Tie::kTrack) r36 += pk == 2 ? 1 : 72;
+      if (Tie::kTrack) {
+        if (need_pure && pk == 2) { PM_WHY(22); return PM_WALK_TIE; }   // a gap extension (- 1/36) rounds
+        r36 += pk == 2 ? 1 : 72;
+      }
       add(2, i, j, 1);
       j = pj;
       k = pk;
@@ -244,12 +255,17 @@ __device__ int coop_walk(const Cell& cell, const Tie& tie, unsigned smask, int b
         if ((c & 3) == 3 || (c & 64)) { PM_WHY(20); return PM_WALK_TIE; }    // the X1 comparison met equal integers
         pk = (c & 4) ? 1 : 0;
       }
-      if (Tie::kTrack) r36 += pk == 1 ? 1 : 72;
+      if (Tie::kTrack) {
+        if (need_pure && pk == 1) { PM_WHY(22); return PM_WALK_TIE; }
+        r36 += pk == 1 ? 1 : 72;
+      }
       add(1, i, j, 1);
       i = pi;
       k = pk;
     }
   }
+  // the walk ended on the row-0 border -(go + (j-1) ge): a rounded constant unless j == 1
+  if (Tie::kTrack && need_pure && i == 0 && j > 1) { PM_WHY(23); return PM_WALK_TIE; }
   flush();
   *n_segs = over ? -1 : nseg;
   return PM_WALK_OK;
