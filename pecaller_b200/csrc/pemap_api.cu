@@ -288,7 +288,7 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   CK(cudaMalloc(&h->d_det_best, 2 * n * 4));
   CK(cudaMalloc(&h->d_det_orient, 2 * n * 4));
   CK(cudaMalloc(&h->d_det_score, 2 * n * 8));
-  h->seed_blocks = h->sm_count * 8;
+  h->seed_blocks = h->sm_count * PM_SEED_CTAS;
   CK(cudaMalloc(&h->d_seed_scratch, (size_t)h->seed_blocks * kSeedWarps * 2 * PM_MAX_SEG * PM_SEG_CAP * 4));
   h->sw_blocks = h->sm_count * 6;  // upper bound of CTAs per SM of the wavefront kernels (scratch is sized for it)
   const size_t max_groups = (size_t)h->sw_blocks * (128 / 16);
@@ -566,6 +566,13 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_seed_chain<kSeedWarps, 3>, kSeedWarps * 32, 0);
     if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
     cudaGetLastError();
+    // Measured on cfg2 (profiles/README_r01.md, r01e): with the L2-resident filter the kernel is fastest when compiled
+    // for and run at 5 CTAs per SM (62.6 ms per 8.4 M read-mates against 64.3 at 6 and 72.2 at 8; capping the grid of
+    // the 8-CTA build at 5 gains nothing: it is the registers per warp, i.e. the loads each warp keeps in flight).
+    // Without the filter (human-sized genomes) it takes every CTA that fits.
+    int want = sv ? PM_SEED_CTAS_FILT : per_sm;
+    if (const char* s = getenv("PEMAP_SEED_CTAS")) want = std::max(1, atoi(s));
+    per_sm = std::min(per_sm, want);
     seed_wave[sv] = std::min(h->seed_blocks, per_sm * h->sm_count);
     if (getenv("PEMAP_VERBOSE")) fprintf(stderr, "pemap: seed kernel %d CTAs per SM\n", per_sm);
   }

@@ -17,7 +17,16 @@
 #pragma once
 #include "pemap_common.cuh"
 
+#ifndef PM_SEED_UNROLL
 #define PM_SEED_UNROLL 8
+#endif
+#define PM_SEED_CTAS 8          // resident CTAs per SM without the filter; the scratch is sized for it
+#ifndef PM_SEED_CTAS_FILT
+#define PM_SEED_CTAS_FILT 5
+#endif                          // with the filter: fewer, fatter warps (more registers, more loads in flight each)
+#ifndef PM_FILTER_LDCG
+#define PM_FILTER_LDCG 1
+#endif
 
 namespace pm {
 
@@ -128,10 +137,10 @@ __device__ __forceinline__ void seed_lookup_tile(const SeedArgs& a, SeedWarpSmem
         uint32_t off = atomicAdd(&sm.segcnt[ssv[u]], cnt);
         uint32_t* dst = lists + (size_t)ssv[u] * PM_SEG_CAP + off;
         const uint32_t* src = a.mers + lo[u];
-        for (uint32_t t = 0; t < cnt; t++) {
+        for (uint32_t t = 0; t < cnt; t++) {  // the head of a list lives in shared memory only (copied out before a long sort)
           const uint32_t v = __ldcg(src + t);
-          dst[t] = v;
           if (off + t < PM_SLIST) sm.slist[ssv[u]][off + t] = v;
+          else dst[t] = v;
         }
         st_pos += cnt;
       }
@@ -214,7 +223,7 @@ __device__ __forceinline__ bool list_has_in_range(const uint32_t* lst, int n, lo
 
 // FK = bits per k-mer of the Bloom filter (1..3), 0 = no filter
 template <int WARPS, int FK>
-__global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, FK > 0 ? PM_SEED_CTAS_FILT : PM_SEED_CTAS) k_seed_chain(SeedArgs a) {
   constexpr bool FILT = FK > 0;
   __shared__ SeedWarpSmem smem[WARPS];
   __shared__ SeedQueueSmem qsmem[FILT ? WARPS : 1];
@@ -302,7 +311,7 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
               if (FK > 1) m |= 1u << ((x >> 5) & 31u);
               if (FK > 2) m |= 1u << ((x >> 10) & 31u);
               fm[u] = m;
-              fw[u] = a.filter[x >> a.filter_shift];  // L2-resident (persisting window)
+              fw[u] = PM_FILTER_LDCG ? __ldcg(a.filter + (x >> a.filter_shift)) : a.filter[x >> a.filter_shift];  // L2-resident (persisting window)
             }
             vq += 32;
             if (vq >= PM_KV) {
@@ -365,8 +374,8 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
                 const uint32_t* src = a.mers + lo[u];
                 for (uint32_t t = 0; t < cnt; t++) {
                   const uint32_t v = __ldcg(src + t);
-                  dst[t] = v;
                   if (off + t < PM_SLIST) sm.slist[ssv[u]][off + t] = v;
+                  else dst[t] = v;
                 }
                 st_pos += cnt;
               }
@@ -382,6 +391,10 @@ __global__ void __launch_bounds__(WARPS * 32, 8) k_seed_chain(SeedArgs a) {
       // ---- ascending sort of every segment list (1613-1614, 1638-1639)
       for (int ss = 0; ss < 2 * nseg; ss++) {
         int n = (int)sm.segcnt[ss];
+        if (n > PM_SLIST) {  // a long list is sorted and searched in the global scratch: its head joins it there
+          if (lane < PM_SLIST) lists[(size_t)ss * PM_SEG_CAP + lane] = sm.slist[ss][lane];
+          __syncwarp();
+        }
         if (n > 1) warp_sort_list(n <= PM_SLIST ? sm.slist[ss] : lists + (size_t)ss * PM_SEG_CAP, n, lane);
       }
       __syncwarp();
