@@ -288,7 +288,7 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   CK(cudaMalloc(&h->d_det_best, 2 * n * 4));
   CK(cudaMalloc(&h->d_det_orient, 2 * n * 4));
   CK(cudaMalloc(&h->d_det_score, 2 * n * 8));
-  h->seed_blocks = h->sm_count * PM_SEED_CTAS;
+  h->seed_blocks = h->sm_count * 8;
   CK(cudaMalloc(&h->d_seed_scratch, (size_t)h->seed_blocks * kSeedWarps * 2 * PM_MAX_SEG * PM_SEG_CAP * 4));
   h->sw_blocks = h->sm_count * 6;  // upper bound of CTAs per SM of the wavefront kernels (scratch is sized for it)
   const size_t max_groups = (size_t)h->sw_blocks * (128 / 16);

@@ -20,7 +20,9 @@
 #ifndef PM_SEED_UNROLL
 #define PM_SEED_UNROLL 8
 #endif
-#define PM_SEED_CTAS 8          // resident CTAs per SM without the filter; the scratch is sized for it
+#ifndef PM_SEED_CTAS
+#define PM_SEED_CTAS 8
+#endif                          // resident CTAs per SM without the filter; the scratch is sized for 8
 #ifndef PM_SEED_CTAS_FILT
 #define PM_SEED_CTAS_FILT 5
 #endif                          // with the filter: fewer, fatter warps (more registers, more loads in flight each)
