@@ -1,5 +1,4 @@
-export PEMAP_BENCH_GENOME=1000000000 PEMAP_BENCH_PAIRS=2097152
-for v in v1 v3; do
-  PEMAP_LIB=$PWD/pecaller_b200/libpemap_$v.so python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err
+export PEMAP_BENCH_PAIRS=4194304 PEMAP_VERBOSE=1
+for mb in 16 32; do
+  PEMAP_FILTER_MB=$mb python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_f$mb.json 2> gpurun_out/bench_f$mb.err
 done
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v0.json 2> gpurun_out/bench_v0.err
