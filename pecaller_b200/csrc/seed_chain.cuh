@@ -247,6 +247,19 @@ __global__ void __launch_bounds__(WARPS * 32, FK > 0 ? PM_SEED_CTAS_FILT : PM_SE
     const int len = a.len[mate][r];
     const char* read = a.reads[mate] + (size_t)r * a.stride;
     int tot = 0;
+    {  // the next read-mate of this warp: its row and length are cold in HBM; start fetching them now (10 % of the
+       // warp's time was the wait for the first load of the read)
+      const int wn = w + nw;
+      if (wn < n_work && lane < 4) {
+        const int rn = a.paired ? (wn >> 1) : wn, mn = a.paired ? (wn & 1) : 0;
+        const char* nxt = a.reads[mn] + (size_t)rn * a.stride;
+        if (lane < 3) {
+          if (lane * 128 < a.stride) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + lane * 128));
+        } else {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(a.len[mn] + rn));
+        }
+      }
+    }
 
     bool ok = (len >= 16 && len < PM_DP_MAX - 21);
     // N filter (1552-1559) + forward / reverse-transcribed copies (1019-1021, 1561-1570)

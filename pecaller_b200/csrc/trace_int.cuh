@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(128) k_trace_dp16(TraceIntArgs a) {
           const uint32_t m01 = __vminu2(q[c] & rc, K1);                      // 1 where the bases match
           const uint32_t s0 = m01 * 48u + diag;                              // (M - 12) + 48 or + 0 (1713 / 1723)
           diag = mu[c];
-          const uint32_t m = __vmaxs2(__vmaxs2(s0, s1), s2);
+          const uint32_t m = __vimax3_s16x2(s0, s1, s2);                      // one VIMNMX3.S16x2
           s0u[c] = s0;
           s1u[c] = s1;
           mu[c] = m - K12;
