@@ -667,7 +667,8 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
       ca.genome = h->d_genome;
       ca.cells_certified = &h->d_counters->sw_cells_certified;
       ca.p = sa.p;
-      pm::k_diag_certify<4><<<h->sm_count * 16, 128, 0, h->stream>>>(ca);
+      if (sa.p.is_bisulfite) pm::k_diag_certify<4, true><<<h->sm_count * 16, 128, 0, h->stream>>>(ca);
+      else pm::k_diag_certify<4, false><<<h->sm_count * 16, 128, 0, h->stream>>>(ca);
       h->stats.launches++;
       ia.list = h->d_sw_list;
       ia.n_items = h->d_cursors + 16;

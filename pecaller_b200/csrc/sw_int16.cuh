@@ -297,16 +297,27 @@ __device__ __forceinline__ bool is_acgt(unsigned ch) {
   return (ch & 0xE0u) == 0x40u && ((0x0010008Au >> (ch & 31u)) & 1u);  // 'A' 0x41, 'C' 0x43, 'G' 0x47, 'T' 0x54
 }
 
-template <int WARPS>
+// 8 consecutive bytes starting at byte `off` of a word array (little endian: byte 0 of .x is the first)
+__device__ __forceinline__ uint2 fetch8(const uint32_t* p, int off) {
+  const int wi = off >> 2, sh = (off & 3) * 8;
+  const uint32_t a = p[wi], b = p[wi + 1], c = p[wi + 2];
+  return make_uint2(__funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh));
+}
+// bit 7 of every byte of x that is not zero
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t x) {
+  return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+
+template <int WARPS, bool BIS>
 __global__ void __launch_bounds__(WARPS * 32) k_diag_certify(CertifyArgs a) {
-  __shared__ unsigned char s_w[WARPS][PM_DP_MAX + 32];
-  __shared__ unsigned char s_r[WARPS][PM_DP_MAX];
+  __shared__ uint32_t s_w[WARPS][(PM_DP_MAX + 32) / 4 + 2];
+  __shared__ uint32_t s_r[WARPS][PM_DP_MAX / 4 + 2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_items = *a.n_items;
   const uint32_t gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
-  unsigned char* w = s_w[warp];
-  unsigned char* q = s_r[warp];
-  const bool bis = a.p.is_bisulfite != 0;
+  unsigned char* w = reinterpret_cast<unsigned char*>(s_w[warp]);
+  unsigned char* q = reinterpret_cast<unsigned char*>(s_r[warp]);
+  constexpr bool bis = BIS;
   unsigned long long cells = 0;
 
   for (uint32_t t0 = gw * 32u; t0 < n_items; t0 += nw * 32u) {
@@ -344,18 +355,28 @@ __global__ void __launch_bounds__(WARPS * 32) k_diag_certify(CertifyArgs a) {
         // first and last 8 columns of diagonal `lane`: mismatches, leading and trailing runs of matches
         int mis = 3, pre = 0, suf = 0;
         if (lane <= K) {
-          mis = 0;
-          bool run = true, runs = true;
+          if (BIS) {
+            mis = 0;
+            bool run = true, runs = true;
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const unsigned rc = w[lane + j], qc = q[j];
-            const bool mt = rc == qc || (bis && rc == 'C' && qc == 'T');
-            mis += !mt;
-            run = run && mt;
-            pre += run;
-            const unsigned rs = w[lane + mm - 1 - j], qs = q[mm - 1 - j];
-            runs = runs && (rs == qs || (bis && rs == 'C' && qs == 'T'));
-            suf += runs;
+            for (int j = 0; j < 8; j++) {
+              const unsigned rc = w[lane + j], qc = q[j];
+              const bool mt = rc == qc || (rc == 'C' && qc == 'T');
+              mis += !mt;
+              run = run && mt;
+              pre += run;
+              const unsigned rs = w[lane + mm - 1 - j], qs = q[mm - 1 - j];
+              runs = runs && (rs == qs || (rs == 'C' && qs == 'T'));
+              suf += runs;
+            }
+          } else {  // 8 characters at a time: xor, per-byte non-zero flags
+            const uint2 wf = fetch8(s_w[warp], lane), qf = fetch8(s_r[warp], 0);
+            const uint2 wl = fetch8(s_w[warp], lane + mm - 8), ql = fetch8(s_r[warp], mm - 8);
+            const uint32_t f0 = nonzero_bytes(wf.x ^ qf.x), f1 = nonzero_bytes(wf.y ^ qf.y);
+            const uint32_t l0 = nonzero_bytes(wl.x ^ ql.x), l1 = nonzero_bytes(wl.y ^ ql.y);
+            mis = __popc(f0) + __popc(f1);
+            pre = f0 ? ((__ffs((int)f0) - 1) >> 3) : f1 ? 4 + ((__ffs((int)f1) - 1) >> 3) : 8;
+            suf = l1 ? (__clz((int)l1) >> 3) : l0 ? 4 + (__clz((int)l0) >> 3) : 8;
           }
         }
         unsigned cand = __ballot_sync(0xFFFFFFFFu, mis < 3);

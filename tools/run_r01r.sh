@@ -1,3 +1,3 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_r.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_r.log
-tail -n 4 gpurun_out/pytest_r.log
-PEMAP_VERBOSE=1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r.json 2> gpurun_out/bench_r.err
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_s.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_s.log
+tail -n 4 gpurun_out/pytest_s.log
+PEMAP_VERBOSE=1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_s.json 2> gpurun_out/bench_s.err
