@@ -1,5 +1,4 @@
+python __graft_entry__.py smoke > gpurun_out/smoke_final.log 2>&1; echo "smoke rc=$?"; tail -n 1 gpurun_out/smoke_final.log
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_final.log 2>&1; echo "pytest rc=$?"; tail -n 2 gpurun_out/pytest_final.log
 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
-python tools/cfg3_check.py > gpurun_out/cfg3_check.json 2> gpurun_out/cfg3_check.err; echo "cfg3 rc=$?"
-python tools/cfg5_check.py > gpurun_out/cfg5_check.json 2> gpurun_out/cfg5_check.err; echo "cfg5 rc=$?"
-python tools/sw_sweep.py > gpurun_out/sw_sweep.json 2> gpurun_out/sw_sweep.err; echo "sweep rc=$?"
