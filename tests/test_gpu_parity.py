@@ -219,6 +219,36 @@ def test_traceback_band_handover(get_fixture, oracle_built, monkeypatch):
     oracle.close()
 
 
+@pytest.mark.parametrize("name", ["pe150", "repeat", "bis"])
+def test_diagonal_certificate_changes_nothing(name, get_fixture, monkeypatch):
+    """k_diag_certify settles candidates whose result follows from their ungapped diagonals (sw_int16.cuh); with
+    PEMAP_CERTIFY=0 every candidate goes through the DP kernel instead.  Loci, mapping types, pileup records and
+    insertions must be identical, and the certificate must actually have fired."""
+    fx = get_fixture(name)
+    bis = int(getattr(fx, "bisulfite", False))  # baked into the index (index_genome_whole.c:174-175)
+    for run in fx.runs:
+        kw = dict(min_align=run.min_align, pair_flag=int(run.paired), min_dist=run.min_dist, max_dist=run.max_dist,
+                  is_bisulfite=int(run.bisulfite))
+        n = min(20000, run.reads1.shape[0])
+        out = {}
+        for cert in ("0", "1"):
+            monkeypatch.setenv("PEMAP_CERTIFY", cert)
+            mapper = pb.PEMapper.from_genome(fx.genome, pb.default_params(is_bisulfite=bis))
+            mapper.set_params(**kw)
+            g = mapper.map_batch(run.reads1[:n], run.reads2[:n] if run.paired else None)
+            rec, ins = mapper.finish()
+            st = mapper.stats()
+            out[cert] = (g, rec.tobytes(), sorted(ins), st["sw_cells_certified"])
+            mapper.close()
+        for x, y in zip(out["0"][0], out["1"][0]):
+            assert np.array_equal(x, y), "%s/%s: per-read results differ with the certificate on" % (name, run.name)
+        assert out["0"][1] == out["1"][1], "%s/%s: pileup records" % (name, run.name)
+        assert out["0"][2] == out["1"][2], "%s/%s: insertions" % (name, run.name)
+        assert out["0"][3] == 0
+        if name != "repeat":
+            assert out["1"][3] > 0, "the certificate never fired"
+
+
 def _two_gpu_worker(rank, world, port, out_path):
     import os
     import torch
