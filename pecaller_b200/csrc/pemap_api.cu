@@ -98,7 +98,7 @@ struct pemap_ctx {
   int certify = 1;                // PEMAP_CERTIFY=0: score every candidate with the DP (cross-check)
   void* d_flagq = nullptr;      // packed decision flags between k_trace_dp16 and k_trace_walk16
   size_t flagq_bytes = 0;
-  int* d_pair_dmid = nullptr;
+  void* d_walk_meta = nullptr;   // per gapped winner: what k_trace_walk16 needs (written by k_trace_dp16)
   void* d_pair_codes = nullptr;  // one-hot base codes of every winner pair (window rows, read columns)
   size_t pair_codes_bytes = 0;
   int exact = 0;  // 1: fp64 kernels for everything (PEMAP_EXACT=1, PEMAP_KEEP_DETAIL, match_bonus != 1)
@@ -431,7 +431,7 @@ int ensure_flag_scratch(pemap_ctx* h, size_t bytes_per_pair, size_t code_bytes) 
     CK(cudaMalloc(&h->d_pair_codes, need_codes));
     h->pair_codes_bytes = need_codes;
   }
-  if (!h->d_pair_dmid) CK(cudaMalloc(&h->d_pair_dmid, pairs * sizeof(int)));
+  if (!h->d_walk_meta) CK(cudaMalloc(&h->d_walk_meta, pairs * 4 * sizeof(uint4)));
   return PEMAP_OK;
 }
 
@@ -453,7 +453,7 @@ int launch_trace_int(pemap_ctx* h, pm::TraceIntArgs& a) {
   if (rc) return rc;
   a.flagq = reinterpret_cast<uint2*>(h->d_flagq);
   a.pair_codes = reinterpret_cast<unsigned char*>(h->d_pair_codes);
-  a.pair_dmid = h->d_pair_dmid;
+  a.walk_meta = reinterpret_cast<uint4*>(h->d_walk_meta);
   const size_t dyn_dp = pm::trace_dp16_smem<G, WD>(), dyn_wk = pm::trace_walk16_smem<G, WD>();
   static int grids_dp[kMaxDev] = {}, grids_wk[kMaxDev] = {};
   int& grid_dp = grids_dp[h->device % kMaxDev];
@@ -759,7 +759,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     ta.p = sa.p;
     ta.work_walk = h->d_cursors + 15;
     ta.flagq = nullptr;
-    ta.pair_dmid = nullptr;
+    ta.walk_meta = nullptr;
     ta.pair_codes = nullptr;
     {
       const int trc = dispatch_trace_int(h, ta, max_len);
@@ -1402,7 +1402,7 @@ void pemap_destroy(pemap_t* h) {
                    h->d_tasks, h->d_results, h->d_cursors,
                    h->d_cand_base, h->d_cand_n, h->d_winners, h->d_det_best, h->d_det_orient,
                    h->d_det_score, h->d_seed_scratch, h->d_dirs, h->d_pend, h->d_counters, h->d_ires, h->d_replay_reads,
-                   h->d_replay_tasks, h->d_diag_winners, h->d_exact_winners, h->d_oob_winners, h->d_flagq, h->d_pair_dmid, h->d_pair_codes, h->d_sw_list};
+                   h->d_replay_tasks, h->d_diag_winners, h->d_exact_winners, h->d_oob_winners, h->d_flagq, h->d_walk_meta, h->d_pair_codes, h->d_sw_list};
     for (void* p : dev)
       if (p) cudaFree(p);
     for (auto& sl : h->slots) {

@@ -42,7 +42,8 @@ struct TraceIntArgs {
   int band_half;               // lanes kept on each side of the end-diagonal lane (PM_BAND_LANES / 2)
   uint2* flagq;                // k_trace_dp16 -> k_trace_walk16: packed decision flags, [pair][winner][band row][lane]
   unsigned char* pair_codes;   // one-hot codes of every pair's windows and oriented reads (low nibble first winner)
-  int* pair_dmid;              // band position of every winner pair (+1024), bit 16 / 17: a base outside ACGTN
+  uint4* walk_meta;            // per winner, 2 quads: {wstart, rm | orient << 31, maxi | maxk << 16, mm},
+                               // {score36, (dmid + 1024) | bad << 16, nn, task}: all the walk kernel needs, one round trip
   uint32_t* work_walk;         // zeroed per launch: next winner of the walk kernel
   DevParams p;
 };
@@ -581,6 +582,15 @@ __global__ void __launch_bounds__(128) k_trace_dp16(TraceIntArgs a) {
     }
     uint32_t out_s0 = 0, out_s2 = 0, out_m = 0;
     __syncwarp();
+    if (have && gl == 0) {  // what the walk kernel needs of the two winners (written now: the registers die here)
+      uint4* meta = a.walk_meta + (size_t)pair * 4;
+      meta[0] = make_uint4(tA.wstart, tA.rm, (uint32_t)rA.maxi | ((uint32_t)rA.maxk << 16), (uint32_t)mmA);
+      meta[1] = make_uint4((uint32_t)(int)lrint(rA.score * 36.0), (uint32_t)(dmid + 1024) | (badA ? (1u << 16) : 0u), (uint32_t)nnA, idA);
+      meta[2] = make_uint4(tB.wstart, tB.rm, (uint32_t)rB.maxi | ((uint32_t)rB.maxk << 16), (uint32_t)mmB);
+      meta[3] = make_uint4((uint32_t)(int)lrint(rB.score * 36.0), (uint32_t)(dmid + 1024) | (badB ? (1u << 16) : 0u), (uint32_t)nnB, idB);
+      atomicAdd(&a.counters->tb_cells_int, (unsigned long long)nnA * (unsigned long long)mmA +
+                                               (itB != itA ? (unsigned long long)nnB * (unsigned long long)mmB : 0ull));
+    }
     if (have) {  // the codes travel with the flags
       uint4* dst = reinterpret_cast<uint4*>(a.pair_codes + (size_t)pair * CB);
       const uint4* srcq = reinterpret_cast<const uint4*>(s_codes[grp]);
@@ -699,11 +709,6 @@ __global__ void __launch_bounds__(128) k_trace_dp16(TraceIntArgs a) {
         }
       }
     }
-    if (have && gl == 0) {
-      a.pair_dmid[pair] = (dmid + 1024) | (badA ? (1 << 16) : 0) | (badB ? (1 << 17) : 0);
-      atomicAdd(&a.counters->tb_cells_int, (unsigned long long)nnA * (unsigned long long)mmA +
-                                               (itB != itA ? (unsigned long long)nnB * (unsigned long long)mmB : 0ull));
-    }
     __syncwarp();
   }
 }
@@ -744,17 +749,16 @@ __global__ void __launch_bounds__(128) k_trace_walk16(TraceIntArgs a) {
     if (item >= n_items) break;
     const uint32_t pair = item >> 1;
     const int hi = (int)(item & 1u);
-    const uint32_t task_id = a.winners[item].task;
-    const Task tk = a.tasks[task_id];
-    const TaskResult res = a.results[task_id];
-    const int orient = (int)(tk.rm >> 31);
-    const uint32_t rm = tk.rm & 0x7FFFFFFFu;
-    const int mm = ((rm & 1u) ? a.len[1] : a.len[0])[rm >> 1];
+    const uint4 m0 = __ldg(a.walk_meta + (size_t)item * 2), m1 = __ldg(a.walk_meta + (size_t)item * 2 + 1);
+    const uint32_t wstart = m0.x;
+    const int orient = (int)(m0.y >> 31);
+    const uint32_t rm = m0.y & 0x7FFFFFFFu;
+    const int maxi = (int)(m0.z & 0xFFFFu), maxk = (int)(m0.z >> 16), mm = (int)m0.w;
     const char* read = ((rm & 1u) ? a.reads[1] : a.reads[0]) + (size_t)(rm >> 1) * a.stride;
-    const int nn = res.maxi < tk.blen ? res.maxi : tk.blen;
-    const int pd = a.pair_dmid[pair];
-    const int dmid = (pd & 0xFFFF) - 1024;
-    const bool bad = (pd >> (16 + hi)) & 1;  // bases outside ACGTN: the scoring kernel sent such reads to the fp64 path already
+    const int r36 = (int)m1.x;
+    const int dmid = (int)(m1.y & 0xFFFFu) - 1024;
+    const bool bad = (m1.y >> 16) & 1u;  // bases outside ACGTN: the scoring kernel sent such reads to the fp64 path already
+    const int nn = (int)m1.z;
 
     __syncwarp();
     {
@@ -775,12 +779,11 @@ __global__ void __launch_bounds__(128) k_trace_walk16(TraceIntArgs a) {
       tie.t.win = codes;
       tie.t.qcode = codes + ROWS;
       tie.t.shift = 4 * hi;
-      const int r36 = (int)lrint(res.score * 36.0);
-      rc = coop_walk<NL>(cell, tie, smask, 0, sl, res.maxk, res.maxi, mm, r36, segs, &nseg);
+      rc = coop_walk<NL>(cell, tie, smask, 0, sl, maxk, maxi, mm, r36, segs, &nseg);
       if (rc == PM_WALK_OK && nseg < 0) rc = PM_WALK_TIE;  // more segments than the scratch holds: exact kernel
     }
     if (rc == PM_WALK_OK) {
-      coop_apply<NL>(segs, nseg, smask, sl, read, mm, orient, tk.wstart, sink, codes + ROWS, 4 * hi);
+      coop_apply<NL>(segs, nseg, smask, sl, read, mm, orient, wstart, sink, codes + ROWS, 4 * hi);
     } else if (sl == 0) {
       const uint32_t w = atomicAdd(a.exact_cursor, 1u);
       a.exact_winners[w] = a.winners[item];
