@@ -75,7 +75,7 @@ __device__ __forceinline__ void track_best(int v0, int v1, int v2, int dq, int i
 // CMM >= 0: every task of the launch has (len-1) % WD == CMM and (len-1) / WD == lane_mm (uniform read length);
 // CMM < 0: per-task lengths.
 template <int G, int WD, int CMM>
-__global__ void __launch_bounds__(128) k_sw_i16(SwIntArgs a) {
+__global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
   constexpr int GPB = 128 / G;
   constexpr int ROWS = (G * WD + 24 < PM_DP_MAX) ? G * WD + 24 : PM_DP_MAX;  // window rows: nn <= len + 21
   __shared__ uint32_t s_win[GPB][ROWS];
