@@ -11,7 +11,8 @@
 //                                                              bump after the max gives the same double)
 // so scores, the last-column argmax (1717-1742) and the traceback predicates are bit-identical to the CPU.
 // MODE 0 scores.  MODE 1/2 trace: 4 decision bits per cell (layout in trace_walk.cuh) are
-// stored and lane 0 walks them, applying the pileup increments with atomics.  MODE 2 keeps the band around the
+// stored and walked (MODE 2: by the whole group, coop_walk in trace_walk.cuh; MODE 1: by lane 0), applying the pileup
+// increments with atomics.  MODE 2 keeps the band around the
 // winner's end diagonal in shared memory (a walk that leaves it hands the winner to the MODE 1 kernel through the
 // `oob` list); MODE 1 keeps every lane's word in a global scratch and can walk anywhere.
 #pragma once

@@ -1,5 +1,9 @@
 // trace_int.cuh - integer traceback of the winners that are not pure diagonals (sm_100a).
 //
+// Two implementations: k_trace_i32 (one winner per sub-warp, 32-bit integers, flags inside the wavefront, lane 0 walks;
+// PEMAP_TRACE32=1, kept as a cross-check) described first, and the production pair k_trace_dp16 + k_trace_walk16
+// (two winners per lane, deferred band pass, cooperative walk) further down; they share the tie certification.
+//
 // Replaces smith_waterman_backtrack (pemapper.c:1752-1965) for winners with gaps.  The DP of the winning
 // (read, window) task is recomputed in exact integers (units of 1/36, sw_int16.cuh) with the same sub-warp
 // wavefront as sw_wavefront.cuh, storing 6 decision bits per cell:
@@ -15,7 +19,7 @@
 // either way.  Lane 0 therefore walks the path twice: a dry pass that only looks for a
 // tie on a consulted decision or a step outside the band, and, if there was none, the pass that applies the pileup
 // increments.  An A tie is first put to resolve_tie(): the tied values are traced back in lock step, and if their
-// histories join again and are provably EQUAL doubles (two certificates, see resolve_tie) the reference's strict '>'
+// histories join again and are provably EQUAL doubles (three certificates, see resolve_tie) the reference's strict '>'
 // keeps the lower state - exactly the integer argmax.  Typical case: a gap inside a homopolymer run or a short
 // tandem repeat.  Only ties that cannot be certified hand the winner to the exact fp64 traceback kernel.  Every consulted comparison then has integer
 // operands that differ, i.e. doubles that differ by >= 1/36, and the walk is the reference's walk.
