@@ -28,8 +28,12 @@ extern "C" {
 #define PEMAP_ERR_NOMEM (-3)       /* host or device allocation failed */
 #define PEMAP_ERR_UNSUPPORTED (-4) /* outside the reference's defined behaviour (e.g. 2..7 contigs) */
 
-/* Reads longer than this overflow the reference's 300x300 DP buffers (window = len+21 <= 299,
-   pemapper.c:155, 916, 2073-2081); shorter than 16 read past the read in convert_seq_int (2408-2423). */
+/* Reads longer than PEMAP_MAX_READ overflow the reference's 300x300 DP buffers (window = len+21 <= 299,
+   pemapper.c:155, 916, 2073-2081); shorter than PEMAP_MIN_READ read past the read in convert_seq_int (2408-2423).
+   Parity with the reference is defined for PEMAP_MIN_READ..PEMAP_MAX_READ only.  The library is lenient at both
+   ends: lengths 0..15 are accepted and reported unmapped (m = 0, the single-end / pair rules then see a mate
+   without candidates), lengths 279..298 are mapped by the same kernels as an extension WITHOUT a reference
+   result to compare with, and only lengths < 0 or > 298 return PEMAP_ERR_ARG. */
 #define PEMAP_MAX_READ 278
 #define PEMAP_MIN_READ 16
 
@@ -154,6 +158,22 @@ int pemap_get_candidates(pemap_t *h, int i, int mate, uint32_t *spots, int8_t *o
    until the next pemap_finish / pemap_reset_counts / pemap_destroy.  Counters are NOT cleared. */
 int pemap_finish(pemap_t *h, const pemap_record **records, uint64_t *n_records, const pemap_insertion **ins,
                  uint64_t *n_ins);
+
+/* The same writer loop without materialising the records: the counters are compacted window by window (16 M sites)
+   through two bounded device buffers and two pinned host buffers, and every window's records are handed to `cb` in
+   ascending coordinate while the next window is compacted and copied.  A fully covered 3.1 Gb genome (50 GB of
+   records) therefore needs 0.5 GB of device memory and no host copy of the whole file; the C host gzwrite()s from
+   the callback exactly as pemapper.c:834-842 does site by site.  `records` is only valid during the call; a
+   non-zero return from `cb` aborts with PEMAP_ERR_ARG.  pemap_finish() is this call collecting into one array. */
+typedef int (*pemap_site_cb)(void *ctx, const pemap_record *records, uint64_t n);
+int pemap_finish_stream(pemap_t *h, pemap_site_cb cb, void *ctx, uint64_t *n_records);
+
+/* The insertion strings accumulated so far, grouped by site (the second half of pemap_finish; shards that only
+   contribute their strings to the writer GPU call this and skip the record pass).  The device append buffer
+   (PEMAP_INS_MB, default 256 MB) is drained to host memory whenever a chunk of reads leaves it more than half full,
+   so its size bounds one chunk's insertions, not the run's; a chunk that overflows it fails pemap_map_batch* with
+   PEMAP_ERR_NOMEM at once. */
+int pemap_get_insertions(pemap_t *h, const pemap_insertion **ins, uint64_t *n_ins);
 
 /* Zero the counters and drop the insertions (pemapper_tsw.c dump_output, tsw:849-965, between samples). */
 int pemap_reset_counts(pemap_t *h);

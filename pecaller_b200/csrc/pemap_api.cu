@@ -16,6 +16,7 @@
 #include "../../include/pemap.h"
 #include "pemap_common.cuh"
 #include "seed_chain.cuh"
+#include "seed_rbi.cuh"
 #include "select_finish.cuh"
 #include "sw_wavefront.cuh"
 #include "sw_int16.cuh"
@@ -26,6 +27,8 @@
 namespace {
 
 constexpr int kSeedWarps = 4;
+constexpr int kRbiWarps = 8;     // k_seed_rbi: 8 warps per CTA, 9.3 KB of shared memory per warp -> 3 CTAs per SM
+constexpr int kRbiBigWarps = 4;
 constexpr int kMaxDev = 16;  // per-device caches of launch configurations
 constexpr uint64_t kInsCapDefault = 256ull << 20;
 
@@ -52,6 +55,16 @@ struct pemap_ctx {
   uint32_t* d_cstart = nullptr;
   int n_contigs = 0;
   double* d_border = nullptr;
+  // device-private rotated bucket index (seed_rbi.cuh): what the seed kernel reads; pos_index / mers are only kept
+  // beside it while the genome is small (tests of the index builder, the legacy seed kernel as a cross-check)
+  uint4* d_rbi_data[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint32_t* d_rbi_dir[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint64_t rbi_bytes = 0;
+  int seed_legacy = 0;             // PEMAP_SEED=legacy: k_seed_chain over pos_index / mers
+  int index_only = 0;              // PEMAP_INDEX_ONLY=1: the handle only builds and hands out the index
+  uint32_t* d_big_list = nullptr;  // read-mates whose strand lists did not fit shared memory (second seed pass)
+  unsigned char* d_big_scratch = nullptr;
+  int big_grid = 0;
   uint32_t* d_filter = nullptr;  // word-blocked Bloom filter of the occupied k-mers (seed_chain.cuh), or null
   int filter_shift = 0, filter_k = 0;
   size_t filter_bytes = 0;
@@ -127,6 +140,19 @@ struct pemap_ctx {
   std::vector<pemap_record> records;
   std::vector<pemap_insertion> ins;
   std::vector<char> ins_pool;
+  // streaming finish: the counters are compacted window by window through two bounded device buffers and two pinned
+  // host buffers (pemap_finish_stream); allocated at the first call
+  uint64_t fin_sites = 0;                       // sites per window (multiple of the compaction tile)
+  pm::PileRecord* d_fin_rec[2] = {nullptr, nullptr};
+  pemap_record* h_fin_rec[2] = {nullptr, nullptr};
+  unsigned long long *d_fin_cnt = nullptr, *d_fin_off = nullptr, *h_fin_total = nullptr;
+  void* d_fin_tmp = nullptr;
+  size_t fin_tmp_bytes = 0;
+  cudaEvent_t ev_fin[2] = {nullptr, nullptr};
+  // insertion records drained from the device append buffer so far (same {pos, len, chars} layout)
+  std::vector<unsigned char> ins_raw;
+  unsigned long long* h_ins_used = nullptr;     // pinned: cursor value after each chunk, one per slot
+  bool want_drain = false;
 
   pemap_stats stats;
 };
@@ -289,7 +315,13 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   CK(cudaMalloc(&h->d_det_orient, 2 * n * 4));
   CK(cudaMalloc(&h->d_det_score, 2 * n * 8));
   h->seed_blocks = h->sm_count * 8;
-  CK(cudaMalloc(&h->d_seed_scratch, (size_t)h->seed_blocks * kSeedWarps * 2 * PM_MAX_SEG * PM_SEG_CAP * 4));
+  if (h->seed_legacy) {
+    CK(cudaMalloc(&h->d_seed_scratch, (size_t)h->seed_blocks * kSeedWarps * 2 * PM_MAX_SEG * PM_SEG_CAP * 4));
+  } else {  // second seed pass (strand lists that do not fit shared memory): one CTA per SM, per-warp lists in HBM
+    h->big_grid = h->sm_count;
+    CK(cudaMalloc(&h->d_big_scratch, (size_t)h->big_grid * kRbiBigWarps * PM_RBI_BIG_BYTES));
+    CK(cudaMalloc(&h->d_big_list, 2 * n * 4));
+  }
   h->sw_blocks = h->sm_count * 6;  // upper bound of CTAs per SM of the wavefront kernels (scratch is sized for it)
   const size_t max_groups = (size_t)h->sw_blocks * (128 / 16);
   // trace scratch: groups * G == sw_blocks * 128 lanes for every instantiation, PM_DP_MAX rows of one word per lane
@@ -298,9 +330,12 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   CK(cudaMalloc(&h->d_counters, sizeof(pm::SeedCounters)));
   CK(cudaMemset(h->d_counters, 0, sizeof(pm::SeedCounters)));
   if (const char* s = getenv("PEMAP_INS_MB")) h->ins_cap = (uint64_t)std::max(1, atoi(s)) << 20;
+  if (const char* s = getenv("PEMAP_INS_BYTES")) h->ins_cap = (uint64_t)std::max(1024, atoi(s));  // tests of the spill path
   CK(cudaMalloc(&h->d_ins, h->ins_cap));
   CK(cudaMalloc(&h->d_ins_cursor, 8));
   CK(cudaMemset(h->d_ins_cursor, 0, 8));
+  CK(cudaHostAlloc(&h->h_ins_used, 2 * 8, cudaHostAllocDefault));
+  h->h_ins_used[0] = h->h_ins_used[1] = 0;
   return PEMAP_OK;
 }
 
@@ -345,9 +380,132 @@ int build_filter(pemap_ctx* h) {
   return PEMAP_OK;
 }
 
+void read_index_env(pemap_ctx* h) {
+  if (const char* s = getenv("PEMAP_SEED")) h->seed_legacy = strcmp(s, "legacy") == 0;
+  if (const char* s = getenv("PEMAP_INDEX_ONLY")) h->index_only = atoi(s) != 0;
+}
+
+// pos_index / mers (28 GB on a human-sized genome) are the input format, not what the seed kernel reads: beside the
+// rotated bucket index they are kept only while small (index tests, PEMAP_SEED=legacy); PEMAP_KEEP_INDEX=0/1 overrides
+void drop_file_index_if_large(pemap_ctx* h) {
+  bool keep = h->n_mers <= (1ull << 30);
+  if (const char* s = getenv("PEMAP_KEEP_INDEX")) keep = atoi(s) != 0;
+  if (keep) return;
+  cudaFree(h->d_pos_index);
+  cudaFree(h->d_mers);
+  h->d_pos_index = nullptr;
+  h->d_mers = nullptr;
+}
+
+// Rotated bucket index from the code-sorted (code, position) list of the indexed k-mers (= pos_index / mers order).
+// `code` is overwritten (sort output); `val` is only read.
+int build_rbi(pemap_ctx* h, uint32_t* code, const uint32_t* val, uint64_t n) {
+  const uint32_t T = (uint32_t)h->params.too_many_spots;
+  uint32_t p0 = 0, plast = 0;
+  CK(cudaMemcpy(&p0, h->d_pos_index, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&plast, h->d_pos_index + 0xFFFFFFFFull, 4, cudaMemcpyDeviceToHost));
+  const uint32_t last_cnt = p0 - plast;  // get_mers(0xFFFFFFFF): which + 1 wraps in 32 bits (pemapper.c:2163)
+  const uint64_t true_last = n - plast;
+  if (last_cnt < T && (uint64_t)last_cnt > true_last)
+    return fail(h, PEMAP_ERR_UNSUPPORTED, "index within 100 entries of 2^32: get_mers(0xFFFFFFFF) reads past the mers array");
+  uint32_t *s1 = nullptr, *s2 = nullptr, *keyg = nullptr, *o2 = nullptr, *bstart = nullptr, *units = nullptr;
+  unsigned char* flag = nullptr;
+  unsigned long long* d_nsel = nullptr;
+  void* tmp = nullptr;
+  auto cleanup = [&]() {
+    void* v[] = {s1, s2, keyg, o2, bstart, units, flag, d_nsel, tmp};
+    for (void* p : v)
+      if (p) cudaFree(p);
+  };
+#define CKB(call)                                                                                         \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) {                                                                              \
+      cleanup();                                                                                          \
+      return fail(h, e_ == cudaErrorMemoryAllocation ? PEMAP_ERR_NOMEM : PEMAP_ERR_CUDA,                  \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                                    \
+    }                                                                                                     \
+  } while (0)
+  const size_t n1 = (size_t)n + 1;
+  CKB(cudaMalloc(&s1, n1 * 4));
+  CKB(cudaMalloc(&s2, n1 * 4));
+  CKB(cudaMalloc(&flag, n1));
+  CKB(cudaMalloc(&d_nsel, 8));
+  const unsigned nblk = (unsigned)((n + 255) / 256);
+  if (n) pm::k_rbi_flag<<<nblk, 256, 0, h->stream>>>(code, h->d_pos_index, n, T, last_cnt, flag);
+  size_t need = 0, tmp_bytes = 0;
+  const long long n_items = (long long)n;
+  cub::DeviceSelect::Flagged(nullptr, need, code, flag, s1, d_nsel, n_items, h->stream);
+  tmp_bytes = need;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, s1, code, s2, s2, n_items + 1, 0, 32, h->stream);
+  tmp_bytes = std::max(tmp_bytes, need);
+  cub::DeviceScan::ExclusiveSum(nullptr, need, s1, s2, (1 << 24) + 1, h->stream);
+  tmp_bytes = std::max(tmp_bytes, need);
+  CKB(cudaMalloc(&tmp, tmp_bytes));
+  need = tmp_bytes;
+  CKB(cub::DeviceSelect::Flagged(tmp, need, code, flag, s1, d_nsel, n_items, h->stream));
+  need = tmp_bytes;
+  CKB(cub::DeviceSelect::Flagged(tmp, need, val, flag, s2, d_nsel, n_items, h->stream));
+  unsigned long long ne = 0;
+  CKB(cudaMemcpyAsync(&ne, d_nsel, 8, cudaMemcpyDeviceToHost, h->stream));
+  CKB(cudaStreamSynchronize(h->stream));
+  cudaFree(flag);
+  flag = nullptr;
+  if (ne) pm::k_rbi_mark<<<(unsigned)((ne + 255) / 256), 256, 0, h->stream>>>(s1, h->d_pos_index, ne, T, last_cnt, s2);
+  if (last_cnt >= T && true_last == 0) {  // poly-T is "crowded" through the wrap although the genome has none: a lone marker
+    const uint32_t kv[2] = {0xFFFFFFFFu, PM_RBI_MARK};
+    CKB(cudaMemcpyAsync(s1 + ne, &kv[0], 4, cudaMemcpyHostToDevice, h->stream));
+    CKB(cudaMemcpyAsync(s2 + ne, &kv[1], 4, cudaMemcpyHostToDevice, h->stream));
+    CKB(cudaStreamSynchronize(h->stream));
+    ne++;
+  }
+  CKB(cudaMalloc(&keyg, n1 * 4));
+  CKB(cudaMalloc(&o2, n1 * 4));
+  const unsigned nb24 = (1u << 24) + 1u;
+  CKB(cudaMalloc(&bstart, ((size_t)nb24 + 1) * 4));
+  CKB(cudaMalloc(&units, (size_t)nb24 * 4));
+  const unsigned eblk = (unsigned)((ne + 255) / 256);
+  h->rbi_bytes = 0;
+  for (int g = 0; g < 4; g++) {
+    const uint32_t *kk = s1, *vv = s2;  // rotation 0: tag = low byte, the code order is the key order
+    if (g > 0) {
+      if (ne) pm::k_rbi_keys<<<eblk, 256, 0, h->stream>>>(s1, ne, g, keyg);
+      need = tmp_bytes;
+      CKB(cub::DeviceRadixSort::SortPairs(tmp, need, keyg, code, s2, o2, (long long)ne, 0, 32, h->stream));
+      kk = code;
+      vv = o2;
+    }
+    pm::k_rbi_bucket_starts<<<(nb24 + 255) / 256, 256, 0, h->stream>>>(kk, ne, bstart);
+    pm::k_rbi_bucket_units<<<(nb24 + 255) / 256, 256, 0, h->stream>>>(bstart, units);
+    CKB(cudaMalloc(&h->d_rbi_dir[g], (size_t)nb24 * 4));
+    need = tmp_bytes;
+    CKB(cub::DeviceScan::ExclusiveSum(tmp, need, units, h->d_rbi_dir[g], (int)nb24, h->stream));
+    uint32_t total_units = 0;
+    CKB(cudaMemcpyAsync(&total_units, h->d_rbi_dir[g] + (1u << 24), 4, cudaMemcpyDeviceToHost, h->stream));
+    CKB(cudaStreamSynchronize(h->stream));
+    const size_t bytes = ((size_t)total_units + 4) * 16;  // the gather may touch the unit after a bucket's last tag word
+    CKB(cudaMalloc(&h->d_rbi_data[g], bytes));
+    CKB(cudaMemsetAsync(h->d_rbi_data[g], 0xFF, bytes, h->stream));
+    if (ne) pm::k_rbi_fill<<<eblk, 256, 0, h->stream>>>(kk, vv, ne, bstart, h->d_rbi_dir[g], h->d_rbi_data[g]);
+    h->rbi_bytes += bytes + (size_t)nb24 * 4;
+  }
+  CKB(cudaStreamSynchronize(h->stream));
+  CKB(cudaGetLastError());
+#undef CKB
+  cleanup();
+  if (getenv("PEMAP_VERBOSE"))
+    fprintf(stderr, "pemap: rotated bucket index: %llu entries (%llu positions), %.2f GB\n", ne, (unsigned long long)n,
+            h->rbi_bytes / 1e9);
+  return PEMAP_OK;
+}
+
 int finish_init(pemap_ctx* h) {
   fill_dev_params(h);
-  {
+  if (h->index_only) {
+    CK(cudaDeviceSynchronize());
+    return PEMAP_OK;
+  }
+  if (h->seed_legacy) {
     int rc0 = build_filter(h);
     if (rc0) return rc0;
   }
@@ -521,16 +679,11 @@ void dispatch_sw_int(pemap_ctx* h, pm::SwIntArgs& a, int max_len, int uniform_le
   h->stats.launches++;
 }
 
-// map one chunk whose reads are already in d_r1/d_r2 (device); results go to d_m1/d_m2/d_type (device)
-int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char* d_r2, const int* d_l2, int stride,
-              int max_len, int uniform_len, uint32_t* d_m1, uint32_t* d_m2, int* d_type, cudaEvent_t* ev) {
-  const bool paired = h->params.pair_flag && d_r2;
-  const bool exact = h->exact || (h->keep & PEMAP_KEEP_DETAIL) || h->params.match_bonus != 1.0;
-  bool forked = false;
-  CK(cudaMemsetAsync(h->d_cursors, 0, 16, h->stream));
-  CK(cudaMemsetAsync(h->d_cursors + 6, 0, 44, h->stream));  // [6..8] lists, [9..15] work counters of the persistent kernels, [16] DP list
-  CK(cudaEventRecord(ev[0], h->stream));
-  pm::SeedArgs sa;
+// the round-1 seed kernel over pos_index / mers (PEMAP_SEED=legacy; cross-check of the rotated bucket index)
+int launch_seed_legacy(pemap_ctx* h, pm::SeedArgs& sa, int n, const char* d_r1, const int* d_l1, const char* d_r2, const int* d_l2,
+                       int stride, bool paired) {
+  if (!h->d_pos_index) return fail(h, PEMAP_ERR_ARG, "PEMAP_SEED=legacy needs the file index resident (PEMAP_KEEP_INDEX=1)");
+  pm::DevParams keep_p = sa.p;
   sa.pos_index = h->d_pos_index;
   sa.mers = h->d_mers;
   sa.cstart = h->d_cstart;
@@ -551,8 +704,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   sa.filter = h->d_filter;
   sa.filter_shift = h->filter_shift;
   sa.filter_k = h->filter_k;
-  sa.p = h->dp;
-  sa.p.pair_flag = paired ? 1 : 0;
+  sa.p = keep_p;
   const int work = paired ? 2 * n : n;
   static int seed_waves[kMaxDev][4] = {};  // one resident wave of the persistent seed kernel, per device and variant
   const int sv = h->d_filter ? std::min(3, std::max(1, h->filter_k)) : 0;  // bits per k-mer of the filter, 0 = none
@@ -581,6 +733,73 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   else if (sv == 1) pm::k_seed_chain<kSeedWarps, 1><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
   else if (sv == 2) pm::k_seed_chain<kSeedWarps, 2><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
   else pm::k_seed_chain<kSeedWarps, 3><<<seed_grid, kSeedWarps * 32, 0, h->stream>>>(sa);
+  return PEMAP_OK;
+}
+
+// map one chunk whose reads are already in d_r1/d_r2 (device); results go to d_m1/d_m2/d_type (device)
+int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char* d_r2, const int* d_l2, int stride,
+              int max_len, int uniform_len, uint32_t* d_m1, uint32_t* d_m2, int* d_type, cudaEvent_t* ev) {
+  const bool paired = h->params.pair_flag && d_r2;
+  const bool exact = h->exact || (h->keep & PEMAP_KEEP_DETAIL) || h->params.match_bonus != 1.0;
+  bool forked = false;
+  CK(cudaMemsetAsync(h->d_cursors, 0, 16, h->stream));
+  CK(cudaMemsetAsync(h->d_cursors + 6, 0, 48, h->stream));  // [6..8] lists, [9..15] work counters of the persistent kernels, [16] DP list, [17] big seed list
+  CK(cudaEventRecord(ev[0], h->stream));
+  pm::SeedArgs sa;
+  sa.p = h->dp;
+  sa.p.pair_flag = paired ? 1 : 0;
+  if (h->seed_legacy) {
+    int rc = launch_seed_legacy(h, sa, n, d_r1, d_l1, d_r2, d_l2, stride, paired);
+    if (rc) return rc;
+  } else {
+    pm::SeedRbiArgs ra;
+    for (int g = 0; g < 4; g++) {
+      ra.ix.data[g] = h->d_rbi_data[g];
+      ra.ix.dir[g] = h->d_rbi_dir[g];
+    }
+    ra.cstart = h->d_cstart;
+    ra.reads[0] = d_r1;
+    ra.reads[1] = d_r2;
+    ra.len[0] = d_l1;
+    ra.len[1] = d_l2;
+    ra.stride = stride;
+    ra.n_reads = n;
+    ra.paired = paired ? 1 : 0;
+    ra.tasks = h->d_tasks;
+    ra.task_cursor = h->d_cursors;
+    ra.task_cap = h->task_cap;
+    ra.cand_base = h->d_cand_base;
+    ra.cand_n = h->d_cand_n;
+    ra.counters = h->d_counters;
+    ra.big_list = h->d_big_list;
+    ra.big_cursor = h->d_cursors + 17;
+    ra.work_list = h->d_big_list;
+    ra.work_n = h->d_cursors + 17;
+    ra.big_scratch = h->d_big_scratch;
+    ra.fast_cap = PM_RBI_CAP;
+    if (const char* s = getenv("PEMAP_RBI_CAP")) ra.fast_cap = std::min(PM_RBI_CAP, std::max(1, atoi(s)));
+    ra.p = sa.p;
+    const int work = paired ? 2 * n : n;
+    static int rbi_wave[kMaxDev] = {};
+    int& wave = rbi_wave[h->device % kMaxDev];
+    const size_t dyn = pm::seed_rbi_smem<kRbiWarps>(false), dyn_big = pm::seed_rbi_smem<kRbiBigWarps>(true);
+    if (!wave) {
+      cudaFuncSetAttribute(pm::k_seed_rbi<kRbiWarps, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      cudaFuncSetAttribute(pm::k_seed_rbi<kRbiBigWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_big);
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_seed_rbi<kRbiWarps, false>, kRbiWarps * 32, dyn) != cudaSuccess ||
+          per_sm < 1)
+        per_sm = 1;
+      cudaGetLastError();
+      if (const char* s = getenv("PEMAP_SEED_CTAS")) per_sm = std::min(per_sm, std::max(1, atoi(s)));
+      wave = per_sm * h->sm_count;
+      if (getenv("PEMAP_VERBOSE")) fprintf(stderr, "pemap: k_seed_rbi %d CTAs per SM, %zu B of shared memory each\n", per_sm, dyn);
+    }
+    const int grid = std::min(wave, (work + kRbiWarps - 1) / kRbiWarps);
+    if (grid > 0) pm::k_seed_rbi<kRbiWarps, false><<<grid, kRbiWarps * 32, dyn, h->stream>>>(ra);
+    pm::k_seed_rbi<kRbiBigWarps, true><<<h->big_grid, kRbiBigWarps * 32, dyn_big, h->stream>>>(ra);
+    h->stats.launches++;
+  }
   h->stats.launches++;
   CK(cudaEventRecord(ev[1], h->stream));
 
@@ -890,9 +1109,58 @@ bool is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
+// Move what the traceback kernels appended so far to the host and rewind the device cursor (the reference mallocs
+// every insertion string, pemapper.c:1871-1904; here the append buffer is bounded and spills to host memory).
+int drain_insertions(pemap_ctx* h) {
+  CK(cudaStreamSynchronize(h->stream));
+  unsigned long long used = 0;
+  CK(cudaMemcpyAsync(&used, h->d_ins_cursor, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (used > h->ins_cap)
+    return fail(h, PEMAP_ERR_NOMEM, "insertion buffer overflow inside one chunk of reads (raise PEMAP_INS_MB or lower PEMAP_CHUNK)");
+  if (used) {
+    const size_t at = h->ins_raw.size();
+    h->ins_raw.resize(at + used);
+    CK(cudaMemcpyAsync(h->ins_raw.data() + at, h->d_ins, used, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemsetAsync(h->d_ins_cursor, 0, 8, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  h->want_drain = false;
+  return PEMAP_OK;
+}
+
+// after a chunk: fail at once when the append buffer overflowed, ask for a drain past the high-water mark
+int check_insertion_fill(pemap_ctx* h, unsigned long long used) {
+  if (used > h->ins_cap)
+    return fail(h, PEMAP_ERR_NOMEM, "insertion buffer overflow inside one chunk of reads (raise PEMAP_INS_MB or lower PEMAP_CHUNK)");
+  if (used > h->ins_cap / 2) h->want_drain = true;
+  return PEMAP_OK;
+}
+
+// scope guard of map_host: whatever path leaves the function, no slot stays marked pending (a stale slot would copy
+// an old chunk's results into the next caller's arrays) and nothing of this call is still running
+struct SlotGuard {
+  pemap_ctx* h;
+  ~SlotGuard() {
+    bool any = false;
+    for (auto& sl : h->slots) any = any || sl.pending;
+    if (any) {
+      cudaStreamSynchronize(h->s_h2d);
+      cudaStreamSynchronize(h->stream);
+      cudaStreamSynchronize(h->s_aux);
+      cudaStreamSynchronize(h->s_d2h);
+      for (auto& sl : h->slots) sl.pending = false;
+    }
+  }
+};
+
 // wait for a chunk's results, hand them to the caller and book its stage times
 int finish_slot(pemap_ctx* h, pemap_ctx::Slot& sl, uint32_t* m1, uint32_t* m2, int* mapping_type) {
   CK(cudaEventSynchronize(sl.ev_d2h));
+  {
+    int rc = check_insertion_fill(h, h->h_ins_used[&sl - h->slots]);
+    if (rc) return rc;
+  }
   if (!sl.direct) {
     memcpy(m1 + sl.first, sl.h_m1, (size_t)sl.n * 4);
     memcpy(m2 + sl.first, sl.h_m2, (size_t)sl.n * 4);
@@ -906,11 +1174,22 @@ int finish_slot(pemap_ctx* h, pemap_ctx::Slot& sl, uint32_t* m1, uint32_t* m2, i
 int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, const int* len1, const char* rows2,
              const char* const* ptr2, const int* len2, int stride, uint32_t* m1, uint32_t* m2, int* mapping_type) {
   if (!h) return PEMAP_ERR_ARG;
+  if (h->index_only) return fail(h, PEMAP_ERR_ARG, "handle was opened with PEMAP_INDEX_ONLY=1");
   if (n < 0 || (!rows1 && !ptr1) || !len1 || !m1 || !m2 || !mapping_type) return fail(h, PEMAP_ERR_ARG, "NULL argument");
   const bool paired = h->params.pair_flag != 0;
   if (paired && ((!rows2 && !ptr2) || !len2)) return fail(h, PEMAP_ERR_ARG, "pair_flag set but read2/len2 is NULL");
   CK(cudaSetDevice(h->device));
+  // every length is checked before the first chunk is submitted: no early return with work in flight
+  for (int m = 0; m < (paired ? 2 : 1); m++) {
+    const int* len = m ? len2 : len1;
+    for (int i = 0; i < n; i++)
+      if (len[i] < 0 || len[i] > PM_DP_MAX - 22)
+        return fail(h, PEMAP_ERR_ARG, "read longer than 298 bases (reference DP buffers are 300x300)");
+  }
+  if (rows1 && !ptr1 && stride > h->stride_cap && is_pinned(rows1))
+    return fail(h, PEMAP_ERR_ARG, "row stride larger than 320 bytes");
   begin_batch(h, n);
+  SlotGuard guard{h};
   const bool direct = rows1 && is_pinned(rows1) && is_pinned(len1) && (!paired || (is_pinned(rows2) && is_pinned(len2))) &&
                       is_pinned(m1) && is_pinned(m2) && is_pinned(mapping_type);
   const bool pipelined = h->keep == 0;  // the inspection modes read shared scratch after every chunk
@@ -922,12 +1201,14 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
       int rc = finish_slot(h, sl, m1, m2, mapping_type);
       if (rc) return rc;
     }
+    if (h->want_drain) {  // the append buffer passed its high-water mark: spill it before more is appended
+      int rc = drain_insertions(h);
+      if (rc) return rc;
+    }
     int max_len = 0, min_len = 1 << 30;
     for (int m = 0; m < (paired ? 2 : 1); m++) {
       const int* len = (m ? len2 : len1) + first;
       for (int i = 0; i < cn; i++) {
-        if (len[i] < 0 || len[i] > PM_DP_MAX - 22)
-          return fail(h, PEMAP_ERR_ARG, "read longer than 298 bases (reference DP buffers are 300x300)");
         max_len = std::max(max_len, len[i]);
         min_len = std::min(min_len, len[i]);
       }
@@ -969,6 +1250,7 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
     CK(cudaMemcpyAsync(o1, sl.d_m1, (size_t)cn * 4, cudaMemcpyDeviceToHost, h->s_d2h));
     CK(cudaMemcpyAsync(o2, sl.d_m2, (size_t)cn * 4, cudaMemcpyDeviceToHost, h->s_d2h));
     CK(cudaMemcpyAsync(ot, sl.d_type, (size_t)cn * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+    CK(cudaMemcpyAsync(h->h_ins_used + (chunk_no & 1), h->d_ins_cursor, 8, cudaMemcpyDeviceToHost, h->s_d2h));
     CK(cudaEventRecord(sl.ev_d2h, h->s_d2h));
     sl.pending = true;
     sl.n = cn;
@@ -1042,6 +1324,16 @@ int pemap_init(pemap_t** out, const pemap_index* ix, const pemap_params* p, int 
   CK(cudaMemcpy(h->d_genome, ix->genome, h->genome_size, cudaMemcpyHostToDevice));
   rc = upload_cstart(h, ix->contig_starts, ix->no_contigs);
   if (rc) return rc;
+  read_index_env(h);
+  if (!h->index_only && !h->seed_legacy) {
+    uint32_t* code_of = nullptr;
+    CK(cudaMalloc(&code_of, (size_t)(h->n_mers + 1) * 4));
+    pm::k_rbi_expand_codes<<<1u << 24, 256, 0, h->stream>>>(h->d_pos_index, code_of, h->n_mers);
+    rc = build_rbi(h, code_of, h->d_mers, h->n_mers);
+    cudaFree(code_of);
+    if (rc) return rc;
+    drop_file_index_if_large(h);
+  }
   return finish_init(h);
 }
 
@@ -1122,12 +1414,20 @@ int pemap_init_from_genome(pemap_t** out, const char* genome, const int64_t* con
   CK(cudaGetLastError());
   cudaFree(tmp);
   cudaFree(d_real);
-  cudaFree(d_key);
   cudaFree(d_val);
   cudaFree(d_key2);
   cudaFree(d_val2);
   cudaFree(d_flag);
   cudaFree(d_nsel);
+  read_index_env(h);
+  if (!h->index_only && !h->seed_legacy) {
+    rc = build_rbi(h, d_key, h->d_mers, nsel);
+    cudaFree(d_key);
+    if (rc) return rc;
+    drop_file_index_if_large(h);
+  } else {
+    cudaFree(d_key);
+  }
   return finish_init(h);
 }
 
@@ -1164,6 +1464,7 @@ int pemap_map_batch_device(pemap_t* h, int n, const char* d_reads1, const int* d
                            const int* d_len2, int stride, int max_len, uint32_t* d_m1, uint32_t* d_m2,
                            int* d_mapping_type) {
   if (!h) return PEMAP_ERR_ARG;
+  if (h->index_only) return fail(h, PEMAP_ERR_ARG, "handle was opened with PEMAP_INDEX_ONLY=1");
   if (n < 0 || !d_reads1 || !d_len1 || !d_m1 || !d_m2 || !d_mapping_type) return fail(h, PEMAP_ERR_ARG, "NULL argument");
   if (max_len < 16 || max_len > PM_DP_MAX - 22) return fail(h, PEMAP_ERR_ARG, "max_len out of range");
   const bool paired = h->params.pair_flag != 0;
@@ -1192,6 +1493,14 @@ int pemap_map_batch_device(pemap_t* h, int n, const char* d_reads1, const int* d
     if (rc) return rc;
     rc = account_chunk(h, cn, paired, h->slots[0].ev);
     if (rc) return rc;
+    CK(cudaMemcpyAsync(h->h_ins_used, h->d_ins_cursor, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    rc = check_insertion_fill(h, h->h_ins_used[0]);
+    if (rc) return rc;
+    if (h->want_drain) {
+      rc = drain_insertions(h);
+      if (rc) return rc;
+    }
     rc = retain_chunk(h, cn, first, paired);
     if (rc) return rc;
   }
@@ -1220,50 +1529,81 @@ int pemap_get_candidates(pemap_t* h, int i, int mate, uint32_t* spots, int8_t* o
   return n;
 }
 
-int pemap_finish(pemap_t* h, const pemap_record** records, uint64_t* n_records, const pemap_insertion** ins,
-                 uint64_t* n_ins) {
-  if (!h || !records || !n_records) return PEMAP_ERR_ARG;
+int pemap_finish_stream(pemap_t* h, pemap_site_cb cb, void* ctx, uint64_t* n_records) {
+  if (!h || !cb) return PEMAP_ERR_ARG;
+  if (h->index_only) return fail(h, PEMAP_ERR_ARG, "handle was opened with PEMAP_INDEX_ONLY=1");
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
   const uint64_t gs = h->genome_size;
   const uint64_t tile = (uint64_t)PM_COMPACT_BLOCK * PM_COMPACT_ITEMS;
-  const unsigned n_tiles = (unsigned)((gs + tile - 1) / tile);
-  unsigned long long *d_cnt = nullptr, *d_off = nullptr;
-  CK(cudaMalloc(&d_cnt, ((size_t)n_tiles + 1) * 8));
-  CK(cudaMalloc(&d_off, ((size_t)n_tiles + 1) * 8));
-  CK(cudaMemsetAsync(d_cnt, 0, ((size_t)n_tiles + 1) * 8, h->stream));
-  pm::k_compact_count<<<n_tiles, PM_COMPACT_BLOCK, 0, h->stream>>>(h->d_counts, gs, d_cnt);
-  void* tmp = nullptr;
-  size_t need = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, need, d_cnt, d_off, (int)n_tiles + 1, h->stream);
-  CK(cudaMalloc(&tmp, need));
-  CK(cub::DeviceScan::ExclusiveSum(tmp, need, d_cnt, d_off, (int)n_tiles + 1, h->stream));
-  unsigned long long total = 0;
-  CK(cudaMemcpyAsync(&total, d_off + n_tiles, 8, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  pm::PileRecord* d_rec = nullptr;
-  CK(cudaMalloc(&d_rec, (size_t)(total + 1) * sizeof(pm::PileRecord)));
-  pm::k_compact_write<<<n_tiles, PM_COMPACT_BLOCK, 0, h->stream>>>(h->d_counts, gs, d_off, d_rec);
-  h->stats.launches += 2;
-  h->records.resize(total);
+  if (!h->fin_sites) {  // staging: two device and two pinned host buffers of one window each
+    uint64_t w = 1ull << 24;  // 16 M sites = 256 MB of records per buffer
+    if (const char* s = getenv("PEMAP_FINISH_SITES")) w = std::max<uint64_t>(tile, strtoull(s, nullptr, 10));
+    w = std::min(w, std::max<uint64_t>(gs, 1));
+    w = (w + tile - 1) / tile * tile;
+    const size_t n_tiles = (size_t)(w / tile);
+    for (int k = 0; k < 2; k++) {
+      CK(cudaMalloc(&h->d_fin_rec[k], (size_t)w * sizeof(pm::PileRecord)));
+      CK(cudaHostAlloc(&h->h_fin_rec[k], (size_t)w * sizeof(pemap_record), cudaHostAllocDefault));
+      CK(cudaEventCreateWithFlags(&h->ev_fin[k], cudaEventDisableTiming));
+    }
+    CK(cudaMalloc(&h->d_fin_cnt, (n_tiles + 1) * 8));
+    CK(cudaMalloc(&h->d_fin_off, 2 * (n_tiles + 1) * 8));
+    CK(cudaHostAlloc(&h->h_fin_total, 2 * 8, cudaHostAllocDefault));
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, h->d_fin_cnt, h->d_fin_off, (int)n_tiles + 1, h->stream);
+    CK(cudaMalloc(&h->d_fin_tmp, need));
+    h->fin_tmp_bytes = need;
+    h->fin_sites = w;
+  }
   static_assert(sizeof(pm::PileRecord) == sizeof(pemap_record) && sizeof(pemap_record) == 16, "record layout");
-  if (total)
-    CK(cudaMemcpyAsync(h->records.data(), d_rec, (size_t)total * sizeof(pemap_record), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  const uint64_t W = h->fin_sites;
+  const uint64_t n_win = (gs + W - 1) / W;
+  uint64_t total_all = 0;
+  uint64_t win_total[2] = {0, 0};
+  int cb_rc = 0;
+  // window w is compacted on the compute stream and copied out on the D2H stream while the caller consumes window w-1
+  for (uint64_t w = 0; w <= n_win; w++) {
+    const int slot = (int)(w & 1);
+    if (w < n_win) {
+      const uint64_t s0 = w * W, ns = std::min(W, gs - s0);
+      const unsigned n_tiles = (unsigned)((ns + tile - 1) / tile);
+      unsigned long long* d_off = h->d_fin_off + (size_t)slot * (W / tile + 1);
+      CK(cudaMemsetAsync(h->d_fin_cnt + n_tiles, 0, 8, h->stream));
+      pm::k_compact_count<<<n_tiles, PM_COMPACT_BLOCK, 0, h->stream>>>(h->d_counts, s0, ns, h->d_fin_cnt);
+      size_t need = h->fin_tmp_bytes;
+      CK(cub::DeviceScan::ExclusiveSum(h->d_fin_tmp, need, h->d_fin_cnt, d_off, (int)n_tiles + 1, h->stream));
+      pm::k_compact_write<<<n_tiles, PM_COMPACT_BLOCK, 0, h->stream>>>(h->d_counts, s0, ns, d_off, h->d_fin_rec[slot]);
+      h->stats.launches += 2;
+      CK(cudaMemcpyAsync(h->h_fin_total + slot, d_off + n_tiles, 8, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      win_total[slot] = h->h_fin_total[slot];
+      if (win_total[slot])
+        CK(cudaMemcpyAsync(h->h_fin_rec[slot], h->d_fin_rec[slot], (size_t)win_total[slot] * sizeof(pemap_record),
+                           cudaMemcpyDeviceToHost, h->s_d2h));
+      CK(cudaEventRecord(h->ev_fin[slot], h->s_d2h));
+    }
+    if (w > 0) {  // hand window w-1 to the caller (its copy overlaps the compaction of window w issued above)
+      const int ps = slot ^ 1;
+      CK(cudaEventSynchronize(h->ev_fin[ps]));
+      if (win_total[ps] && !cb_rc) cb_rc = cb(ctx, h->h_fin_rec[ps], win_total[ps]);
+      total_all += win_total[ps];
+    }
+  }
   CK(cudaGetLastError());
-  cudaFree(tmp);
-  cudaFree(d_cnt);
-  cudaFree(d_off);
-  cudaFree(d_rec);
-  *records = h->records.data();
-  *n_records = total;
+  if (n_records) *n_records = total_all;
+  if (cb_rc) return fail(h, PEMAP_ERR_ARG, "pemap_finish_stream: the callback returned non-zero");
+  return fetch_counters(h);
+}
 
-  // insertion strings: {u32 pos, u32 len, chars padded to 4} records appended by the traceback kernel
-  unsigned long long used = 0;
-  CK(cudaMemcpy(&used, h->d_ins_cursor, 8, cudaMemcpyDeviceToHost));
-  if (used > h->ins_cap) return fail(h, PEMAP_ERR_NOMEM, "insertion buffer overflow (raise PEMAP_INS_MB)");
-  std::vector<unsigned char> raw(used);
-  if (used) CK(cudaMemcpy(raw.data(), h->d_ins, used, cudaMemcpyDeviceToHost));
+int pemap_get_insertions(pemap_t* h, const pemap_insertion** ins, uint64_t* n_ins) {
+  if (!h) return PEMAP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  // insertion strings: {u32 pos, u32 len, chars padded to 4} records appended by the traceback kernels
+  int rc = drain_insertions(h);
+  if (rc) return rc;
+  const std::vector<unsigned char>& raw = h->ins_raw;
+  const size_t used = raw.size();
   h->ins.clear();
   h->ins_pool.clear();
   std::vector<size_t> offs;
@@ -1289,18 +1629,42 @@ int pemap_finish(pemap_t* h, const pemap_record** records, uint64_t* n_records, 
   });
   if (ins) *ins = h->ins.data();
   if (n_ins) *n_ins = h->ins.size();
-  return fetch_counters(h);
+  return PEMAP_OK;
+}
+
+static int collect_records(void* ctx, const pemap_record* rec, uint64_t n) {
+  std::vector<pemap_record>* v = static_cast<std::vector<pemap_record>*>(ctx);
+  v->insert(v->end(), rec, rec + n);
+  return 0;
+}
+
+int pemap_finish(pemap_t* h, const pemap_record** records, uint64_t* n_records, const pemap_insertion** ins,
+                 uint64_t* n_ins) {
+  if (!h || !records || !n_records) return PEMAP_ERR_ARG;
+  h->records.clear();
+  uint64_t total = 0;
+  int rc = pemap_finish_stream(h, collect_records, &h->records, &total);
+  if (rc) return rc;
+  *records = h->records.data();
+  *n_records = total;
+  return pemap_get_insertions(h, ins, n_ins);
 }
 
 int pemap_reset_counts(pemap_t* h) {
   if (!h) return PEMAP_ERR_ARG;
+  if (h->index_only) return PEMAP_OK;
   CK(cudaSetDevice(h->device));
+  // stream-ordered: every work stream of the handle is non-blocking, so a memset on the legacy stream would not be
+  // ordered against the next batch's kernels (the aux and copy streams only ever run between events of h->stream)
+  CK(cudaMemsetAsync(h->d_counts, 0, (size_t)h->genome_size * 6 * 4, h->stream));
+  CK(cudaMemsetAsync(h->d_ins_cursor, 0, 8, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemset(h->d_counts, 0, (size_t)h->genome_size * 6 * 4));
-  CK(cudaMemset(h->d_ins_cursor, 0, 8));
   h->records.clear();
+  h->records.shrink_to_fit();
   h->ins.clear();
   h->ins_pool.clear();
+  h->ins_raw.clear();
+  h->want_drain = false;
   return PEMAP_OK;
 }
 
@@ -1352,7 +1716,8 @@ int pemap_get_stats(pemap_t* h, pemap_stats* out) {
 int pemap_reset_stats(pemap_t* h) {
   if (!h) return PEMAP_ERR_ARG;
   CK(cudaSetDevice(h->device));
-  CK(cudaMemset(h->d_counters, 0, sizeof(pm::SeedCounters)));
+  CK(cudaMemsetAsync(h->d_counters, 0, sizeof(pm::SeedCounters), h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   memset(&h->stats, 0, sizeof(h->stats));
   return PEMAP_OK;
 }
@@ -1368,6 +1733,7 @@ int pemap_index_device(pemap_t* h, const uint32_t** d_pos_index, const uint32_t*
 int pemap_read_pos_index(pemap_t* h, uint64_t first, uint64_t n, uint32_t* out) {
   if (!h || !out) return PEMAP_ERR_ARG;
   if (first + n > ((uint64_t)1 << 32) + 1) return fail(h, PEMAP_ERR_ARG, "range beyond 2^32+1");
+  if (!h->d_pos_index) return fail(h, PEMAP_ERR_ARG, "pos_index is not resident (dropped after the bucket index was built; PEMAP_KEEP_INDEX=1)");
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpy(out, h->d_pos_index + first, n * 4, cudaMemcpyDeviceToHost));
   return PEMAP_OK;
@@ -1376,6 +1742,7 @@ int pemap_read_pos_index(pemap_t* h, uint64_t first, uint64_t n, uint32_t* out) 
 int pemap_read_mers(pemap_t* h, uint64_t first, uint64_t n, uint32_t* out) {
   if (!h || !out) return PEMAP_ERR_ARG;
   if (first + n > h->n_mers) return fail(h, PEMAP_ERR_ARG, "range beyond n_mers");
+  if (!h->d_mers) return fail(h, PEMAP_ERR_ARG, "mers is not resident (dropped after the bucket index was built; PEMAP_KEEP_INDEX=1)");
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpy(out, h->d_mers + first, n * 4, cudaMemcpyDeviceToHost));
   return PEMAP_OK;
@@ -1405,6 +1772,18 @@ void pemap_destroy(pemap_t* h) {
                    h->d_replay_tasks, h->d_diag_winners, h->d_exact_winners, h->d_oob_winners, h->d_flagq, h->d_walk_meta, h->d_pair_codes, h->d_sw_list};
     for (void* p : dev)
       if (p) cudaFree(p);
+    void* rbi[] = {h->d_rbi_data[0], h->d_rbi_data[1], h->d_rbi_data[2], h->d_rbi_data[3], h->d_rbi_dir[0], h->d_rbi_dir[1],
+                   h->d_rbi_dir[2], h->d_rbi_dir[3], h->d_big_list, h->d_big_scratch};
+    for (void* p : rbi)
+      if (p) cudaFree(p);
+    void* fin[] = {h->d_fin_rec[0], h->d_fin_rec[1], h->d_fin_cnt, h->d_fin_off, h->d_fin_tmp};
+    for (void* p : fin)
+      if (p) cudaFree(p);
+    void* finh[] = {h->h_fin_rec[0], h->h_fin_rec[1], h->h_fin_total, h->h_ins_used};
+    for (void* p : finh)
+      if (p) cudaFreeHost(p);
+    for (auto& ev : h->ev_fin)
+      if (ev) cudaEventDestroy(ev);
     for (auto& sl : h->slots) {
       void* dv[] = {sl.d_reads[0], sl.d_reads[1], sl.d_len[0], sl.d_len[1], sl.d_m1, sl.d_m2, sl.d_type};
       for (void* p : dv)

@@ -1,0 +1,570 @@
+// seed_rbi.cuh - seed lookup + co-linear chaining over a device-private ROTATED BUCKET INDEX (sm_100a).
+//
+// Same contract as seed_chain.cuh (initial_map, pemapper.c:1539-1690: fill_mers 1969-2003, get_mers 2158-2165, the
+// gather / veto / sort loop 1594-1640, find_matches 2189-2289, then the windows of map_everything 1047-1081), other
+// memory layout.  pos_index / mers are the reference's FILE format; looked up as the reference does they cost
+// 49 isolated DRAM accesses per segment (980 per 150-bp read-mate plus ~500 list gathers on a human-sized genome), and
+// a B200 serves 41.7 G isolated accesses/s whatever their size (profiles/gather_probe_r01.json) while it streams random
+// 1 KiB chunks at 5.3-6.0 TB/s (tools/chunk_probe.cu, profiles/chunk_probe_r02.json).
+//
+// The 49 k-mers of a segment are the exact code and code ^ (d << 2f), f = 0..15, d = 1..3.  Cut the 32 code bits into
+// four byte-wide groups g = 0..3 ("tag" = bits 8g..8g+7, "bucket" = the other 24 bits): the 12 neighbours that differ
+// inside group g share the segment's bucket of rotation g.  The index keeps, for every rotation, all indexed positions
+// grouped by bucket (a directory of 2^24+1 offsets) with their one-byte tags, so the 49 lists of a segment are FOUR
+// contiguous reads of ~256 * (genome / 2^32) entries each (~0.9 KB on 3.1 Gb) filtered by tag, instead of 49 + ~25
+// isolated accesses.  A k-mer with >= too_many_spots positions is stored as ONE marker entry (its positions are never
+// used: 1602-1606 empties the segment).  Nothing is approximated: every position of every one of the 49 lists comes out.
+//
+// Bucket layout (16-byte units): n4 = ceil(n / 4) units of 4 positions each, then ceil(n4 / 4) units holding the n tags
+// (unit S = n4 + ceil(n4/4) per bucket, so n4 = S - ceil(S/5) follows from two directory words).  Unused slots hold
+// PM_RBI_EMPTY.
+//
+// Chaining: the reference sorts every segment list and, per anchor, scans the later lists for a position whose
+// diagonal (pos - segment offset) is within +-11 of the anchor's.  Here the entries of a strand are hashed by
+// diagonal / 16 in shared memory, every entry gets its `found` count in one parallel pass over the three bins around
+// it, and only the few anchors that reach min_match are ordered (segment, position) and fed to the reference's
+// sequential rules (reset on better, dedup, the 200-cap return).
+#pragma once
+#include "pemap_common.cuh"
+
+#define PM_RBI_EMPTY 0xFFFFFFFFu
+#define PM_RBI_MARK 0xFFFFFFFEu
+#define PM_RBI_CAP 512                  // entries of one strand kept in shared memory (a 150-bp read on 3.1 Gb has ~360)
+#define PM_RBI_TAB 512                  // hash slots of the fast path
+#define PM_RBI_MAXB (4 * PM_MAX_SEG)    // buckets per strand
+#define PM_RBI_BIG_CAP 98304            // >= 19 segments * 49 * 99 positions: the slow path holds any strand
+#define PM_RBI_BIG_TAB 131072
+#ifndef PM_RBI_UNROLL
+#define PM_RBI_UNROLL 4
+#endif
+
+namespace pm {
+
+__host__ __device__ __forceinline__ uint32_t rbi_tag(uint32_t code, int g) { return (code >> (8 * g)) & 255u; }
+__host__ __device__ __forceinline__ uint32_t rbi_bucket(uint32_t code, int g) {
+  const uint32_t lo = g ? (code & ((1u << (8 * g)) - 1u)) : 0u;
+  const uint32_t hi = g == 3 ? 0u : (code >> (8 * g + 8));
+  return (hi << (8 * g)) | lo;
+}
+__host__ __device__ __forceinline__ uint32_t rbi_units(uint32_t n) {  // 16-byte units of a bucket with n entries
+  const uint32_t n4 = (n + 3u) >> 2;
+  return n4 + ((n4 + 3u) >> 2);
+}
+
+struct RbiIndex {
+  const uint4* data[4];     // bucket arrays of the four rotations
+  const uint32_t* dir[4];   // 2^24+1 offsets each, in 16-byte units
+};
+
+// ------------------------------------------------------------------------------------------------ builder kernels
+
+// code_of[i] = k-mer code owning mers[i]: one thread per code, runs of pos_index (only the pemap_init path needs it)
+__global__ void __launch_bounds__(256) k_rbi_expand_codes(const uint32_t* pos_index, uint32_t* code_of, uint64_t n_mers) {
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w > 0xFFFFFFFFull) return;
+  uint64_t lo = pos_index[w], hi = pos_index[w + 1];
+  if (hi > n_mers) hi = n_mers;
+  for (uint64_t i = lo; i < hi; i++) code_of[i] = (uint32_t)w;
+}
+
+// keep flag of entry i of the code-sorted (code, pos) list: positions of k-mers below the veto threshold are kept, a
+// crowded k-mer keeps its first entry only (turned into the marker by k_rbi_mark after the compaction).  Counts are
+// get_mers' (2158-2165): pos_index[(u32)(w+1)] - pos_index[w] in 32-bit arithmetic, so the count of 0xFFFFFFFF wraps
+// (`last_cnt`, computed on the host).
+__device__ __forceinline__ uint32_t rbi_kmer_count(const uint32_t* pos_index, uint32_t c, uint32_t last_cnt) {
+  return c == 0xFFFFFFFFu ? last_cnt : pos_index[(uint64_t)c + 1] - pos_index[c];
+}
+__global__ void __launch_bounds__(256) k_rbi_flag(const uint32_t* code, const uint32_t* pos_index, uint64_t n, uint32_t too_many,
+                                                  uint32_t last_cnt, unsigned char* flag) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t c = code[i];
+  const uint32_t cnt = rbi_kmer_count(pos_index, c, last_cnt);
+  const uint64_t rank = i - pos_index[c];
+  // cnt < true count only for the wrapped 0xFFFFFFFF (then the reference sees the first cnt positions)
+  flag[i] = cnt >= too_many ? (rank == 0 ? 1 : 0) : (rank < cnt ? 1 : 0);
+}
+__global__ void __launch_bounds__(256) k_rbi_mark(const uint32_t* code, const uint32_t* pos_index, uint64_t n, uint32_t too_many,
+                                                  uint32_t last_cnt, uint32_t* val) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && rbi_kmer_count(pos_index, code[i], last_cnt) >= too_many) val[i] = PM_RBI_MARK;
+}
+
+__global__ void __launch_bounds__(256) k_rbi_keys(const uint32_t* code, uint64_t n, int g, uint32_t* key) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) key[i] = (rbi_bucket(code[i], g) << 8) | rbi_tag(code[i], g);
+}
+
+// bstart[b] = first entry of bucket b in the key-sorted list, b = 0..2^24
+__global__ void __launch_bounds__(256) k_rbi_bucket_starts(const uint32_t* key, uint64_t n, uint32_t* bstart) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > (1u << 24)) return;
+  uint64_t lo = 0, hi = n;
+  if (b == (1u << 24)) lo = n;
+  else {
+    const uint32_t k = b << 8;
+    while (lo < hi) {
+      const uint64_t m = (lo + hi) >> 1;
+      if (key[m] < k) lo = m + 1; else hi = m;
+    }
+  }
+  bstart[b] = (uint32_t)lo;
+}
+
+__global__ void __launch_bounds__(256) k_rbi_bucket_units(const uint32_t* bstart, uint32_t* units) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > (1u << 24)) return;
+  units[b] = b == (1u << 24) ? 0u : rbi_units(bstart[b + 1] - bstart[b]);
+}
+
+__global__ void __launch_bounds__(256) k_rbi_fill(const uint32_t* key, const uint32_t* val, uint64_t n, const uint32_t* bstart,
+                                                  const uint32_t* dir, uint4* data) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k = key[i], b = k >> 8;
+  const uint32_t first = bstart[b], nb = bstart[b + 1] - first, r = (uint32_t)(i - first);
+  const uint64_t base = dir[b];
+  const uint32_t n4 = (nb + 3u) >> 2;
+  reinterpret_cast<uint32_t*>(data)[base * 4 + r] = val[i];
+  reinterpret_cast<unsigned char*>(data)[(base + n4) * 16 + r] = (unsigned char)(k & 255u);
+}
+
+// ------------------------------------------------------------------------------------------------ seed kernel
+
+struct SeedRbiArgs {
+  RbiIndex ix;
+  const uint32_t* cstart;      // n_contigs+1 (padded to >= 9 entries)
+  const char* reads[2];        // [n][stride] each
+  const int* len[2];
+  int stride;
+  int n_reads;                 // reads (pairs) in this chunk
+  int paired;
+  Task* tasks;
+  uint32_t* task_cursor;
+  uint32_t task_cap;
+  uint32_t* cand_base;         // [2*n_reads]
+  uint32_t* cand_n;            // [2*n_reads]
+  SeedCounters* counters;
+  uint32_t* big_list;          // read-mate work items whose strand lists did not fit shared memory
+  uint32_t* big_cursor;
+  const uint32_t* work_list;   // BIG: the items to process, *work_n of them
+  const uint32_t* work_n;
+  unsigned char* big_scratch;  // BIG: per warp PM_RBI_BIG_BYTES
+  int fast_cap;                // entries of a strand the first pass accepts (<= PM_RBI_CAP; PEMAP_RBI_CAP lowers it in tests)
+  DevParams p;
+};
+
+#define PM_RBI_BIG_BYTES ((size_t)PM_RBI_BIG_CAP * 10 + (size_t)PM_RBI_BIG_TAB * 4)
+
+struct RbiWarpSmem {           // per warp, both paths
+  uint32_t b_off[PM_RBI_MAXB];       // bucket start (16-byte units)
+  uint32_t b_pre[PM_RBI_MAXB + 1];   // prefix sum of the buckets' position quads
+  uint32_t b_meta[PM_RBI_MAXB];      // segment | rotation << 8 | exact tag << 16
+  uint32_t kcode[2 * PM_MAX_SEG];
+  uint32_t segcnt[PM_MAX_SEG];
+  uint32_t hit_pos[PM_MAX_HITS];
+  uint16_t hit_off[PM_MAX_HITS];
+  uint8_t hit_or[PM_MAX_HITS];
+  char rd[2][PM_DP_MAX];             // forward read and its reverse_transcribe (C->T converted when bisulfite)
+};
+
+struct RbiFastStore {          // per warp, fast path only: the entries of one strand
+  uint32_t pos[PM_RBI_CAP];
+  uint32_t head[PM_RBI_TAB];         // chain heads; afterwards scratch of the anchor sort
+  uint16_t next[PM_RBI_CAP];
+  uint8_t seg[PM_RBI_CAP];
+  uint8_t found[PM_RBI_CAP];
+};
+
+__device__ __forceinline__ uint4 rbi_ld16(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t rbi_ld4(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t rbi_hash(uint32_t bin, uint32_t mask) {
+  uint32_t x = bin * 0x9E3779B1u;
+  return (x ^ (x >> 15)) & mask;
+}
+
+// ascending sort of idx[0..n) by key pos[idx] (keys are distinct: positions of one segment); idx has room for the next
+// power of two, the padding sorts last
+__device__ __forceinline__ void rbi_sort_idx(uint32_t* idx, const uint32_t* pos, int n, int lane) {
+  int P = 1;
+  while (P < n) P <<= 1;
+  for (int i = n + lane; i < P; i += 32) idx[i] = 0xFFFFFFFFu;
+  __syncwarp();
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < P; i += 32) {
+        const int x = i ^ j;
+        if (x > i) {
+          const uint32_t a = idx[i], b = idx[x];
+          const uint32_t ka = a == 0xFFFFFFFFu ? 0xFFFFFFFFu : pos[a], kb = b == 0xFFFFFFFFu ? 0xFFFFFFFFu : pos[b];
+          const bool up = (i & k) == 0;
+          if ((ka > kb) == up) {
+            idx[i] = b;
+            idx[x] = a;
+          }
+        }
+      }
+      __syncwarp();
+    }
+}
+
+// One read-mate.  BIG = false: entries in shared memory (st_*), a strand with more than `cap` entries makes the function
+// return false and the caller queues the read-mate for the BIG pass, whose stores live in a per-warp global scratch.
+template <bool BIG, class NextT>
+__device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpSmem& sm, uint32_t* st_pos, uint32_t* st_head,
+                                                  NextT* st_next, uint8_t* st_seg, uint8_t* st_found, const int cap,
+                                                  const uint32_t tab_mask, const int w, const int lane,
+                                                  unsigned long long& stat_pos, unsigned long long& stat_cand,
+                                                  unsigned long long& stat_cells, unsigned long long& stat_lookups) {
+  constexpr NextT NIL = (NextT)~(NextT)0;
+  const int r = a.paired ? (w >> 1) : w, mate = a.paired ? (w & 1) : 0;
+  const uint32_t rm = 2u * (uint32_t)r + (uint32_t)mate;
+  const int len = a.len[mate][r];
+  const char* read = a.reads[mate] + (size_t)r * a.stride;
+  int tot = 0;
+  unsigned long long l_pos = 0, l_lookups = 0;  // booked when the read-mate is finished (not when it is handed to the BIG pass)
+  bool ok = (len >= 16 && len < PM_DP_MAX - 21);
+  // N filter (1552-1559) + forward / reverse-transcribed copies (1019-1021, 1561-1570)
+  if (ok) {
+    int n_count = 0;
+    for (int i = lane; i < len; i += 32) {
+      const char ch = read[i];
+      n_count += (ch == 'N');
+      char f = ch, v = rt_char(ch);
+      if (a.p.is_bisulfite) {
+        if (f == 'C') f = 'T';
+        if (v == 'C') v = 'T';
+      }
+      sm.rd[0][i] = f;
+      sm.rd[1][len - 1 - i] = v;
+    }
+    n_count = __reduce_add_sync(0xFFFFFFFFu, n_count);
+    if (n_count >= 1 + len / 10) ok = false;
+  }
+  __syncwarp();
+
+  if (ok) {
+    int total_cuts = len / 16;  // 1573-1587 with idepth == 16
+    if ((len & 15) == 0) total_cuts--;
+    const int nseg = total_cuts + 1;
+    // exact 16-mer of every (strand, segment): convert_seq_int 2408-2423
+    for (int ss = lane; ss < 2 * nseg; ss += 32) {
+      const int strand = ss >= nseg, s = strand ? ss - nseg : ss;
+      const int off = (s < total_cuts) ? 16 * s : len - 16;
+      const char* q = sm.rd[strand] + off;
+      uint32_t code = 0;
+#pragma unroll
+      for (int i = 0; i < 16; i++) code = (code << 2) | base_code(q[i]);
+      sm.kcode[ss] = code;
+    }
+    __syncwarp();
+    l_lookups = (unsigned long long)(2 * nseg * PM_KV);
+
+    int min_match = total_cuts > 1 ? total_cuts : 1;  // 1642-1645
+    if (total_cuts > 4) min_match = (4 * total_cuts) / 5;
+    if (min_match > 4) min_match = 4;
+    const int max_depth = total_cuts;
+    const int mo = (a.p.idepth - 4 > 2) ? a.p.idepth - 4 : 2;  // max_off (2196)
+    const int nb = 4 * nseg;
+
+    for (int strand = 0; strand < 2; strand++) {
+      if (strand == 1 && tot >= a.p.max_hits) break;  // 1658
+      // ---- bucket directory: four buckets per segment
+      uint32_t carry = 0;
+      if (lane == 0) sm.b_pre[0] = 0;
+      for (int b0 = 0; b0 < nb; b0 += 32) {
+        const int b = b0 + lane;
+        uint32_t n4 = 0;
+        if (b < nb) {
+          const int s = b >> 2, g = b & 3;
+          const uint32_t code = sm.kcode[strand * nseg + s];
+          const uint32_t bk = rbi_bucket(code, g);
+          const uint32_t d0 = __ldg(a.ix.dir[g] + bk), d1 = __ldg(a.ix.dir[g] + bk + 1);
+          const uint32_t S = d1 - d0;
+          n4 = S - (S + 4u) / 5u;
+          sm.b_off[b] = d0;
+          sm.b_meta[b] = (uint32_t)s | ((uint32_t)g << 8) | (rbi_tag(code, g) << 16);
+        }
+        uint32_t inc = n4;  // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (b < nb) sm.b_pre[b + 1] = carry + inc;
+        carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+      }
+      __syncwarp();
+      const uint32_t Q = carry;  // position quads of the strand's buckets
+
+      // ---- gather (get_mers 2158-2165, loop 1594-1612 / 1619-1637): every entry whose tag is the segment's tag or one
+      // 2-bit field away from it; the exact k-mer sits in all four of its buckets and is taken from rotation 0
+      int cnt = 0;           // warp-uniform
+      uint32_t vmask = 0;    // segments with a crowded k-mer (per lane, OR-reduced below)
+      bool overflow = false;
+      int cur = 0;           // per-lane bucket cursor: flat quad indices only grow
+      for (uint32_t f0 = 0; f0 < Q; f0 += 32 * PM_RBI_UNROLL) {
+        uint4 P[PM_RBI_UNROLL];
+        uint32_t T[PM_RBI_UNROLL], M[PM_RBI_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PM_RBI_UNROLL; u++) {
+          const uint32_t f = f0 + (uint32_t)(u * 32 + lane);
+          P[u] = make_uint4(PM_RBI_EMPTY, PM_RBI_EMPTY, PM_RBI_EMPTY, PM_RBI_EMPTY);
+          T[u] = 0;
+          M[u] = 0;
+          if (f < Q) {
+            while (f >= sm.b_pre[cur + 1]) cur++;
+            const uint32_t q = f - sm.b_pre[cur], n4 = sm.b_pre[cur + 1] - sm.b_pre[cur];
+            const uint32_t meta = sm.b_meta[cur];
+            const uint4* base = a.ix.data[(meta >> 8) & 3u] + sm.b_off[cur];
+            P[u] = rbi_ld16(base + q);
+            T[u] = rbi_ld4(reinterpret_cast<const uint32_t*>(base + n4) + q);
+            M[u] = meta;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < PM_RBI_UNROLL; u++) {
+          // per tag byte: fields that differ from the exact tag; a byte qualifies when at most one field differs
+          const uint32_t X = T[u] ^ ((M[u] >> 16) * 0x01010101u);
+          const uint32_t D = (X | (X >> 1)) & 0x55555555u;
+          const uint32_t Z = D & ((D | 0x80808080u) - 0x01010101u);            // byte == 0 <=> <= 1 field differs
+          uint32_t hit = ((Z + 0x7F7F7F7Fu) & 0x80808080u) ^ 0x80808080u;      // bit 7 of byte k: tag k qualifies
+          if (((M[u] >> 8) & 3u) != 0u) {                                        // rotations 1..3 skip the exact k-mer
+            const uint32_t nz = ((D + 0x7F7F7F7Fu) & 0x80808080u);              // bit 7 of byte k: tag differs
+            hit &= nz;
+          }
+          const uint32_t pv[4] = {P[u].x, P[u].y, P[u].z, P[u].w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            bool take = ((hit >> (8 * k + 7)) & 1u) && pv[k] != PM_RBI_EMPTY;
+            if (take && pv[k] == PM_RBI_MARK) {
+              vmask |= 1u << (M[u] & 31u);
+              take = false;
+            }
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, take);
+            if (bal) {
+              const int at = cnt + __popc(bal & ((1u << lane) - 1u));
+              if (take) {
+                if (at < cap) {
+                  st_pos[at] = pv[k];
+                  st_seg[at] = (uint8_t)(M[u] & 255u);
+                } else {
+                  overflow = true;
+                }
+              }
+              cnt += __popc(bal);
+            }
+          }
+        }
+      }
+      if (__any_sync(0xFFFFFFFFu, overflow)) {
+        if (!BIG) return false;
+        cnt = cap;  // cannot happen: the BIG stores hold 19 * 49 * 99 entries
+      }
+      vmask = __reduce_or_sync(0xFFFFFFFFu, vmask);
+      const int N = cnt;
+      l_pos += (unsigned long long)N;
+      __syncwarp();
+
+      // ---- 2200-2207: every segment list longer than max_hits -> no hits at all (also wipes the other strand's)
+      if (N > a.p.max_hits) {  // otherwise some segment has <= max_hits positions
+        for (int s = lane; s < nseg; s += 32) sm.segcnt[s] = 0;
+        __syncwarp();
+        for (int e = lane; e < N; e += 32) atomicAdd(&sm.segcnt[st_seg[e]], 1u);
+        __syncwarp();
+        uint32_t ms = 10000;
+        for (int s = lane; s < nseg; s += 32) ms = min(ms, ((vmask >> s) & 1u) ? 0u : sm.segcnt[s]);
+        ms = __reduce_min_sync(0xFFFFFFFFu, ms);
+        if (ms > (uint32_t)a.p.max_hits) {
+          tot = 0;
+          continue;
+        }
+      }
+
+      // ---- hash the entries by diagonal / 16 (vetoed segments have no list: 1602-1606)
+      for (uint32_t i = lane; i <= tab_mask; i += 32) st_head[i] = 0xFFFFFFFFu;
+      __syncwarp();
+      for (int e = lane; e < N; e += 32) {
+        const int s = st_seg[e];
+        if ((vmask >> s) & 1u) continue;
+        const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
+        const uint32_t bin = (uint32_t)(((unsigned long long)st_pos[e] + 512ull - off) >> 4);
+        const uint32_t old = atomicExch(&st_head[rbi_hash(bin, tab_mask)], (uint32_t)e);
+        st_next[e] = old == 0xFFFFFFFFu ? NIL : (NextT)old;
+      }
+      __syncwarp();
+      // ---- found count of every entry as an anchor (2230-2249): later segments with a position whose diagonal is
+      // within max_off - 1 of the anchor's
+      for (int e = lane; e < N; e += 32) {
+        const int s = st_seg[e];
+        int fnd = 0;
+        if (!((vmask >> s) & 1u) && 1 + max_depth - s >= min_match) {  // an anchor of segment s reaches at most 1 + max_depth - s
+          const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
+          const long long dg = (long long)st_pos[e] + 512ll - (long long)off;
+          const uint32_t bin = (uint32_t)(dg >> 4);
+          uint32_t segs = 0;
+#pragma unroll
+          for (int db = -1; db <= 1; db++) {
+            uint32_t q = st_head[rbi_hash(bin + (uint32_t)db, tab_mask)];
+            while (q != 0xFFFFFFFFu) {
+              const int sq = st_seg[q];
+              if (sq > s) {
+                const uint32_t offq = (sq < total_cuts) ? 16u * (uint32_t)sq : (uint32_t)(len - 16);
+                const long long d = (long long)st_pos[q] + 512ll - (long long)offq - dg;
+                if (d > -(long long)mo && d < (long long)mo) segs |= 1u << sq;  // 2244
+              }
+              const NextT nx = st_next[q];
+              q = nx == NIL ? 0xFFFFFFFFu : (uint32_t)nx;
+            }
+          }
+          fnd = 1 + __popc(segs);
+        }
+        st_found[e] = (uint8_t)fnd;
+      }
+      __syncwarp();
+
+      // ---- the reference's sequential rules over the anchors that can still matter, in its order: segment, position
+      bool done = false;
+      uint32_t* order = st_head;  // the chains are no longer needed
+      for (int loop = 0; !done && loop <= 1 + max_depth - min_match; loop++) {
+        const int off_loop = (loop < total_cuts) ? 16 * loop : len - 16;
+        int R = 0;
+        for (int e0 = 0; e0 < N; e0 += 32) {
+          const int e = e0 + lane;
+          const bool c = e < N && st_seg[e] == loop && (int)st_found[e] >= min_match;
+          const unsigned bal = __ballot_sync(0xFFFFFFFFu, c);
+          if (c) order[R + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)e;
+          R += __popc(bal);
+        }
+        __syncwarp();
+        if (R > 1) rbi_sort_idx(order, st_pos, R, lane);
+        for (int i = 0; i < R && !done; i++) {
+          const uint32_t e = order[i];
+          const int f = st_found[e];
+          const uint32_t apos = st_pos[e];
+          if (f > min_match) {  // 2251-2260
+            min_match = f;
+            if (lane == 0) {
+              sm.hit_pos[0] = apos;
+              sm.hit_off[0] = (uint16_t)off_loop;
+              sm.hit_or[0] = (uint8_t)strand;
+            }
+            tot = 1;
+            __syncwarp();
+          } else if (f == min_match) {
+            if (tot < a.p.max_hits) {  // 2264-2282
+              const uint32_t key = apos - (uint32_t)off_loop;
+              bool dup = false;
+              for (int k = lane; k < tot; k += 32) dup |= (sm.hit_pos[k] - (uint32_t)sm.hit_off[k]) == key;
+              dup = __any_sync(0xFFFFFFFFu, dup);
+              if (!dup) {
+                if (lane == 0) {
+                  sm.hit_pos[tot] = apos;
+                  sm.hit_off[tot] = (uint16_t)off_loop;
+                  sm.hit_or[tot] = (uint8_t)strand;
+                }
+                tot++;
+                __syncwarp();
+              }
+            } else {  // 2283-2284
+              done = true;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  // ---- candidate windows (1047-1081) -> alignment tasks
+  uint32_t base = 0;
+  if (lane == 0 && tot > 0) base = atomicAdd(a.task_cursor, (uint32_t)tot);
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  if (tot > 0 && base + (uint32_t)tot > a.task_cap) tot = 0;  // cannot happen: cap = 200 * work items
+  for (int c = lane; c < tot; c += 32) {
+    const long long t = (long long)sm.hit_pos[c] - (long long)sm.hit_off[c];  // 1664-1669
+    const uint32_t spot = (uint32_t)(t > 0 ? t : 0);
+    Task tk;
+    tk.rm = rm | ((uint32_t)sm.hit_or[c] << 31);
+    tk.spot = spot;
+    candidate_window(a.cstart, a.p.n_contigs, spot, len, a.p.misalign_slop, &tk.wstart, &tk.blen);
+    a.tasks[base + c] = tk;
+    if (tk.blen > 0) stat_cells += (unsigned long long)tk.blen * (unsigned long long)len;
+  }
+  if (lane == 0) {
+    a.cand_base[rm] = base;
+    a.cand_n[rm] = (uint32_t)tot;
+    stat_cand += (unsigned long long)tot;
+    stat_pos += l_pos;
+    stat_lookups += l_lookups;
+  }
+  __syncwarp();
+  return true;
+}
+
+template <int WARPS, bool BIG>
+__global__ void __launch_bounds__(WARPS * 32) k_seed_rbi(SeedRbiArgs a) {
+  extern __shared__ __align__(16) unsigned char rbi_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  RbiWarpSmem& sm = reinterpret_cast<RbiWarpSmem*>(rbi_smem)[warp];
+  const int gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
+  unsigned long long st_pos = 0, st_cand = 0, st_cells = 0, st_lookups = 0;
+  if (BIG) {
+    unsigned char* sc = a.big_scratch + (size_t)gw * PM_RBI_BIG_BYTES;
+    uint32_t* g_pos = reinterpret_cast<uint32_t*>(sc);
+    uint32_t* g_next = g_pos + PM_RBI_BIG_CAP;
+    uint32_t* g_head = g_next + PM_RBI_BIG_CAP;
+    uint8_t* g_seg = reinterpret_cast<uint8_t*>(g_head + PM_RBI_BIG_TAB);
+    uint8_t* g_found = g_seg + PM_RBI_BIG_CAP;
+    const int n_work = (int)*a.work_n;
+    for (int i = gw; i < n_work; i += nw)
+      rbi_map_read_mate<true, uint32_t>(a, sm, g_pos, g_head, g_next, g_seg, g_found, PM_RBI_BIG_CAP, PM_RBI_BIG_TAB - 1,
+                                        (int)a.work_list[i], lane, st_pos, st_cand, st_cells, st_lookups);
+  } else {
+    RbiFastStore& fs = reinterpret_cast<RbiFastStore*>(rbi_smem + WARPS * sizeof(RbiWarpSmem))[warp];
+    const int n_work = a.paired ? 2 * a.n_reads : a.n_reads;
+    for (int w = gw; w < n_work; w += nw) {
+      {  // the next read-mate of this warp: its row and length are cold in HBM; start fetching them now
+        const int wn = w + nw;
+        if (wn < n_work && lane < 4) {
+          const int rn = a.paired ? (wn >> 1) : wn, mn = a.paired ? (wn & 1) : 0;
+          const char* nxt = a.reads[mn] + (size_t)rn * a.stride;
+          if (lane < 3) {
+            if (lane * 128 < a.stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + lane * 128));
+          } else {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.len[mn] + rn));
+          }
+        }
+      }
+      const bool fit = rbi_map_read_mate<false, uint16_t>(a, sm, fs.pos, fs.head, fs.next, fs.seg, fs.found, a.fast_cap,
+                                                          PM_RBI_TAB - 1, w, lane, st_pos, st_cand, st_cells, st_lookups);
+      if (!fit && lane == 0) a.big_list[atomicAdd(a.big_cursor, 1u)] = (uint32_t)w;
+      __syncwarp();
+    }
+  }
+  // statistics: one atomic per counter per warp (lane 0 holds the totals)
+  unsigned long long cells = st_cells;
+  for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xFFFFFFFFu, cells, o);
+  if (lane == 0) {
+    atomicAdd(&a.counters->lookups, st_lookups);
+    atomicAdd(&a.counters->mer_positions, st_pos);
+    atomicAdd(&a.counters->candidates, st_cand);
+    atomicAdd(&a.counters->sw_cells, cells);
+  }
+}
+
+template <int WARPS>
+constexpr size_t seed_rbi_smem(bool big) {
+  return WARPS * sizeof(RbiWarpSmem) + (big ? 0 : WARPS * sizeof(RbiFastStore));
+}
+
+}  // namespace pm

@@ -176,14 +176,15 @@ __device__ __forceinline__ bool site_covered(const uint32_t* c6) {
   return t > 0;  // 829-831
 }
 
-// pass 1: covered sites per tile of PM_COMPACT_BLOCK*PM_COMPACT_ITEMS sites
-__global__ void __launch_bounds__(PM_COMPACT_BLOCK) k_compact_count(const uint32_t* counts, uint64_t genome_size,
+// pass 1: covered sites per tile of PM_COMPACT_BLOCK*PM_COMPACT_ITEMS sites.  Both passes work on a window of the
+// genome, sites [site0, site0 + n_sites): pemap_finish_stream compacts window by window through a bounded buffer.
+__global__ void __launch_bounds__(PM_COMPACT_BLOCK) k_compact_count(const uint32_t* counts, uint64_t site0, uint64_t n_sites,
                                                                     unsigned long long* tile_count) {
   const uint64_t tile0 = (uint64_t)blockIdx.x * (PM_COMPACT_BLOCK * PM_COMPACT_ITEMS);
   int n = 0;
   for (int k = 0; k < PM_COMPACT_ITEMS; k++) {
     uint64_t s = tile0 + (uint64_t)k * PM_COMPACT_BLOCK + threadIdx.x;
-    if (s < genome_size) n += site_covered(counts + s * 6) ? 1 : 0;
+    if (s < n_sites) n += site_covered(counts + (site0 + s) * 6) ? 1 : 0;
   }
   n = __reduce_add_sync(0xFFFFFFFFu, n);
   __shared__ int ws[PM_COMPACT_BLOCK / 32];
@@ -196,8 +197,8 @@ __global__ void __launch_bounds__(PM_COMPACT_BLOCK) k_compact_count(const uint32
   }
 }
 
-// pass 2: tile_off = exclusive scan of tile_count (done on the host side with a device scan); write records in order
-__global__ void __launch_bounds__(PM_COMPACT_BLOCK) k_compact_write(const uint32_t* counts, uint64_t genome_size,
+// pass 2: tile_off = exclusive scan of tile_count (a device scan between the passes); write the window's records in order
+__global__ void __launch_bounds__(PM_COMPACT_BLOCK) k_compact_write(const uint32_t* counts, uint64_t site0, uint64_t n_sites,
                                                                     const unsigned long long* tile_off, PileRecord* out) {
   const uint64_t tile0 = (uint64_t)blockIdx.x * (PM_COMPACT_BLOCK * PM_COMPACT_ITEMS);
   __shared__ uint32_t warp_tot[PM_COMPACT_BLOCK / 32];
@@ -209,9 +210,9 @@ __global__ void __launch_bounds__(PM_COMPACT_BLOCK) k_compact_write(const uint32
     const uint64_t s = tile0 + (uint64_t)k * PM_COMPACT_BLOCK + threadIdx.x;
     uint32_t c6[6] = {0, 0, 0, 0, 0, 0};
     bool cov = false;
-    if (s < genome_size) {
+    if (s < n_sites) {
 #pragma unroll
-      for (int i = 0; i < 6; i++) c6[i] = counts[s * 6 + i];
+      for (int i = 0; i < 6; i++) c6[i] = counts[(site0 + s) * 6 + i];
       cov = site_covered(c6);
     }
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, cov);
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(PM_COMPACT_BLOCK) k_compact_write(const uint32
     for (int w = 0; w < warp; w++) base += warp_tot[w];
     if (cov) {
       PileRecord rec;
-      rec.pos = (uint32_t)s;
+      rec.pos = (uint32_t)(site0 + s);
 #pragma unroll
       for (int i = 0; i < 6; i++) rec.c[i] = (uint16_t)(c6[i] & 0xFFFFu);
       out[base + __popc(bal & ((1u << lane) - 1u))] = rec;

@@ -54,9 +54,11 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+SITE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)  # pemap_site_cb(ctx, records, n)
+
 EXPORTS = ["pemap_version", "pemap_default_params", "pemap_init", "pemap_init_from_genome", "pemap_set_params",
            "pemap_map_batch", "pemap_map_batch_rows", "pemap_map_batch_device", "pemap_keep", "pemap_get_detail",
-           "pemap_get_candidates", "pemap_finish", "pemap_reset_counts", "pemap_counts_device", "pemap_get_stats",
+           "pemap_get_candidates", "pemap_finish", "pemap_finish_stream", "pemap_get_insertions", "pemap_reset_counts", "pemap_counts_device", "pemap_get_stats",
            "pemap_reset_stats", "pemap_stream", "pemap_reduce_counts_peer", "pemap_index_device", "pemap_read_pos_index", "pemap_read_mers", "pemap_last_error",
            "pemap_destroy"]
 
@@ -90,6 +92,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.pemap_get_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int]
     L.pemap_finish.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.POINTER(Insertion)),
                                C.POINTER(C.c_uint64)]
+    L.pemap_finish_stream.argtypes = [vp, SITE_CB, vp, C.POINTER(C.c_uint64)]
+    L.pemap_get_insertions.argtypes = [vp, C.POINTER(C.POINTER(Insertion)), C.POINTER(C.c_uint64)]
     L.pemap_reset_counts.argtypes = [vp]
     L.pemap_counts_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.pemap_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -263,6 +267,24 @@ class PEMapper:
             records = np.zeros(0, dtype=RECORD_DTYPE)
         insertions = [(int(ins[i].pos), ins[i].seq.decode()) for i in range(nins.value)]
         return records, insertions
+
+    def finish_stream(self, consume=None):
+        """pemap_finish_stream: `consume(records)` is called with every window's RECORD_DTYPE view (valid only during
+        the call) in ascending position; returns the number of records.  consume=None only counts."""
+        def cb(_ctx, ptr, n):
+            if consume is not None:
+                buf = (C.c_char * (16 * n)).from_address(ptr)
+                consume(np.frombuffer(buf, dtype=RECORD_DTYPE))
+            return 0
+        total = C.c_uint64()
+        self._ck(self._L.pemap_finish_stream(self._h, SITE_CB(cb), None, C.byref(total)))
+        return total.value
+
+    def insertions(self):
+        ins = C.POINTER(Insertion)()
+        nins = C.c_uint64()
+        self._ck(self._L.pemap_get_insertions(self._h, C.byref(ins), C.byref(nins)))
+        return [(int(ins[i].pos), ins[i].seq.decode()) for i in range(nins.value)]
 
     def reset_counts(self):
         self._ck(self._L.pemap_reset_counts(self._h))

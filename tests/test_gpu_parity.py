@@ -249,6 +249,82 @@ def test_diagonal_certificate_changes_nothing(name, get_fixture, monkeypatch):
             assert out["1"][3] > 0, "the certificate never fired"
 
 
+@pytest.mark.parametrize("name", ["pe150", "repeat", "bis", "edge9"])
+def test_seed_index_layouts_agree(name, get_fixture, monkeypatch):
+    """The seed stage reads a device-private rotated bucket index (seed_rbi.cuh); PEMAP_SEED=legacy runs the round-1
+    kernel over pos_index / mers as the reference lays them out, and PEMAP_RBI_CAP=8 pushes nearly every read-mate
+    through the second (global-memory) pass of the new kernel.  Candidate lists in order, loci, types, pileup records
+    and insertions must be identical in all three."""
+    fx = get_fixture(name)
+    bis = int(getattr(fx, "bisulfite", False))
+    for run in fx.runs:
+        kw = dict(min_align=run.min_align, pair_flag=int(run.paired), min_dist=run.min_dist, max_dist=run.max_dist,
+                  is_bisulfite=int(run.bisulfite))
+        n = min(20000, run.reads1.shape[0])
+        out = {}
+        for mode in ("legacy", "rbi", "rbi-big"):
+            monkeypatch.setenv("PEMAP_SEED", "legacy" if mode == "legacy" else "rbi")
+            monkeypatch.setenv("PEMAP_RBI_CAP", "8" if mode == "rbi-big" else "512")
+            mapper = pb.PEMapper.from_genome(fx.genome, pb.default_params(is_bisulfite=bis))
+            mapper.set_params(**kw)
+            mapper.keep(pb.KEEP_CANDIDATES)
+            g = mapper.map_batch(run.reads1[:n], run.reads2[:n] if run.paired else None)
+            cands = [mapper.candidates(i, m) for i in range(0, n, 7) for m in range(2 if run.paired else 1)]
+            rec, ins = mapper.finish()
+            st = mapper.stats()
+            out[mode] = (g, cands, rec.tobytes(), sorted(ins), st["candidates"], st["mer_positions"])
+            mapper.close()
+        for mode in ("rbi", "rbi-big"):
+            tag = "%s/%s %s vs legacy" % (name, run.name, mode)
+            for x, y in zip(out["legacy"][0], out[mode][0]):
+                assert np.array_equal(x, y), tag + ": per-read results"
+            for (s0, o0), (s1, o1) in zip(out["legacy"][1], out[mode][1]):
+                assert np.array_equal(s0, s1) and np.array_equal(o0, o1), tag + ": candidate lists"
+            assert out["legacy"][2] == out[mode][2], tag + ": pileup records"
+            assert out["legacy"][3] == out[mode][3], tag + ": insertions"
+            assert out["legacy"][4] == out[mode][4], tag + ": candidate totals"
+
+
+def test_bounded_finish_and_insertion_spill(get_fixture, oracle_built, monkeypatch):
+    """pemap_finish_stream compacts the counters through bounded windows and the insertion append buffer spills to the
+    host when a chunk leaves it more than half full: with 4096-site windows, 32 KB of insertion buffer (a 1024-pair
+    chunk appends ~4 KB; the fill level is seen two chunks late because chunks are pipelined) and 1024-read chunks the records, the callback's windows and the insertion multiset equal the oracle's."""
+    fx = get_fixture("pe150")
+    run = fx.runs[0]
+    n = 20000
+    kw = dict(min_align=run.min_align, pair_flag=int(run.paired), min_dist=run.min_dist, max_dist=run.max_dist)
+    oracle = ol.Oracle(fx.genome)
+    oracle.set_params(**kw)
+    o = oracle.map_batch(run.reads1[:n], run.reads2[:n] if run.paired else None, nthreads=16)
+    orec, oins = oracle.records(), oracle.insertions()
+    assert len(oins) > 200
+    monkeypatch.setenv("PEMAP_FINISH_SITES", "4096")
+    monkeypatch.setenv("PEMAP_INS_BYTES", "32768")
+    monkeypatch.setenv("PEMAP_CHUNK", "1024")
+    mapper = pb.PEMapper.from_genome(fx.genome)
+    mapper.set_params(**kw)
+    g = mapper.map_batch(run.reads1[:n], run.reads2[:n] if run.paired else None)
+    for x, y in zip(o[:3], g):
+        assert np.array_equal(x, y)
+    parts = []
+    total = mapper.finish_stream(lambda r: parts.append(r.copy()))
+    assert total == orec.shape[0] and len(parts) > 10
+    assert np.concatenate(parts).tobytes() == orec.tobytes()
+    assert sorted(mapper.insertions()) == oins
+    rec, ins = mapper.finish()               # the collecting wrapper, again (counters are not cleared)
+    assert rec.tobytes() == orec.tobytes() and sorted(ins) == oins
+    mapper.close()
+    # an append buffer too small for ONE chunk fails that batch at once instead of at the end of the run
+    monkeypatch.setenv("PEMAP_INS_BYTES", "1024")
+    monkeypatch.setenv("PEMAP_CHUNK", "16384")
+    mapper = pb.PEMapper.from_genome(fx.genome)
+    mapper.set_params(**kw)
+    with pytest.raises(pb.PemapError):
+        mapper.map_batch(run.reads1[:n], run.reads2[:n] if run.paired else None)
+    mapper.close()
+    oracle.close()
+
+
 def _two_gpu_worker(rank, world, port, out_path):
     import os
     import torch
