@@ -1,17 +1,20 @@
 #!/usr/bin/env python
 """bench.py - mapped reads/s of the PEMapper hot path (seed lookup -> Smith-Waterman -> pileup) on N B200s.
 
-Workload (BASELINE.json configs[1]): synthetic 64 Mb single-contig genome, 10 M paired-end 150 bp reads with
-1 % substitutions and 0.1 % 1-3 bp insertions / deletions, insert U[250,450].  One "step" = one pass of the
-hot path over the 10 M pairs (20 M read-mates).  With N > 1 ranks the reads are sharded weakly (every rank
-maps its own 10 M pairs against its replica of the index) and the step ends with the NCCL sum of the per-GPU
-pileup counter arrays onto rank 0.
+Workload (default, BASELINE.json configs[2] = the north-star target): synthetic human-sized genome, 24 contigs with
+sizes proportional to chr1-22, X, Y totalling 3.1e9 bp, paired-end 150 bp reads with 1 % substitutions and 0.1 % 1-3 bp
+insertions / deletions, insert U[250,450].  One "step" = one pass of the hot path over 10 M pairs (20 M read-mates) per
+GPU.  `--config cfg2` runs BASELINE.json configs[1] (64 Mb single contig) instead.  With N > 1 ranks the reads are
+sharded weakly (every rank maps its own 10 M pairs against its replica of the index) and the step ends with the sum of
+the per-GPU pileup counter arrays onto rank 0 (NCCL over NVLink, chromosome by chromosome).
 
   value  reads/s with the reads already in HBM (pemap_map_batch_device), CUDA events on the library's stream
-  e2e    reads/s through pemap_map_batch_rows with pinned HOST buffers: H2D of the reads and D2H of m1/m2/type
-         inside the timed region
+  e2e    reads/s through the C-ABI with pinned HOST buffers: H2D of the reads, D2H of m1/m2/type AND one
+         pemap_finish_stream (bounded compaction + pinned D2H of every pileup record of the step) inside the timed
+         region, counters reset before every step
   --impl reference : the reference's own CPU implementation (oracle/_ref/libpemapper_ref.so = unmodified
-         pemapper.c built in-process; falls back to the oracle port) on the box's host cores, bounded sample.
+         pemapper.c built in-process; falls back to the oracle port) on all of the box's host threads, each step a
+         bounded sample (threads x 20,000 pairs, so that every worker thread holds a full batch).
 """
 import argparse
 import json
@@ -36,6 +39,14 @@ INSERT = (250, 450)
 MIN_ALIGN, MAX_DIST, MIN_DIST = 0.85, 500, 0
 ALG_BYTES_PER_READ_150 = 7840          # 2 strands x 10 segments x 49 k-mers x 8 B (pos_index words)
 INT_OPS_PER_CELL = 10
+REF_BATCH = 20_000                     # reads_per_thread of the reference (pemapper.c:158)
+CHR_MB = [248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
+
+CONFIGS = {
+    "cfg3": {"genome_seed": 30, "read_seed": 31, "total": float(os.environ.get("PEMAP_CFG3_BASES", 3.1e9)),
+             "text": "cfg3: %d contigs (sizes ~ human chr1-22,X,Y) totalling %.2e bp"},
+    "cfg2": {"genome_seed": 20, "read_seed": 21, "total": float(GENOME_LEN), "text": "cfg2: %d contig of %.2e bp"},
+}
 
 
 def env_int(k, d):
@@ -47,6 +58,67 @@ def env_int(k, d):
 def make_genome(seed, n):
     rng = np.random.Generator(np.random.PCG64(seed))
     return np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n, dtype=np.uint8)]
+
+
+def config_genome(name, device):
+    """-> (list of host contigs (uint8 arrays), the concatenated genome as a torch tensor on `device`).
+    cfg2 uses numpy's PCG64 stream (the tests' genome); cfg3's 3.1e9 bases come from torch's generator on `device`."""
+    import torch
+    cfg = CONFIGS[name]
+    if name == "cfg2":
+        g = make_genome(cfg["genome_seed"], int(cfg["total"]))
+        return [g], torch.from_numpy(g).to(device)
+    lens = [int(cfg["total"] * m / sum(CHR_MB)) for m in CHR_MB]
+    G = sum(lens)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(cfg["genome_seed"])
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    gt = torch.empty(G, dtype=torch.uint8, device=device)
+    step = 1 << 28
+    for lo in range(0, G, step):
+        m = min(step, G - lo)
+        gt[lo:lo + m] = acgt[torch.randint(0, 4, (m,), generator=gen, device=device)]
+    host = gt.cpu().numpy()
+    contigs, at = [], 0
+    for L in lens:
+        contigs.append(host[at:at + L])
+        at += L
+    return contigs, gt
+
+
+def workload_text(name, contigs, pairs):
+    cfg = CONFIGS[name]
+    return (cfg["text"] % (len(contigs), float(sum(int(c.shape[0]) for c in contigs))) +
+            ", %d paired-end 150 bp reads per GPU per step, 1%% subs + 0.1%% ins + 0.1%% del, insert U[250,450]" % pairs)
+
+
+def host_index(contigs, params, device_ok):
+    """The index as pemapper's main() holds it (pos_index[2^32+1], mers, contig_starts), for the CPU arm.  Built by the
+    device index builder when a GPU is there (bit-equal to index_genome_whole's files: tests/test_gpu_parity.py),
+    read back through a handle that holds nothing but the index (PEMAP_INDEX_ONLY=1); else by the oracle's indexer."""
+    lens = np.array([int(c.shape[0]) for c in contigs], dtype=np.int64)
+    cstarts = np.concatenate([[0], np.cumsum(lens - 15)]).astype(np.uint32)
+    if device_ok:
+        import pecaller_b200 as pb
+        os.environ["PEMAP_INDEX_ONLY"] = "1"
+        try:
+            m = pb.PEMapper.from_genome(contigs, params)
+        finally:
+            del os.environ["PEMAP_INDEX_ONLY"]
+        mers = np.concatenate([m.read_mers(), np.zeros(4, np.uint32)])
+        total = (1 << 32) + 1
+        pos_index = np.empty(total, dtype=np.uint32)
+        step = 1 << 30
+        for first in range(0, total, step):
+            k = min(step, total - first)
+            pos_index[first:first + k] = m.read_pos_index(first, k)
+        m.close()
+        return pos_index, mers, cstarts
+    import oracle_lib as ol
+    o = ol.Oracle(contigs, ol.default_params())
+    out = (o.dense_pos_index(), np.concatenate([o.mers(), np.zeros(4, np.uint32)]), o.contig_starts())
+    o.close()
+    return out
 
 
 def torch_reads(genome_t, n_pairs, seed, device, chunk=1_000_000):
@@ -146,29 +218,43 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ CPU arms
 
-def cpu_reference_run(genome, r1, r2, threads, steps, warmup, want_setup=True):
-    """Time the reference's own CPU implementation of the path on a bounded sample. -> (reads/s list, kind)"""
-    import oracle_lib as ol
-    oracle = ol.Oracle([genome], ol.default_params(min_align=MIN_ALIGN, pair_flag=1, min_dist=MIN_DIST, max_dist=MAX_DIST))
-    kind = "port"
-    ref = None
-    if ol.have_reference_lib() and os.environ.get("PEMAP_BENCH_PORT", "0") != "1":
-        try:
-            ref = ol.ReferenceLib(oracle, min_align=MIN_ALIGN, paired=True, min_dist=MIN_DIST, max_dist=MAX_DIST)
-            kind = "reference"
-        except Exception as e:  # e.g. not enough host RAM for the 16 GiB table
-            sys.stderr.write("reference library unusable (%s); timing the oracle port\n" % e)
-    rates = []
-    for it in range(warmup + steps):
-        t = time.perf_counter()
-        if ref is not None:
-            ref.map(r1, r2, nthreads=threads)
-        else:
-            oracle.map_batch(r1, r2, nthreads=threads)
-        dt = time.perf_counter() - t
-        if it >= warmup:
-            rates.append(2 * r1.shape[0] / dt)
-    return rates, kind
+class CpuArm:
+    """The reference's own CPU implementation of the path on a bounded sample: libpemapper_ref.so (the unmodified
+    pemapper.c, `kind` = "reference") when it was built, else the oracle port."""
+
+    def __init__(self, contigs, index_arrays, threads):
+        import oracle_lib as ol
+        self.threads = threads
+        self.kind = "port"
+        self.ref = None
+        self.oracle = None
+        if ol.have_reference_lib() and os.environ.get("PEMAP_BENCH_PORT", "0") != "1":
+            try:
+                pos_index, mers, cstarts = index_arrays()
+                cat = contigs[0] if len(contigs) == 1 else np.concatenate(contigs)
+                self.ref = ol.ReferenceLib(None, min_align=MIN_ALIGN, paired=True, min_dist=MIN_DIST, max_dist=MAX_DIST,
+                                           arrays=(cat, cstarts, pos_index, mers, len(contigs)))
+                self.kind = "reference"
+            except Exception as e:  # e.g. not enough host RAM for the 32 B x genome BASE_NODE array
+                sys.stderr.write("reference library unusable (%s); timing the oracle port\n" % e)
+        if self.ref is None:
+            self.oracle = ol.Oracle(contigs, ol.default_params(min_align=MIN_ALIGN, pair_flag=1, min_dist=MIN_DIST, max_dist=MAX_DIST))
+        self.live = 0
+
+    def run(self, r1, r2, steps, warmup):
+        rates = []
+        for it in range(warmup + steps):
+            t = time.perf_counter()
+            if self.ref is not None:
+                self.ref.map(r1, r2, nthreads=self.threads)
+                self.live = self.ref.live_threads()
+            else:
+                self.oracle.map_batch(r1, r2, nthreads=self.threads)
+                self.live = min(self.threads, (r1.shape[0] + REF_BATCH - 1) // REF_BATCH)
+            dt = time.perf_counter() - t
+            if it >= warmup:
+                rates.append(2 * r1.shape[0] / dt)
+        return rates
 
 
 def peaks():
@@ -195,8 +281,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=os.environ.get("PEMAP_BENCH_CONFIG", "cfg3"), choices=sorted(CONFIGS))
     ap.add_argument("--pairs", type=int, default=env_int("PEMAP_BENCH_PAIRS", PAIRS), help="pairs per rank per step")
-    ap.add_argument("--cpu-sample-pairs", type=int, default=env_int("PEMAP_BENCH_CPU_PAIRS", 100_000))
+    ap.add_argument("--cpu-sample-pairs", type=int, default=env_int("PEMAP_BENCH_CPU_PAIRS", 0),
+                    help="pairs per CPU step (default: host threads x 20,000 = one full batch per worker thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
@@ -205,31 +293,43 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     threads = os.cpu_count() or 1
+    cpu_pairs = a.cpu_sample_pairs or threads * REF_BATCH
+    cfg = CONFIGS[a.config]
+
+    import torch
 
     if a.impl == "reference":
         if rank != 0:
             return 0
-        genome = make_genome(20, GENOME_LEN)
-        import torch
-        gt = torch.from_numpy(genome)
-        n = a.cpu_sample_pairs
-        r1, r2 = torch_reads(gt, n, 21, "cpu", chunk=250_000)
-        r1, r2 = r1[:, :READ_LEN].numpy(), r2[:, :READ_LEN].numpy()
-        rates, kind = cpu_reference_run(genome, r1, r2, threads, a.steps, a.warmup)
+        import pecaller_b200 as pb
+        have_gpu = torch.cuda.is_available()
+        dev = torch.device("cuda", local) if have_gpu else torch.device("cpu")
+        contigs, gt = config_genome(a.config, dev)
+        r1, r2 = torch_reads(gt, cpu_pairs, cfg["read_seed"], dev, chunk=250_000)
+        r1, r2 = r1[:, :READ_LEN].cpu().numpy(), r2[:, :READ_LEN].cpu().numpy()
+        del gt
+        if have_gpu:
+            torch.cuda.empty_cache()
+        params = pb.default_params(min_align=MIN_ALIGN, pair_flag=1, min_dist=MIN_DIST, max_dist=MAX_DIST) if have_gpu else None
+        t0 = time.time()
+        arm = CpuArm(contigs, lambda: host_index(contigs, params, have_gpu), threads)
+        t_setup = time.time() - t0
+        rates = arm.run(r1, r2, a.steps, a.warmup)
         v = float(np.mean(rates))
+        sample = "%d pairs (%d read-mates) per step = one 20,000-read batch for each of %d worker threads (%d live)" % (
+            cpu_pairs, 2 * cpu_pairs, threads, arm.live)
         line = {"impl": "reference", "metric": "mapped reads/sec", "value": v, "unit": "reads/s", "n_gpus": a.gpus,
-                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * 2 * n / v, "higher_is_better": True,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * 2 * cpu_pairs / v, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "cfg2: %d Mb single-contig genome, %d paired-end 150 bp reads per GPU per step, "
-                                       "1%% subs + 0.1%% ins + 0.1%% del, insert U[250,450]" % (GENOME_LEN // 1000000, a.pairs),
-                           "sample": "each step maps the first %d pairs of that workload on %d host threads" % (n, threads)},
-                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": kind,
-                                 "sample": "%d pairs (%d read-mates) per step, %d threads" % (n, 2 * n, threads)},
+                "config": {"workload": workload_text(a.config, contigs, a.pairs),
+                           "sample": "each step maps the first %d pairs of that workload on %d host threads" % (cpu_pairs, threads),
+                           "setup_s": round(t_setup, 1)},
+                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "threads_live": arm.live, "kind": arm.kind,
+                                 "sample": sample},
                 "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return 0
 
-    import torch
     import torch.distributed as dist
     import pecaller_b200 as pb
     if not torch.cuda.is_available():
@@ -240,18 +340,24 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    genome = make_genome(20, GENOME_LEN)
     params = pb.default_params(min_align=MIN_ALIGN, pair_flag=1, min_dist=MIN_DIST, max_dist=MAX_DIST)
     t0 = time.time()
-    mapper = pb.PEMapper.from_genome([genome], params, device=local)
-    t_index = time.time() - t0
-    gt = torch.from_numpy(genome).to(dev)
+    contigs, gt = config_genome(a.config, dev)
+    t_genome = time.time() - t0
+    want_cpu = (not a.no_cpu_baseline) and world == 1
+    idx_host = None
+    if want_cpu:  # the CPU arm needs the index on the host: fetch it before the mapper fills the HBM
+        idx_host = host_index(contigs, params, True)
     n = a.pairs
     t0 = time.time()
-    d_r1, d_r2 = torch_reads(gt, n, 21 + rank, dev)
+    d_r1, d_r2 = torch_reads(gt, n, cfg["read_seed"] + rank, dev)
     torch.cuda.synchronize()
     t_gen = time.time() - t0
     del gt
+    torch.cuda.empty_cache()
+    t0 = time.time()
+    mapper = pb.PEMapper.from_genome(contigs, params, device=local)
+    t_index = time.time() - t0
     d_len = torch.full((n,), READ_LEN, dtype=torch.int32, device=dev)
     d_m1 = torch.zeros(n, dtype=torch.int32, device=dev)
     d_m2 = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -264,10 +370,11 @@ def main():
     h_m2 = torch.zeros(n, dtype=torch.int32).pin_memory()
     h_ty = torch.zeros(n, dtype=torch.int32).pin_memory()
     torch.cuda.synchronize()
+    free_b, total_b = torch.cuda.mem_get_info()
 
     lib_stream = torch.cuda.ExternalStream(mapper.stream_ptr(), device=dev)
     from pecaller_b200 import sharding
-    counts_t = sharding.counts_tensor(mapper, dev) if world > 1 else None  # torch view of the library's counter array
+    reducer = sharding.CountReducer(mapper, dev, contigs) if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -279,13 +386,18 @@ def main():
         mapper.map_device(n, d_r1.data_ptr(), d_len.data_ptr(), d_r2.data_ptr(), d_len.data_ptr(), STRIDE, READ_LEN,
                           d_m1.data_ptr(), d_m2.data_ptr(), d_ty.data_ptr())
         if world > 1:
-            sharding.reduce_counts(counts_t, dst=0)
+            reducer.reduce(dst=0)
+
+    fin = {"records": 0}
 
     def step_host():
+        mapper.reset_counts()
         mapper._ck(mapper._L.pemap_map_batch_rows(mapper._h, n, h_r1.data_ptr(), h_len.data_ptr(), h_r2.data_ptr(),
                                                   h_len.data_ptr(), STRIDE, h_m1.data_ptr(), h_m2.data_ptr(), h_ty.data_ptr()))
         if world > 1:
-            sharding.reduce_counts(counts_t, dst=0)
+            reducer.reduce(dst=0)
+        if rank == 0:  # the writer: every covered site of the step's pileup crosses to pinned host memory
+            fin["records"] = mapper.finish_stream(None)
 
     # ---- device-resident leg
     for _ in range(a.warmup):
@@ -309,14 +421,11 @@ def main():
         ms_dev = max(ms_dev, 1000.0 * wall_dev)
     stats = mapper.stats()
     clocks = sampler.stop()
-    # size-independent sanity at full size: counter mass == mapped bases (minus N/indel columns handled separately)
     mapped = int((d_m1 != 0).sum().item() + (d_m2 != 0).sum().item())
     types = torch.bincount(d_ty.long(), minlength=9).tolist()
 
-    # ---- end-to-end leg (host buffers, copies inside the timed region)
-    mapper.reset_counts()
+    # ---- end-to-end leg (host buffers, copies and the pileup hand-over inside the timed region)
     step_host()
-    mapper.reset_counts()
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
@@ -356,13 +465,15 @@ def main():
             return {"kernel": kernel, "bound": "alu", "achieved": g, "peak": peak, "unit": "GCUPS",
                     "frac": (g / peak) if peak else None, "traffic": None, "ms_per_step": 1000 * secs,
                     "peak_source": src if peak else "not measured"}
-        roof_seed = {"kernel": "k_seed_chain", "bound": "hbm", "achieved": seed_gbs, "peak": hbm_peak, "unit": "GB/s",
+        roof_seed = {"kernel": "k_seed_rbi", "bound": "hbm", "achieved": seed_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": seed_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "ms_per_step": 1000 * seed_s,
-                     "note": "algorithmic bytes (SURVEY 8d: 8 B per pos_index lookup + 4 B per position + packed read) over the "
-                             "stage time; random 8-byte gathers from HBM top out at %.1f G lookups/s = %.0f GB/s of algorithmic "
-                             "bytes on this part (profiles/gather_probe_r01.json), the L2-resident k-mer filter is how the "
-                             "kernel gets past that" % (ap_.get("random_gather_glookups_s", 41.7),
-                                                        8 * ap_.get("random_gather_glookups_s", 41.7))}
+                     "glookups_per_s": per_step["lookups"] / seed_s / 1e9,
+                     "note": "achieved = SURVEY 8d's ALGORITHMIC bytes (8 B per pos_index lookup of the reference's 49 per "
+                             "segment + 4 B per gathered position + packed read) over the stage time.  The kernel does not "
+                             "do those lookups one by one (isolated 8-byte gathers top out at 41.7 G/s = 334 GB/s of such "
+                             "bytes on this part, profiles/gather_probe_r01.json): it streams the four ~1 KB buckets of the "
+                             "rotated bucket index that hold a segment's 49 k-mers, so its DRAM traffic (`traffic`, ncu) "
+                             "is several times the algorithmic bytes by design and is what runs near the copy bandwidth."}
         roof_sw = alu_roof("k_sw_i16 (s16x2 DPX scoring of the candidates k_diag_certify could not settle)",
                            per_step["sw_cells_dp"], sw_s, pk16)
         roof_sw["note"] = ("cells computed by the DP only; %.1f %% of the candidates' cells were settled by the "
@@ -374,20 +485,22 @@ def main():
         dominant = max((roof_seed, roof_sw, roof_tbi, roof_tbf), key=lambda r: r["ms_per_step"])
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
-            trj = json.load(open(tr))
+            trj = json.load(open(tr)).get(a.config, {})
             for rf in (roof_seed, roof_sw, roof_tbi, roof_tbf):
                 rf["traffic"] = trj.get(rf["kernel"].split(" ")[0])
         line = {"metric": "mapped reads/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "s16x2 integer DP in units of 1/36 (fp64 only for rational ties)",
                 "data": "synthetic",
-                "config": {"workload": "cfg2: %d Mb single-contig genome, %d paired-end 150 bp reads per GPU per step, "
-                                       "1%% subs + 0.1%% ins + 0.1%% del, insert U[250,450]" % (GENOME_LEN // 1000000, n),
-                           "l2": "inputs (%.1f GB of reads per step) and the 16 GiB index exceed the 126 MB L2" % (2 * n * STRIDE / 1e9),
+                "config": {"workload": workload_text(a.config, contigs, n),
+                           "l2": "inputs (%.1f GB of reads per step) and the index exceed the 126 MB L2" % (2 * n * STRIDE / 1e9),
                            "parallelism": "reads sharded over %d GPU(s), index replicated, NCCL sum of pileup counters" % world,
-                           "index_build_s": round(t_index, 2), "datagen_s": round(t_gen, 2)},
+                           "index_build_s": round(t_index, 2), "datagen_s": round(t_gen + t_genome, 2),
+                           "hbm_used_gb": round((total_b - free_b) / 1e9, 1)},
                 "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": 2 * n * STRIDE + 2 * n * 4,
-                        "d2h_bytes_per_step": 3 * n * 4, "ms_per_step": ms_e2e / a.steps, "matches_device_leg": same},
+                        "d2h_bytes_per_step": 3 * n * 4 + 16 * fin["records"], "ms_per_step": ms_e2e / a.steps,
+                        "matches_device_leg": same, "pileup_records_per_step": fin["records"],
+                        "includes": "pemap_reset_counts + pemap_map_batch_rows (pinned rows) + pemap_finish_stream per step"},
                 "gpu_launches": int(stats["launches"]),
                 "clocks": clocks,
                 "roofline": dominant, "roofline_seed": roof_seed, "roofline_sw": roof_sw,
@@ -401,17 +514,21 @@ def main():
                 "tracebacks_per_step": {"pure_diagonal": stats["diag_traced"] / a.steps,
                                         "fp64_after_tie": stats["exact_traced"] / a.steps,
                                         "replayed_read_mates": stats["replayed"] / a.steps}}
-        if not a.no_cpu_baseline and world == 1:
-            ns = a.cpu_sample_pairs
-            r1 = h_r1[:ns, :READ_LEN].numpy()
-            r2 = h_r2[:ns, :READ_LEN].numpy()
-            rates, kind = cpu_reference_run(genome, r1, r2, threads, 1, 0)
-            line["cpu_baseline"] = {"value": rates[0], "unit": "reads/s", "cores": threads, "kind": kind,
-                                    "sample": "first %d pairs (%d read-mates) of the same workload, %d threads, 1 pass" % (ns, 2 * ns, threads)}
-        print(json.dumps(line), flush=True)
+    r1 = h_r1[:cpu_pairs, :READ_LEN].numpy().copy() if want_cpu else None
+    r2 = h_r2[:cpu_pairs, :READ_LEN].numpy().copy() if want_cpu else None
     mapper.close()
+    del h_r1, h_r2, d_r1, d_r2
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0:
+        if want_cpu:  # after the GPU legs and with their buffers released: the reference wants 32 B per genome base
+            arm = CpuArm(contigs, lambda: idx_host, threads)
+            rates = arm.run(r1, r2, 1, 0)
+            line["cpu_baseline"] = {"value": rates[0], "unit": "reads/s", "cores": threads, "threads_live": arm.live,
+                                    "kind": arm.kind,
+                                    "sample": "first %d pairs (%d read-mates) of the same workload = one 20,000-read batch "
+                                              "for each of %d worker threads, 1 pass" % (cpu_pairs, 2 * cpu_pairs, threads)}
+        print(json.dumps(line), flush=True)
     return 0
 
 

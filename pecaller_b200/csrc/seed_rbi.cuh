@@ -157,11 +157,9 @@ struct SeedRbiArgs {
 #define PM_RBI_BIG_BYTES ((size_t)PM_RBI_BIG_CAP * 10 + (size_t)PM_RBI_BIG_TAB * 4)
 
 struct RbiWarpSmem {           // per warp, both paths
-  uint32_t b_off[PM_RBI_MAXB];       // bucket start (16-byte units)
-  uint32_t b_pre[PM_RBI_MAXB + 1];   // prefix sum of the buckets' position quads
-  uint32_t b_meta[PM_RBI_MAXB];      // segment | rotation << 8 | exact tag << 16
+  uint32_t b_off[2 * PM_RBI_MAXB];   // bucket start (16-byte units), both strands: [4 * (strand * nseg + segment) + rotation]
+  uint32_t b_n4[2 * PM_RBI_MAXB];    // its position quads
   uint32_t kcode[2 * PM_MAX_SEG];
-  uint32_t segcnt[PM_MAX_SEG];
   uint32_t hit_pos[PM_MAX_HITS];
   uint16_t hit_off[PM_MAX_HITS];
   uint8_t hit_or[PM_MAX_HITS];
@@ -275,127 +273,106 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
     const int max_depth = total_cuts;
     const int mo = (a.p.idepth - 4 > 2) ? a.p.idepth - 4 : 2;  // max_off (2196)
     const int nb = 4 * nseg;
+    // ---- bucket directory: four buckets per (strand, segment), all 8 * nseg look-ups in one go
+    for (int b = lane; b < 2 * nb; b += 32) {
+      const int g = b & 3;
+      const uint32_t code = sm.kcode[b >> 2];
+      const uint32_t bk = rbi_bucket(code, g);
+      const uint32_t d0 = __ldg(a.ix.dir[g] + bk), d1 = __ldg(a.ix.dir[g] + bk + 1);
+      const uint32_t S = d1 - d0;
+      sm.b_off[b] = d0;
+      sm.b_n4[b] = S - (S + 4u) / 5u;
+    }
+    __syncwarp();
+    // lanes 8g..8g+7 read the bucket of rotation g
+    const int rot = lane >> 3, l8 = lane & 7;
+    const uint4* const rdata = a.ix.data[rot];
+    const uint32_t keep_exact = rot == 0 ? 0x80808080u : 0u;  // the exact k-mer sits in all four buckets: rotation 0 takes it
 
     for (int strand = 0; strand < 2; strand++) {
       if (strand == 1 && tot >= a.p.max_hits) break;  // 1658
-      // ---- bucket directory: four buckets per segment
-      uint32_t carry = 0;
-      if (lane == 0) sm.b_pre[0] = 0;
-      for (int b0 = 0; b0 < nb; b0 += 32) {
-        const int b = b0 + lane;
-        uint32_t n4 = 0;
-        if (b < nb) {
-          const int s = b >> 2, g = b & 3;
-          const uint32_t code = sm.kcode[strand * nseg + s];
-          const uint32_t bk = rbi_bucket(code, g);
-          const uint32_t d0 = __ldg(a.ix.dir[g] + bk), d1 = __ldg(a.ix.dir[g] + bk + 1);
-          const uint32_t S = d1 - d0;
-          n4 = S - (S + 4u) / 5u;
-          sm.b_off[b] = d0;
-          sm.b_meta[b] = (uint32_t)s | ((uint32_t)g << 8) | (rbi_tag(code, g) << 16);
-        }
-        uint32_t inc = n4;  // inclusive warp scan
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-          if (lane >= o) inc += t;
-        }
-        if (b < nb) sm.b_pre[b + 1] = carry + inc;
-        carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
-      }
-      __syncwarp();
-      const uint32_t Q = carry;  // position quads of the strand's buckets
-
-      // ---- gather (get_mers 2158-2165, loop 1594-1612 / 1619-1637): every entry whose tag is the segment's tag or one
-      // 2-bit field away from it; the exact k-mer sits in all four of its buckets and is taken from rotation 0
-      int cnt = 0;           // warp-uniform
-      uint32_t vmask = 0;    // segments with a crowded k-mer (per lane, OR-reduced below)
+      // ---- gather (get_mers 2158-2165, loop 1594-1612 / 1619-1637): per segment, every entry of its four buckets whose
+      // tag is the segment's tag or one 2-bit field away from it
+      int cnt = 0;              // warp-uniform
+      uint32_t min_spots = 10000;
       bool overflow = false;
-      int cur = 0;           // per-lane bucket cursor: flat quad indices only grow
-      for (uint32_t f0 = 0; f0 < Q; f0 += 32 * PM_RBI_UNROLL) {
-        uint4 P[PM_RBI_UNROLL];
-        uint32_t T[PM_RBI_UNROLL], M[PM_RBI_UNROLL];
+      for (int s = 0; s < nseg; s++) {
+        const int b = 4 * (strand * nseg + s) + rot;
+        const uint32_t n4 = sm.b_n4[b];
+        const uint4* base = rdata + sm.b_off[b];
+        const uint32_t* tags = reinterpret_cast<const uint32_t*>(base + n4);
+        const uint32_t etagx = ((sm.kcode[strand * nseg + s] >> (8 * rot)) & 255u) * 0x01010101u;
+        const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, n4);
+        const int cnt0 = cnt;
+        bool crowded = false;
+        for (uint32_t q0 = 0; q0 < nmax; q0 += 8 * PM_RBI_UNROLL) {
+          uint4 P[PM_RBI_UNROLL];
+          uint32_t T[PM_RBI_UNROLL];
 #pragma unroll
-        for (int u = 0; u < PM_RBI_UNROLL; u++) {
-          const uint32_t f = f0 + (uint32_t)(u * 32 + lane);
-          P[u] = make_uint4(PM_RBI_EMPTY, PM_RBI_EMPTY, PM_RBI_EMPTY, PM_RBI_EMPTY);
-          T[u] = 0;
-          M[u] = 0;
-          if (f < Q) {
-            while (f >= sm.b_pre[cur + 1]) cur++;
-            const uint32_t q = f - sm.b_pre[cur], n4 = sm.b_pre[cur + 1] - sm.b_pre[cur];
-            const uint32_t meta = sm.b_meta[cur];
-            const uint4* base = a.ix.data[(meta >> 8) & 3u] + sm.b_off[cur];
-            P[u] = rbi_ld16(base + q);
-            T[u] = rbi_ld4(reinterpret_cast<const uint32_t*>(base + n4) + q);
-            M[u] = meta;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < PM_RBI_UNROLL; u++) {
-          // per tag byte: fields that differ from the exact tag; a byte qualifies when at most one field differs
-          const uint32_t X = T[u] ^ ((M[u] >> 16) * 0x01010101u);
-          const uint32_t D = (X | (X >> 1)) & 0x55555555u;
-          const uint32_t Z = D & ((D | 0x80808080u) - 0x01010101u);            // byte == 0 <=> <= 1 field differs
-          uint32_t hit = ((Z + 0x7F7F7F7Fu) & 0x80808080u) ^ 0x80808080u;      // bit 7 of byte k: tag k qualifies
-          if (((M[u] >> 8) & 3u) != 0u) {                                        // rotations 1..3 skip the exact k-mer
-            const uint32_t nz = ((D + 0x7F7F7F7Fu) & 0x80808080u);              // bit 7 of byte k: tag differs
-            hit &= nz;
-          }
-          const uint32_t pv[4] = {P[u].x, P[u].y, P[u].z, P[u].w};
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            bool take = ((hit >> (8 * k + 7)) & 1u) && pv[k] != PM_RBI_EMPTY;
-            if (take && pv[k] == PM_RBI_MARK) {
-              vmask |= 1u << (M[u] & 31u);
-              take = false;
+          for (int u = 0; u < PM_RBI_UNROLL; u++) {
+            const uint32_t q = q0 + (uint32_t)(8 * u + l8);
+            T[u] = etagx ^ 0x0F0F0F0Fu;  // two fields away: never qualifies
+            P[u] = make_uint4(PM_RBI_EMPTY, PM_RBI_EMPTY, PM_RBI_EMPTY, PM_RBI_EMPTY);
+            if (q < n4) {
+              P[u] = rbi_ld16(base + q);
+              T[u] = rbi_ld4(tags + q);
             }
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, take);
-            if (bal) {
-              const int at = cnt + __popc(bal & ((1u << lane) - 1u));
+          }
+#pragma unroll
+          for (int u = 0; u < PM_RBI_UNROLL; u++) {
+            if (q0 + 8u * (uint32_t)u >= nmax) break;  // warp-uniform
+            // per tag byte: fields that differ from the exact tag; a byte qualifies when at most one field differs
+            const uint32_t X = T[u] ^ etagx;
+            const uint32_t D = (X | (X >> 1)) & 0x55555555u;
+            const uint32_t Z = D & ((D | 0x80808080u) - 0x01010101u);             // byte == 0 <=> <= 1 field differs
+            uint32_t hit = ((Z + 0x7F7F7F7Fu) & 0x80808080u) ^ 0x80808080u;       // bit 7 of byte k: tag k qualifies
+            hit &= ((D + 0x7F7F7F7Fu) & 0x80808080u) | keep_exact;                 // ... and it is not the exact tag (rot > 0)
+            // the qualifying entries of the 32 lanes, one per lane and round (a quad rarely holds two)
+            while (true) {
+              uint32_t pos = PM_RBI_EMPTY;
+              if (hit) {
+                const uint32_t low = hit & (0u - hit);
+                pos = low == 0x80u ? P[u].x : low == 0x8000u ? P[u].y : low == 0x800000u ? P[u].z : P[u].w;
+                hit ^= low;
+              }
+              crowded |= pos == PM_RBI_MARK;
+              const bool take = pos < PM_RBI_MARK;
+              const unsigned bal = __ballot_sync(0xFFFFFFFFu, take);
               if (take) {
+                const int at = cnt + __popc(bal & ((1u << lane) - 1u));
                 if (at < cap) {
-                  st_pos[at] = pv[k];
-                  st_seg[at] = (uint8_t)(M[u] & 255u);
+                  st_pos[at] = pos;
+                  st_seg[at] = (uint8_t)s;
                 } else {
                   overflow = true;
                 }
               }
               cnt += __popc(bal);
+              if (!__any_sync(0xFFFFFFFFu, hit != 0u)) break;
             }
           }
         }
+        if (__any_sync(0xFFFFFFFFu, crowded)) cnt = cnt0;  // 1602-1606: one crowded k-mer empties the segment's list
+        if (cnt > cap) cnt = cap;                          // (overflow is reported below; keep the stores in range)
+        min_spots = min(min_spots, (uint32_t)(cnt - cnt0));
       }
       if (__any_sync(0xFFFFFFFFu, overflow)) {
-        if (!BIG) return false;
-        cnt = cap;  // cannot happen: the BIG stores hold 19 * 49 * 99 entries
+        if (!BIG) return false;  // the BIG stores hold 19 * 49 * 99 entries
       }
-      vmask = __reduce_or_sync(0xFFFFFFFFu, vmask);
       const int N = cnt;
       l_pos += (unsigned long long)N;
       __syncwarp();
-
       // ---- 2200-2207: every segment list longer than max_hits -> no hits at all (also wipes the other strand's)
-      if (N > a.p.max_hits) {  // otherwise some segment has <= max_hits positions
-        for (int s = lane; s < nseg; s += 32) sm.segcnt[s] = 0;
-        __syncwarp();
-        for (int e = lane; e < N; e += 32) atomicAdd(&sm.segcnt[st_seg[e]], 1u);
-        __syncwarp();
-        uint32_t ms = 10000;
-        for (int s = lane; s < nseg; s += 32) ms = min(ms, ((vmask >> s) & 1u) ? 0u : sm.segcnt[s]);
-        ms = __reduce_min_sync(0xFFFFFFFFu, ms);
-        if (ms > (uint32_t)a.p.max_hits) {
-          tot = 0;
-          continue;
-        }
+      if (min_spots > (uint32_t)a.p.max_hits) {
+        tot = 0;
+        continue;
       }
 
-      // ---- hash the entries by diagonal / 16 (vetoed segments have no list: 1602-1606)
+      // ---- hash the entries by diagonal / 16
       for (uint32_t i = lane; i <= tab_mask; i += 32) st_head[i] = 0xFFFFFFFFu;
       __syncwarp();
       for (int e = lane; e < N; e += 32) {
         const int s = st_seg[e];
-        if ((vmask >> s) & 1u) continue;
         const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
         const uint32_t bin = (uint32_t)(((unsigned long long)st_pos[e] + 512ull - off) >> 4);
         const uint32_t old = atomicExch(&st_head[rbi_hash(bin, tab_mask)], (uint32_t)e);
@@ -404,10 +381,11 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
       __syncwarp();
       // ---- found count of every entry as an anchor (2230-2249): later segments with a position whose diagonal is
       // within max_off - 1 of the anchor's
+      bool relevant = false;  // some anchor reaches the running min_match
       for (int e = lane; e < N; e += 32) {
         const int s = st_seg[e];
         int fnd = 0;
-        if (!((vmask >> s) & 1u) && 1 + max_depth - s >= min_match) {  // an anchor of segment s reaches at most 1 + max_depth - s
+        if (1 + max_depth - s >= min_match) {  // an anchor of segment s reaches at most 1 + max_depth - s
           const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
           const long long dg = (long long)st_pos[e] + 512ll - (long long)off;
           const uint32_t bin = (uint32_t)(dg >> 4);
@@ -429,8 +407,10 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
           fnd = 1 + __popc(segs);
         }
         st_found[e] = (uint8_t)fnd;
+        relevant |= fnd >= min_match;
       }
       __syncwarp();
+      if (!__any_sync(0xFFFFFFFFu, relevant)) continue;  // the usual fate of the strand the read does not come from
 
       // ---- the reference's sequential rules over the anchors that can still matter, in its order: segment, position
       bool done = false;

@@ -226,7 +226,11 @@ class ReferenceLib:
     """One per process (the reference keeps its state in file-static globals)."""
     _inst = None
 
-    def __init__(self, oracle: Oracle, min_align=0.9, bisulfite=False, paired=False, min_dist=0, max_dist=500):
+    def __init__(self, oracle: Oracle | None, min_align=0.9, bisulfite=False, paired=False, min_dist=0, max_dist=500,
+                 arrays=None):
+        """arrays = (genome_cat, contig_starts, pos_index[2^32+1], mers, n_contigs): an index built elsewhere (the
+        device index builder, bit-equal to index_genome_whole's files) instead of the oracle's CPU indexer - the
+        only practical way to a 3.1 Gb genome."""
         assert ReferenceLib._inst is None, "the reference library can be initialised once per process"
         ReferenceLib._inst = self
         R = C.CDLL(REF_SO)
@@ -246,11 +250,18 @@ class ReferenceLib:
         R.refw_sw_align.argtypes = [C.c_uint, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
         for f in ("refw_mate_count", "refw_total_reads", "refw_total_bases", "refw_total_dist", "refw_no_dists"):
             getattr(R, f).restype = C.c_long
-        self.genome = np.concatenate(oracle.genome)
-        self.cstarts = oracle.contig_starts()
-        self.pos_index = oracle.dense_pos_index()
-        self.mers = np.concatenate([oracle.mers(), np.zeros(4, np.uint32)])
-        rc = R.refw_init(self.genome.ctypes.data, self.genome.shape[0], self.cstarts.ctypes.data, oracle.n_contigs,
+        R.refw_last_live_threads.restype = C.c_int
+        if arrays is not None:
+            self.genome, self.cstarts, self.pos_index, self.mers, n_contigs = arrays
+            assert self.pos_index.dtype == np.uint32 and self.pos_index.shape[0] == (1 << 32) + 1
+            assert self.mers.dtype == np.uint32 and self.cstarts.dtype == np.uint32
+        else:
+            self.genome = np.concatenate(oracle.genome)
+            self.cstarts = oracle.contig_starts()
+            self.pos_index = oracle.dense_pos_index()
+            self.mers = np.concatenate([oracle.mers(), np.zeros(4, np.uint32)])
+            n_contigs = oracle.n_contigs
+        rc = R.refw_init(self.genome.ctypes.data, self.genome.shape[0], self.cstarts.ctypes.data, n_contigs,
                          self.pos_index.ctypes.data, self.mers.ctypes.data, min_align, int(bisulfite), int(paired),
                          min_dist, max_dist)
         assert rc == 0
@@ -272,6 +283,10 @@ class ReferenceLib:
                              ty.ctypes.data, nthreads)
         assert rc == 0
         return m1, m2, ty
+
+    def live_threads(self):
+        """worker threads that had a batch in the widest wave of the last map() call"""
+        return self.R.refw_last_live_threads()
 
     def records(self):
         n = self.R.refw_records(None, 0)

@@ -68,7 +68,12 @@ def _worker(rank, world, port, out_path):
     ty = np.concatenate([p[2] for p in parts])
     counts = torch.from_numpy(_dense_counts(oracle).reshape(-1))
     counts += (1 << 16) * (rank + 1)      # every rank's array is shifted by a multiple of 2^16: must vanish
-    sharding.reduce_counts(counts, dst=0)
+    # chromosome by chromosome, as bench.py and the 8-GPU runs do it (the tiny genome is one contig: cut it in three)
+    gs = counts.shape[0] // 6
+    bounds = sharding.contig_word_bounds([gs // 3, gs // 3, gs - 2 * (gs // 3)])
+    assert bounds[0][0] == 0 and bounds[-1][1] == counts.shape[0]
+    for w in sharding.reduce_counts_by_contig(counts, bounds, dst=0):
+        w.wait()
     res = sharding.gather_results(n, ranges, m1, m2, ty, dst=0)
     if rank == 0:
         rec = sharding.records_from_counts(counts.numpy())
