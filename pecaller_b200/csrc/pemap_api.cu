@@ -253,9 +253,15 @@ int open_device(pemap_ctx* h, int device) {
   if (prop.major < 10) return fail(h, PEMAP_ERR_CUDA, "device is not sm_100 (this library has only sm_100a code)");
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
-  // random 8-byte gathers into the 16 GiB table: ask for sector-sized (32 B) DRAM fetches instead of the default
-  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-  cudaGetLastError();
+  // legacy seed kernel: random 8-byte gathers into the 16 GiB table want sector-sized (32 B) DRAM fetches; the rotated
+  // bucket index is read as contiguous ~1 KB buckets, 128-byte pieces at a time: whole lines (PEMAP_L2_FETCH overrides)
+  {
+    size_t gran = 128;
+    if (const char* s = getenv("PEMAP_SEED")) gran = strcmp(s, "legacy") == 0 ? 32 : 128;
+    if (const char* s = getenv("PEMAP_L2_FETCH")) gran = (size_t)atoi(s);
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    cudaGetLastError();
+  }
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));

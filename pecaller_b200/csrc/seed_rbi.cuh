@@ -37,6 +37,7 @@
 #ifndef PM_RBI_UNROLL
 #define PM_RBI_UNROLL 4
 #endif
+#define PM_RBI_QUEUE 8                  // per-lane queue of qualifying positions between two appends (a quad adds <= 4)
 
 namespace pm {
 
@@ -305,6 +306,33 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
         const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, n4);
         const int cnt0 = cnt;
         bool crowded = false;
+        // qualifying positions wait in a per-lane queue (a segment leaves ~1 per lane) and are appended to the strand's
+        // list with one warp scan per segment, so that the scan of a quad carries no warp-wide dependency
+        uint32_t mq[PM_RBI_QUEUE];
+        int mc = 0;
+#pragma unroll
+        for (int i = 0; i < PM_RBI_QUEUE; i++) mq[i] = 0;
+        auto flush = [&]() {
+          int inc = mc;  // inclusive scan of the queue lengths
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += t;
+          }
+          const int at = cnt + inc - mc;
+#pragma unroll
+          for (int i = 0; i < PM_RBI_QUEUE; i++)
+            if (i < mc) {
+              if (at + i < cap) {
+                st_pos[at + i] = mq[i];
+                st_seg[at + i] = (uint8_t)s;
+              } else {
+                overflow = true;
+              }
+            }
+          cnt += __shfl_sync(0xFFFFFFFFu, inc, 31);
+          mc = 0;
+        };
         for (uint32_t q0 = 0; q0 < nmax; q0 += 8 * PM_RBI_UNROLL) {
           uint4 P[PM_RBI_UNROLL];
           uint32_t T[PM_RBI_UNROLL];
@@ -320,38 +348,29 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
           }
 #pragma unroll
           for (int u = 0; u < PM_RBI_UNROLL; u++) {
-            if (q0 + 8u * (uint32_t)u >= nmax) break;  // warp-uniform
+            if (__any_sync(0xFFFFFFFFu, mc > PM_RBI_QUEUE - 4)) flush();  // room for the four entries of a quad
             // per tag byte: fields that differ from the exact tag; a byte qualifies when at most one field differs
             const uint32_t X = T[u] ^ etagx;
             const uint32_t D = (X | (X >> 1)) & 0x55555555u;
             const uint32_t Z = D & ((D | 0x80808080u) - 0x01010101u);             // byte == 0 <=> <= 1 field differs
             uint32_t hit = ((Z + 0x7F7F7F7Fu) & 0x80808080u) ^ 0x80808080u;       // bit 7 of byte k: tag k qualifies
             hit &= ((D + 0x7F7F7F7Fu) & 0x80808080u) | keep_exact;                 // ... and it is not the exact tag (rot > 0)
-            // the qualifying entries of the 32 lanes, one per lane and round (a quad rarely holds two)
-            while (true) {
-              uint32_t pos = PM_RBI_EMPTY;
-              if (hit) {
-                const uint32_t low = hit & (0u - hit);
-                pos = low == 0x80u ? P[u].x : low == 0x8000u ? P[u].y : low == 0x800000u ? P[u].z : P[u].w;
-                hit ^= low;
+            while (hit) {  // ~5 % of the entries
+              const uint32_t low = hit & (0u - hit);
+              const uint32_t pos = low == 0x80u ? P[u].x : low == 0x8000u ? P[u].y : low == 0x800000u ? P[u].z : P[u].w;
+              hit ^= low;
+              if (pos < PM_RBI_MARK) {
+#pragma unroll
+                for (int i = PM_RBI_QUEUE - 1; i > 0; i--) mq[i] = mq[i - 1];
+                mq[0] = pos;
+                mc++;
+              } else {
+                crowded |= pos == PM_RBI_MARK;
               }
-              crowded |= pos == PM_RBI_MARK;
-              const bool take = pos < PM_RBI_MARK;
-              const unsigned bal = __ballot_sync(0xFFFFFFFFu, take);
-              if (take) {
-                const int at = cnt + __popc(bal & ((1u << lane) - 1u));
-                if (at < cap) {
-                  st_pos[at] = pos;
-                  st_seg[at] = (uint8_t)s;
-                } else {
-                  overflow = true;
-                }
-              }
-              cnt += __popc(bal);
-              if (!__any_sync(0xFFFFFFFFu, hit != 0u)) break;
             }
           }
         }
+        flush();
         if (__any_sync(0xFFFFFFFFu, crowded)) cnt = cnt0;  // 1602-1606: one crowded k-mer empties the segment's list
         if (cnt > cap) cnt = cap;                          // (overflow is reported below; keep the stores in range)
         min_spots = min(min_spots, (uint32_t)(cnt - cnt0));
@@ -368,19 +387,34 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
         continue;
       }
 
-      // ---- hash the entries by diagonal / 16
-      for (uint32_t i = lane; i <= tab_mask; i += 32) st_head[i] = 0xFFFFFFFFu;
+      // ---- hash the entries by diagonal / 16.  Fast path: a slot word holds the chain head (bits 0-9, 0x3FF = none)
+      // and the set of segments hashed into the slot (bit 13 + segment); BIG: the head index alone.
+      constexpr uint32_t HNIL = BIG ? 0xFFFFFFFFu : 0x3FFu;
+      for (uint32_t i = lane; i <= tab_mask; i += 32) st_head[i] = HNIL;
       __syncwarp();
       for (int e = lane; e < N; e += 32) {
         const int s = st_seg[e];
         const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
         const uint32_t bin = (uint32_t)(((unsigned long long)st_pos[e] + 512ull - off) >> 4);
-        const uint32_t old = atomicExch(&st_head[rbi_hash(bin, tab_mask)], (uint32_t)e);
-        st_next[e] = old == 0xFFFFFFFFu ? NIL : (NextT)old;
+        uint32_t* hp = &st_head[rbi_hash(bin, tab_mask)];
+        uint32_t old;
+        if (BIG) {
+          old = atomicExch(hp, (uint32_t)e);
+        } else {
+          old = *hp;
+          uint32_t assumed;
+          do {
+            assumed = old;
+            old = atomicCAS(hp, assumed, (assumed & 0xFFFFE000u) | (1u << (13 + s)) | (uint32_t)e);
+          } while (old != assumed);
+          old &= 0x3FFu;
+        }
+        st_next[e] = old == HNIL ? NIL : (NextT)old;
       }
       __syncwarp();
       // ---- found count of every entry as an anchor (2230-2249): later segments with a position whose diagonal is
-      // within max_off - 1 of the anchor's
+      // within max_off - 1 of the anchor's.  The segments present in the three slots around the anchor bound it from
+      // above; only anchors whose bound reaches min_match (the read's true locus, rarely a chance cluster) walk the chains.
       bool relevant = false;  // some anchor reaches the running min_match
       for (int e = lane; e < N; e += 32) {
         const int s = st_seg[e];
@@ -389,22 +423,32 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
           const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
           const long long dg = (long long)st_pos[e] + 512ll - (long long)off;
           const uint32_t bin = (uint32_t)(dg >> 4);
-          uint32_t segs = 0;
+          uint32_t hw[3];
 #pragma unroll
-          for (int db = -1; db <= 1; db++) {
-            uint32_t q = st_head[rbi_hash(bin + (uint32_t)db, tab_mask)];
-            while (q != 0xFFFFFFFFu) {
-              const int sq = st_seg[q];
-              if (sq > s) {
-                const uint32_t offq = (sq < total_cuts) ? 16u * (uint32_t)sq : (uint32_t)(len - 16);
-                const long long d = (long long)st_pos[q] + 512ll - (long long)offq - dg;
-                if (d > -(long long)mo && d < (long long)mo) segs |= 1u << sq;  // 2244
-              }
-              const NextT nx = st_next[q];
-              q = nx == NIL ? 0xFFFFFFFFu : (uint32_t)nx;
-            }
+          for (int db = 0; db < 3; db++) hw[db] = st_head[rbi_hash(bin + (uint32_t)(db - 1), tab_mask)];
+          bool walk = true;
+          if (!BIG) {
+            const uint32_t later = ~((2u << s) - 1u);
+            walk = 1 + __popc(((hw[0] | hw[1] | hw[2]) >> 13) & later) >= min_match;
           }
-          fnd = 1 + __popc(segs);
+          if (walk) {
+            uint32_t segs = 0;
+#pragma unroll
+            for (int db = 0; db < 3; db++) {
+              uint32_t q = BIG ? hw[db] : (hw[db] & 0x3FFu);
+              while (q != HNIL) {
+                const int sq = st_seg[q];
+                if (sq > s) {
+                  const uint32_t offq = (sq < total_cuts) ? 16u * (uint32_t)sq : (uint32_t)(len - 16);
+                  const long long d = (long long)st_pos[q] + 512ll - (long long)offq - dg;
+                  if (d > -(long long)mo && d < (long long)mo) segs |= 1u << sq;  // 2244
+                }
+                const NextT nx = st_next[q];
+                q = nx == NIL ? HNIL : (uint32_t)nx;
+              }
+            }
+            fnd = 1 + __popc(segs);
+          }
         }
         st_found[e] = (uint8_t)fnd;
         relevant |= fnd >= min_match;
