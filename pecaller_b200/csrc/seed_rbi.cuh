@@ -37,7 +37,6 @@
 #ifndef PM_RBI_UNROLL
 #define PM_RBI_UNROLL 4
 #endif
-#define PM_RBI_QUEUE 8                  // per-lane queue of qualifying positions between two appends (a quad adds <= 4)
 
 namespace pm {
 
@@ -161,6 +160,9 @@ struct RbiWarpSmem {           // per warp, both paths
   uint32_t b_off[2 * PM_RBI_MAXB];   // bucket start (16-byte units), both strands: [4 * (strand * nseg + segment) + rotation]
   uint32_t b_n4[2 * PM_RBI_MAXB];    // its position quads
   uint32_t kcode[2 * PM_MAX_SEG];
+  uint32_t n_ent;                    // entries of the strand gathered so far (appended to by the lanes that hold a match)
+  uint32_t pad_[3];
+  uint32_t pend[64];                 // anchors waiting for their exact found count
   uint32_t hit_pos[PM_MAX_HITS];
   uint16_t hit_off[PM_MAX_HITS];
   uint8_t hit_or[PM_MAX_HITS];
@@ -294,9 +296,11 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
       if (strand == 1 && tot >= a.p.max_hits) break;  // 1658
       // ---- gather (get_mers 2158-2165, loop 1594-1612 / 1619-1637): per segment, every entry of its four buckets whose
       // tag is the segment's tag or one 2-bit field away from it
-      int cnt = 0;              // warp-uniform
+      int cnt = 0;              // warp-uniform copy of sm.n_ent between segments
       uint32_t min_spots = 10000;
       bool overflow = false;
+      if (lane == 0) sm.n_ent = 0;
+      __syncwarp();
       for (int s = 0; s < nseg; s++) {
         const int b = 4 * (strand * nseg + s) + rot;
         const uint32_t n4 = sm.b_n4[b];
@@ -305,34 +309,6 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
         const uint32_t etagx = ((sm.kcode[strand * nseg + s] >> (8 * rot)) & 255u) * 0x01010101u;
         const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, n4);
         const int cnt0 = cnt;
-        bool crowded = false;
-        // qualifying positions wait in a per-lane queue (a segment leaves ~1 per lane) and are appended to the strand's
-        // list with one warp scan per segment, so that the scan of a quad carries no warp-wide dependency
-        uint32_t mq[PM_RBI_QUEUE];
-        int mc = 0;
-#pragma unroll
-        for (int i = 0; i < PM_RBI_QUEUE; i++) mq[i] = 0;
-        auto flush = [&]() {
-          int inc = mc;  // inclusive scan of the queue lengths
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-            if (lane >= o) inc += t;
-          }
-          const int at = cnt + inc - mc;
-#pragma unroll
-          for (int i = 0; i < PM_RBI_QUEUE; i++)
-            if (i < mc) {
-              if (at + i < cap) {
-                st_pos[at + i] = mq[i];
-                st_seg[at + i] = (uint8_t)s;
-              } else {
-                overflow = true;
-              }
-            }
-          cnt += __shfl_sync(0xFFFFFFFFu, inc, 31);
-          mc = 0;
-        };
         for (uint32_t q0 = 0; q0 < nmax; q0 += 8 * PM_RBI_UNROLL) {
           uint4 P[PM_RBI_UNROLL];
           uint32_t T[PM_RBI_UNROLL];
@@ -348,31 +324,49 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
           }
 #pragma unroll
           for (int u = 0; u < PM_RBI_UNROLL; u++) {
-            if (__any_sync(0xFFFFFFFFu, mc > PM_RBI_QUEUE - 4)) flush();  // room for the four entries of a quad
             // per tag byte: fields that differ from the exact tag; a byte qualifies when at most one field differs
             const uint32_t X = T[u] ^ etagx;
             const uint32_t D = (X | (X >> 1)) & 0x55555555u;
             const uint32_t Z = D & ((D | 0x80808080u) - 0x01010101u);             // byte == 0 <=> <= 1 field differs
             uint32_t hit = ((Z + 0x7F7F7F7Fu) & 0x80808080u) ^ 0x80808080u;       // bit 7 of byte k: tag k qualifies
             hit &= ((D + 0x7F7F7F7Fu) & 0x80808080u) | keep_exact;                 // ... and it is not the exact tag (rot > 0)
-            while (hit) {  // ~5 % of the entries
-              const uint32_t low = hit & (0u - hit);
-              const uint32_t pos = low == 0x80u ? P[u].x : low == 0x8000u ? P[u].y : low == 0x800000u ? P[u].z : P[u].w;
-              hit ^= low;
-              if (pos < PM_RBI_MARK) {
-#pragma unroll
-                for (int i = PM_RBI_QUEUE - 1; i > 0; i--) mq[i] = mq[i - 1];
-                mq[0] = pos;
-                mc++;
+            if (hit) {  // ~19 % of the quads: the lane reserves its slots in the strand's list and fills them, no loop
+              const uint32_t at = atomicAdd(&sm.n_ent, (uint32_t)__popc(hit));
+              if (at + 4u <= (uint32_t)cap) {
+                if (hit & 0x80u) { st_pos[at] = P[u].x; st_seg[at] = (uint8_t)s; }
+                if (hit & 0x8000u) { const uint32_t o = at + ((hit >> 7) & 1u); st_pos[o] = P[u].y; st_seg[o] = (uint8_t)s; }
+                if (hit & 0x800000u) { const uint32_t o = at + (uint32_t)__popc(hit & 0x8080u); st_pos[o] = P[u].z; st_seg[o] = (uint8_t)s; }
+                if (hit & 0x80000000u) { const uint32_t o = at + (uint32_t)__popc(hit & 0x808080u); st_pos[o] = P[u].w; st_seg[o] = (uint8_t)s; }
               } else {
-                crowded |= pos == PM_RBI_MARK;
+                overflow = true;
               }
             }
           }
         }
-        flush();
-        if (__any_sync(0xFFFFFFFFu, crowded)) cnt = cnt0;  // 1602-1606: one crowded k-mer empties the segment's list
-        if (cnt > cap) cnt = cap;                          // (overflow is reported below; keep the stores in range)
+        __syncwarp();
+        cnt = (int)sm.n_ent;
+        if (cnt > cap) cnt = cap;  // (overflow is reported below; keep the reads in range)
+        // markers of crowded k-mers and the padding of a bucket's last quad came along as positions: a marker empties
+        // the segment's list (1602-1606), padding is dropped (only tags next to 0xFF ever pick it up)
+        bool crowded = false, padded = false;
+        for (int e = cnt0 + lane; e < cnt; e += 32) {
+          const uint32_t v = st_pos[e];
+          crowded |= v == PM_RBI_MARK;
+          padded |= v == PM_RBI_EMPTY;
+        }
+        if (__any_sync(0xFFFFFFFFu, crowded)) cnt = cnt0;
+        else if (__any_sync(0xFFFFFFFFu, padded)) {
+          int wr = cnt0;
+          if (lane == 0)
+            for (int e = cnt0; e < cnt; e++) {
+              const uint32_t v = st_pos[e];
+              if (v != PM_RBI_EMPTY) st_pos[wr++] = v;
+            }
+          cnt = __shfl_sync(0xFFFFFFFFu, wr, 0);
+        }
+        __syncwarp();
+        if (lane == 0) sm.n_ent = (uint32_t)cnt;
+        __syncwarp();
         min_spots = min(min_spots, (uint32_t)(cnt - cnt0));
       }
       if (__any_sync(0xFFFFFFFFu, overflow)) {
@@ -390,7 +384,8 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
       // ---- hash the entries by diagonal / 16.  Fast path: a slot word holds the chain head (bits 0-9, 0x3FF = none)
       // and the set of segments hashed into the slot (bit 13 + segment); BIG: the head index alone.
       constexpr uint32_t HNIL = BIG ? 0xFFFFFFFFu : 0x3FFu;
-      for (uint32_t i = lane; i <= tab_mask; i += 32) st_head[i] = HNIL;
+      for (uint32_t i = 4u * lane; i <= tab_mask; i += 128)
+        *reinterpret_cast<uint4*>(st_head + i) = make_uint4(HNIL, HNIL, HNIL, HNIL);
       __syncwarp();
       for (int e = lane; e < N; e += 32) {
         const int s = st_seg[e];
@@ -416,43 +411,63 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
       // within max_off - 1 of the anchor's.  The segments present in the three slots around the anchor bound it from
       // above; only anchors whose bound reaches min_match (the read's true locus, rarely a chance cluster) walk the chains.
       bool relevant = false;  // some anchor reaches the running min_match
-      for (int e = lane; e < N; e += 32) {
+      auto exact_found = [&](const uint32_t e) {
         const int s = st_seg[e];
-        int fnd = 0;
-        if (1 + max_depth - s >= min_match) {  // an anchor of segment s reaches at most 1 + max_depth - s
-          const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
-          const long long dg = (long long)st_pos[e] + 512ll - (long long)off;
-          const uint32_t bin = (uint32_t)(dg >> 4);
-          uint32_t hw[3];
+        const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
+        const long long dg = (long long)st_pos[e] + 512ll - (long long)off;
+        const uint32_t bin = (uint32_t)(dg >> 4);
+        uint32_t segs = 0;
 #pragma unroll
-          for (int db = 0; db < 3; db++) hw[db] = st_head[rbi_hash(bin + (uint32_t)(db - 1), tab_mask)];
-          bool walk = true;
-          if (!BIG) {
-            const uint32_t later = ~((2u << s) - 1u);
-            walk = 1 + __popc(((hw[0] | hw[1] | hw[2]) >> 13) & later) >= min_match;
-          }
-          if (walk) {
-            uint32_t segs = 0;
-#pragma unroll
-            for (int db = 0; db < 3; db++) {
-              uint32_t q = BIG ? hw[db] : (hw[db] & 0x3FFu);
-              while (q != HNIL) {
-                const int sq = st_seg[q];
-                if (sq > s) {
-                  const uint32_t offq = (sq < total_cuts) ? 16u * (uint32_t)sq : (uint32_t)(len - 16);
-                  const long long d = (long long)st_pos[q] + 512ll - (long long)offq - dg;
-                  if (d > -(long long)mo && d < (long long)mo) segs |= 1u << sq;  // 2244
-                }
-                const NextT nx = st_next[q];
-                q = nx == NIL ? HNIL : (uint32_t)nx;
-              }
+        for (int db = 0; db < 3; db++) {
+          const uint32_t hw = st_head[rbi_hash(bin + (uint32_t)(db - 1), tab_mask)];
+          uint32_t q = BIG ? hw : (hw & 0x3FFu);
+          while (q != HNIL) {
+            const int sq = st_seg[q];
+            if (sq > s) {
+              const uint32_t offq = (sq < total_cuts) ? 16u * (uint32_t)sq : (uint32_t)(len - 16);
+              const long long d = (long long)st_pos[q] + 512ll - (long long)offq - dg;
+              if (d > -(long long)mo && d < (long long)mo) segs |= 1u << sq;  // 2244
             }
-            fnd = 1 + __popc(segs);
+            const NextT nx = st_next[q];
+            q = nx == NIL ? HNIL : (uint32_t)nx;
           }
         }
+        const int fnd = 1 + __popc(segs);
         st_found[e] = (uint8_t)fnd;
         relevant |= fnd >= min_match;
+      };
+      int np = 0;  // anchors waiting in sm.pend (warp-uniform): they are walked 32 at a time, all lanes busy
+      for (int e0 = 0; e0 < N; e0 += 32) {
+        const int e = e0 + lane;
+        bool pass = false;
+        if (e < N) {
+          const int s = st_seg[e];
+          if (1 + max_depth - s >= min_match) {  // an anchor of segment s reaches at most 1 + max_depth - s
+            pass = true;
+            if (!BIG) {
+              const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
+              const uint32_t bin = (uint32_t)(((unsigned long long)st_pos[e] + 512ull - off) >> 4);
+              const uint32_t hw = st_head[rbi_hash(bin - 1u, tab_mask)] | st_head[rbi_hash(bin, tab_mask)] |
+                                  st_head[rbi_hash(bin + 1u, tab_mask)];
+              pass = 1 + __popc((hw >> 13) & ~((2u << s) - 1u)) >= min_match;
+            }
+          }
+          if (!pass) st_found[e] = 0;
+        }
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
+        if (pass) sm.pend[np + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)e;
+        np += __popc(bal);
+        __syncwarp();
+        if (np >= 32) {
+          exact_found(sm.pend[lane]);
+          const uint32_t keep = lane < np - 32 ? sm.pend[32 + lane] : 0u;
+          __syncwarp();
+          if (lane < np - 32) sm.pend[lane] = keep;
+          np -= 32;
+          __syncwarp();
+        }
       }
+      if (lane < np) exact_found(sm.pend[lane]);
       __syncwarp();
       if (!__any_sync(0xFFFFFFFFu, relevant)) continue;  // the usual fate of the strand the read does not come from
 

@@ -474,35 +474,33 @@ __device__ __forceinline__ int ge_good(int s36, double good36) {
   return -1;
 }
 
+// Single-end rule (1101-1127) on integers.  Scores below the integer maximum differ from it by >= 1/36 as doubles
+// too, so they can neither end up as `top` nor be counted as ties of it: the double-precision outcome is a function
+// of the candidates AT the maximum alone (their order and their rounded scores).  Hence
+//   maximum clearly below the threshold            -> NEITHER_MAP, no double needed
+//   maximum clearly above it, one candidate has it -> UNIQUE_SINGLE (fp64 only if its own last-column argmax tied)
+//   several candidates at the maximum, or the maximum on the threshold -> *amb, and only those candidates are
+//   re-scored in fp64 (*narrow = their score); a base outside ACGTN anywhere -> *amb with every candidate re-scored.
 __device__ __forceinline__ int single_rule_int(const ITaskResult* res, int n, int len, const DevParams& p, int* best,
-                                               bool* amb) {
+                                               bool* amb, int* narrow) {
   const double good36 = (double)len * p.min_align * p.match_bonus * 36.0;
-  int top = -72 * len, count = 0;
-  bool tie = false;
-  *best = -1;
+  int smax = -0x7FFFFFFF, nmax = 0, first = -1;
+  bool odd = false;
   for (int q = 0; q < n; q++) {
     const int s = res[q].score36;
-    if (res[q].flags & 2) *amb = true;
-    const int ge = ge_good(s, good36);
-    if (ge < 0) *amb = true;
-    if (s > top && ge > 0) {
-      top = s;
-      count = 1;
-      *best = q;
-      tie = false;
-    } else if (s == top && count > 0) {  // double: either '>' by an ulp (new unique top) or counted as a tie
-      count++;
-      tie = true;
-    }
-  }
-  if (tie) *amb = true;
-  if (count == 0) { *best = -1; return T_NEITHER_MAP; }
-  if (count == 1) {
-    if (res[*best].flags & 1) *amb = true;
-    return T_UNIQUE_SINGLE;
+    odd |= (res[q].flags & 2) != 0;
+    if (s > smax) { smax = s; nmax = 1; first = q; }
+    else if (s == smax) nmax++;
   }
   *best = -1;
-  return T_NON_NO;
+  *narrow = smax;
+  if (odd) { *amb = true; *narrow = -0x7FFFFFFF; return T_NEITHER_MAP; }
+  const int ge = ge_good(smax, good36);
+  if (ge == 0) return T_NEITHER_MAP;
+  if (ge < 0 || nmax > 1) { *amb = true; return T_NEITHER_MAP; }
+  *best = first;
+  if (res[first].flags & 1) *amb = true;
+  return T_UNIQUE_SINGLE;
 }
 
 __device__ __forceinline__ int pair_rule_int(const Task* ta, const ITaskResult* ra, int n1, int l1, const Task* tb,
@@ -589,11 +587,40 @@ __global__ void __launch_bounds__(128) k_select_int(SelectIntArgs a) {
   const int l1 = a.len[0][r], l3 = a.p.pair_flag ? a.len[1][r] : 0;
   int keep1 = -1, keep2 = -1, call;
   bool amb = false;
-  if (n1 > 0 && n2 == 0) call = single_rule_int(a.ires + b1, n1, l1, a.p, &keep1, &amb);
-  else if (n2 > 0 && n1 == 0) call = single_rule_int(a.ires + b2, n2, l3, a.p, &keep2, &amb);
+  int narrow = -0x7FFFFFFF;  // single-end rule: only candidates with this integer score need their double
+  if (n1 > 0 && n2 == 0) call = single_rule_int(a.ires + b1, n1, l1, a.p, &keep1, &amb, &narrow);
+  else if (n2 > 0 && n1 == 0) call = single_rule_int(a.ires + b2, n2, l3, a.p, &keep2, &amb, &narrow);
   else if (n1 > 0 && n2 > 0)
     call = pair_rule_int(a.tasks + b1, a.ires + b1, n1, l1, a.tasks + b2, a.ires + b2, n2, l3, a.p, &keep1, &keep2, &amb);
   else call = T_NEITHER_MAP;
+  if (amb && narrow != -0x7FFFFFFF) {
+    // single-end rule with a rational tie at the top: the exact selection (k_select) needs the reference's doubles of
+    // the tied candidates only; every other candidate gets its rational score, which orders it exactly as its double
+    // would (>= 1/36 below the top) and is never consulted for anything else
+    const uint32_t slot = atomicAdd(a.replay_read_cursor, 1u);
+    a.replay_reads[slot] = (uint32_t)r;
+    const int n = n1 > 0 ? n1 : n2;
+    const uint32_t b = n1 > 0 ? b1 : b2, rmv = n1 > 0 ? 2u * r : 2u * r + 1u;
+    int tied = 0;
+    for (int q = 0; q < n; q++) tied += a.ires[b + q].score36 == narrow;
+    uint32_t at = atomicAdd(a.replay_task_cursor, (uint32_t)tied);
+    for (int q = 0; q < n; q++) {
+      const ITaskResult ir = a.ires[b + q];
+      if (ir.score36 == narrow) {
+        a.replay_tasks[at].task = b + q;
+        a.replay_tasks[at].rm = rmv;
+        at++;
+      } else {
+        TaskResult t64;
+        t64.score = (double)ir.score36 / 36.0;
+        t64.maxi = ir.maxi;
+        t64.maxk = ir.maxk;
+        a.results64[b + q] = t64;
+      }
+    }
+    atomicAdd(&a.counters->replayed, 1ull);
+    return;
+  }
   if (amb) {  // hand the whole read (pair) to the exact path
     const uint32_t slot = atomicAdd(a.replay_read_cursor, 1u);
     a.replay_reads[slot] = (uint32_t)r;
