@@ -46,6 +46,8 @@ CONFIGS = {
     "cfg3": {"genome_seed": 30, "read_seed": 31, "total": float(os.environ.get("PEMAP_CFG3_BASES", 3.1e9)),
              "text": "cfg3: %d contigs (sizes ~ human chr1-22,X,Y) totalling %.2e bp"},
     "cfg2": {"genome_seed": 20, "read_seed": 21, "total": float(GENOME_LEN), "text": "cfg2: %d contig of %.2e bp"},
+    "cfg5": {"genome_seed": 50, "read_seed": 51, "total": 64e6,
+             "text": "cfg5: %d contigs totalling %.2e bp, half of it copies of 200 2-kb units at 0-2 %% divergence"},
 }
 
 
@@ -68,6 +70,11 @@ def config_genome(name, device):
     if name == "cfg2":
         g = make_genome(cfg["genome_seed"], int(cfg["total"]))
         return [g], torch.from_numpy(g).to(device)
+    if name == "cfg5":
+        from pecaller_b200 import synth
+        contigs = synth.repeat_genome(cfg["genome_seed"], [int(cfg["total"]) // 16] * 16, unit_len=2000, n_units=200, frac=0.5,
+                                      max_div=0.02)
+        return contigs, torch.from_numpy(np.concatenate(contigs)).to(device)
     lens = [int(cfg["total"] * m / sum(CHR_MB)) for m in CHR_MB]
     G = sum(lens)
     gen = torch.Generator(device=device)

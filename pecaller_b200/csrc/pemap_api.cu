@@ -28,6 +28,7 @@ namespace {
 
 constexpr int kSeedWarps = 4;
 constexpr int kRbiWarps = 8;     // k_seed_rbi: 8 warps per CTA, 9.3 KB of shared memory per warp -> 3 CTAs per SM
+constexpr int kRbiMidWarps = 4;  // second pass: 27 KB per warp
 constexpr int kRbiBigWarps = 4;
 constexpr int kMaxDev = 16;  // per-device caches of launch configurations
 constexpr uint64_t kInsCapDefault = 256ull << 20;
@@ -62,7 +63,8 @@ struct pemap_ctx {
   uint64_t rbi_bytes = 0;
   int seed_legacy = 0;             // PEMAP_SEED=legacy: k_seed_chain over pos_index / mers
   int index_only = 0;              // PEMAP_INDEX_ONLY=1: the handle only builds and hands out the index
-  uint32_t* d_big_list = nullptr;  // read-mates whose strand lists did not fit shared memory (second seed pass)
+  uint32_t* d_big_list = nullptr;  // read-mates whose strand lists did not fit the first seed pass / the second
+  uint32_t* d_big_list2 = nullptr;
   unsigned char* d_big_scratch = nullptr;
   int big_grid = 0;
   uint32_t* d_filter = nullptr;  // word-blocked Bloom filter of the occupied k-mers (seed_chain.cuh), or null
@@ -324,9 +326,10 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   if (h->seed_legacy) {
     CK(cudaMalloc(&h->d_seed_scratch, (size_t)h->seed_blocks * kSeedWarps * 2 * PM_MAX_SEG * PM_SEG_CAP * 4));
   } else {  // second seed pass (strand lists that do not fit shared memory): one CTA per SM, per-warp lists in HBM
-    h->big_grid = h->sm_count;
+    h->big_grid = 2 * h->sm_count;
     CK(cudaMalloc(&h->d_big_scratch, (size_t)h->big_grid * kRbiBigWarps * PM_RBI_BIG_BYTES));
     CK(cudaMalloc(&h->d_big_list, 2 * n * 4));
+    CK(cudaMalloc(&h->d_big_list2, 2 * n * 4));
   }
   h->sw_blocks = h->sm_count * 6;  // upper bound of CTAs per SM of the wavefront kernels (scratch is sized for it)
   const size_t max_groups = (size_t)h->sw_blocks * (128 / 16);
@@ -749,7 +752,7 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
   const bool exact = h->exact || (h->keep & PEMAP_KEEP_DETAIL) || h->params.match_bonus != 1.0;
   bool forked = false;
   CK(cudaMemsetAsync(h->d_cursors, 0, 16, h->stream));
-  CK(cudaMemsetAsync(h->d_cursors + 6, 0, 48, h->stream));  // [6..8] lists, [9..15] work counters of the persistent kernels, [16] DP list, [17] big seed list
+  CK(cudaMemsetAsync(h->d_cursors + 6, 0, 52, h->stream));  // [6..8] lists, [9..15] work counters of the persistent kernels, [16] DP list, [17]/[18] seed lists of the second / third pass
   CK(cudaEventRecord(ev[0], h->stream));
   pm::SeedArgs sa;
   sa.p = h->dp;
@@ -777,33 +780,55 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     ra.cand_base = h->d_cand_base;
     ra.cand_n = h->d_cand_n;
     ra.counters = h->d_counters;
-    ra.big_list = h->d_big_list;
-    ra.big_cursor = h->d_cursors + 17;
-    ra.work_list = h->d_big_list;
-    ra.work_n = h->d_cursors + 17;
     ra.big_scratch = h->d_big_scratch;
     ra.fast_cap = PM_RBI_CAP;
     if (const char* s = getenv("PEMAP_RBI_CAP")) ra.fast_cap = std::min(PM_RBI_CAP, std::max(1, atoi(s)));
     ra.p = sa.p;
     const int work = paired ? 2 * n : n;
-    static int rbi_wave[kMaxDev] = {};
+    static int rbi_wave[kMaxDev] = {}, rbi_wave2[kMaxDev] = {};
     int& wave = rbi_wave[h->device % kMaxDev];
-    const size_t dyn = pm::seed_rbi_smem<kRbiWarps>(false), dyn_big = pm::seed_rbi_smem<kRbiBigWarps>(true);
+    int& wave2 = rbi_wave2[h->device % kMaxDev];
+    constexpr size_t dyn = pm::seed_rbi_smem<kRbiWarps, PM_RBI_CAP>(), dyn2 = pm::seed_rbi_smem<kRbiMidWarps, PM_RBI_CAP2>(),
+                     dyn_big = pm::seed_rbi_smem<kRbiBigWarps, 0>();
     if (!wave) {
-      cudaFuncSetAttribute(pm::k_seed_rbi<kRbiWarps, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-      cudaFuncSetAttribute(pm::k_seed_rbi<kRbiBigWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_big);
-      int per_sm = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_seed_rbi<kRbiWarps, false>, kRbiWarps * 32, dyn) != cudaSuccess ||
+      cudaFuncSetAttribute(pm::k_seed_rbi<kRbiWarps, PM_RBI_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      cudaFuncSetAttribute(pm::k_seed_rbi<kRbiMidWarps, PM_RBI_CAP2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2);
+      cudaFuncSetAttribute(pm::k_seed_rbi<kRbiBigWarps, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_big);
+      int per_sm = 0, per_sm2 = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm::k_seed_rbi<kRbiWarps, PM_RBI_CAP>, kRbiWarps * 32, dyn) != cudaSuccess ||
           per_sm < 1)
         per_sm = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, pm::k_seed_rbi<kRbiMidWarps, PM_RBI_CAP2>, kRbiMidWarps * 32, dyn2) !=
+              cudaSuccess || per_sm2 < 1)
+        per_sm2 = 1;
       cudaGetLastError();
       if (const char* s = getenv("PEMAP_SEED_CTAS")) per_sm = std::min(per_sm, std::max(1, atoi(s)));
       wave = per_sm * h->sm_count;
-      if (getenv("PEMAP_VERBOSE")) fprintf(stderr, "pemap: k_seed_rbi %d CTAs per SM, %zu B of shared memory each\n", per_sm, dyn);
+      wave2 = per_sm2 * h->sm_count;
+      if (getenv("PEMAP_VERBOSE"))
+        fprintf(stderr, "pemap: k_seed_rbi %d CTAs per SM (%zu B of shared memory each), second pass %d CTAs per SM (%zu B)\n", per_sm,
+                dyn, per_sm2, dyn2);
     }
+    // pass 1: every read-mate, 512 entries per strand in shared memory; pass 2: what did not fit, 2048 entries (reads in
+    // repeats); pass 3: the rest in the per-warp global scratch (any strand fits)
+    ra.work_list = nullptr;
+    ra.work_n = nullptr;
+    ra.next_list = h->d_big_list;
+    ra.next_cursor = h->d_cursors + 17;
     const int grid = std::min(wave, (work + kRbiWarps - 1) / kRbiWarps);
-    if (grid > 0) pm::k_seed_rbi<kRbiWarps, false><<<grid, kRbiWarps * 32, dyn, h->stream>>>(ra);
-    pm::k_seed_rbi<kRbiBigWarps, true><<<h->big_grid, kRbiBigWarps * 32, dyn_big, h->stream>>>(ra);
+    if (grid > 0) pm::k_seed_rbi<kRbiWarps, PM_RBI_CAP><<<grid, kRbiWarps * 32, dyn, h->stream>>>(ra);
+    ra.work_list = h->d_big_list;
+    ra.work_n = h->d_cursors + 17;
+    ra.next_list = h->d_big_list2;
+    ra.next_cursor = h->d_cursors + 18;
+    ra.fast_cap = ra.fast_cap < PM_RBI_CAP ? 4 * ra.fast_cap : PM_RBI_CAP2;
+    pm::k_seed_rbi<kRbiMidWarps, PM_RBI_CAP2><<<wave2, kRbiMidWarps * 32, dyn2, h->stream>>>(ra);
+    ra.work_list = h->d_big_list2;
+    ra.work_n = h->d_cursors + 18;
+    ra.next_list = nullptr;
+    ra.next_cursor = nullptr;
+    pm::k_seed_rbi<kRbiBigWarps, 0><<<h->big_grid, kRbiBigWarps * 32, dyn_big, h->stream>>>(ra);
+    h->stats.launches += 2;
     h->stats.launches++;
   }
   h->stats.launches++;
@@ -1779,7 +1804,7 @@ void pemap_destroy(pemap_t* h) {
     for (void* p : dev)
       if (p) cudaFree(p);
     void* rbi[] = {h->d_rbi_data[0], h->d_rbi_data[1], h->d_rbi_data[2], h->d_rbi_data[3], h->d_rbi_dir[0], h->d_rbi_dir[1],
-                   h->d_rbi_dir[2], h->d_rbi_dir[3], h->d_big_list, h->d_big_scratch};
+                   h->d_rbi_dir[2], h->d_rbi_dir[3], h->d_big_list, h->d_big_list2, h->d_big_scratch};
     for (void* p : rbi)
       if (p) cudaFree(p);
     void* fin[] = {h->d_fin_rec[0], h->d_fin_rec[1], h->d_fin_cnt, h->d_fin_off, h->d_fin_tmp};

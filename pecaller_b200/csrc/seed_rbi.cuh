@@ -30,7 +30,7 @@
 #define PM_RBI_EMPTY 0xFFFFFFFFu
 #define PM_RBI_MARK 0xFFFFFFFEu
 #define PM_RBI_CAP 512                  // entries of one strand kept in shared memory (a 150-bp read on 3.1 Gb has ~360)
-#define PM_RBI_TAB 512                  // hash slots of the fast path
+#define PM_RBI_CAP2 2048                // second pass: strands of reads that sit in repeats
 #define PM_RBI_MAXB (4 * PM_MAX_SEG)    // buckets per strand
 #define PM_RBI_BIG_CAP 98304            // >= 19 segments * 49 * 99 positions: the slow path holds any strand
 #define PM_RBI_BIG_TAB 131072
@@ -145,9 +145,9 @@ struct SeedRbiArgs {
   uint32_t* cand_base;         // [2*n_reads]
   uint32_t* cand_n;            // [2*n_reads]
   SeedCounters* counters;
-  uint32_t* big_list;          // read-mate work items whose strand lists did not fit shared memory
-  uint32_t* big_cursor;
-  const uint32_t* work_list;   // BIG: the items to process, *work_n of them
+  uint32_t* next_list;         // work items whose strand lists did not fit this pass's stores (nullptr in the last pass)
+  uint32_t* next_cursor;
+  const uint32_t* work_list;   // the items to process, *work_n of them; nullptr = every read-mate of the chunk
   const uint32_t* work_n;
   unsigned char* big_scratch;  // BIG: per warp PM_RBI_BIG_BYTES
   int fast_cap;                // entries of a strand the first pass accepts (<= PM_RBI_CAP; PEMAP_RBI_CAP lowers it in tests)
@@ -156,25 +156,29 @@ struct SeedRbiArgs {
 
 #define PM_RBI_BIG_BYTES ((size_t)PM_RBI_BIG_CAP * 10 + (size_t)PM_RBI_BIG_TAB * 4)
 
-struct RbiWarpSmem {           // per warp, both paths
+struct RbiWarpSmem {           // per warp, every path
   uint32_t b_off[2 * PM_RBI_MAXB];   // bucket start (16-byte units), both strands: [4 * (strand * nseg + segment) + rotation]
-  uint32_t b_n4[2 * PM_RBI_MAXB];    // its position quads
+  uint16_t b_n4[2 * PM_RBI_MAXB];    // its position quads (<= 256 * 99 / 4)
   uint32_t kcode[2 * PM_MAX_SEG];
-  uint32_t n_ent;                    // entries of the strand gathered so far (appended to by the lanes that hold a match)
-  uint32_t pad_[3];
-  uint32_t pend[64];                 // anchors waiting for their exact found count
   uint32_t hit_pos[PM_MAX_HITS];
   uint16_t hit_off[PM_MAX_HITS];
   uint8_t hit_or[PM_MAX_HITS];
-  char rd[2][PM_DP_MAX];             // forward read and its reverse_transcribe (C->T converted when bisulfite)
+  union {
+    char rd[2][PM_DP_MAX];           // forward read and its reverse_transcribe (C->T converted when bisulfite): until the k-mers are cut
+    struct {
+      uint32_t n_ent;                // entries of the strand gathered so far (appended to by the lanes that hold a match)
+      uint32_t pend[64];             // anchors waiting for their exact found count
+    } g;
+  };
 };
 
-struct RbiFastStore {          // per warp, fast path only: the entries of one strand
-  uint32_t pos[PM_RBI_CAP];
-  uint32_t head[PM_RBI_TAB];         // chain heads; afterwards scratch of the anchor sort
-  uint16_t next[PM_RBI_CAP];
-  uint8_t seg[PM_RBI_CAP];
-  uint8_t found[PM_RBI_CAP];
+template <int CAP>
+struct RbiSmemStore {          // per warp: the entries of one strand (CAP = 512 first pass, 2048 second pass)
+  uint32_t pos[CAP];
+  uint32_t head[CAP];                // chain heads + segment sets; afterwards scratch of the anchor sort
+  uint16_t next[CAP];
+  uint8_t seg[CAP];
+  uint8_t found[CAP];
 };
 
 __device__ __forceinline__ uint4 rbi_ld16(const uint4* p) {
@@ -220,13 +224,16 @@ __device__ __forceinline__ void rbi_sort_idx(uint32_t* idx, const uint32_t* pos,
 
 // One read-mate.  BIG = false: entries in shared memory (st_*), a strand with more than `cap` entries makes the function
 // return false and the caller queues the read-mate for the BIG pass, whose stores live in a per-warp global scratch.
-template <bool BIG, class NextT>
+template <int CAPT, class NextT>   // CAPT = capacity of the shared-memory stores, 0 = stores in global memory (BIG)
 __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpSmem& sm, uint32_t* st_pos, uint32_t* st_head,
                                                   NextT* st_next, uint8_t* st_seg, uint8_t* st_found, const int cap,
                                                   const uint32_t tab_mask, const int w, const int lane,
                                                   unsigned long long& stat_pos, unsigned long long& stat_cand,
                                                   unsigned long long& stat_cells, unsigned long long& stat_lookups) {
   constexpr NextT NIL = (NextT)~(NextT)0;
+  constexpr bool BIG = CAPT == 0;
+  constexpr uint32_t IMASK = BIG ? 0xFFFFFFFFu : (uint32_t)(2 * CAPT - 1);  // index field of a slot word; all ones = none
+  static_assert(CAPT <= 4096, "the segment set of a slot word starts at bit 13");
   const int r = a.paired ? (w >> 1) : w, mate = a.paired ? (w & 1) : 0;
   const uint32_t rm = 2u * (uint32_t)r + (uint32_t)mate;
   const int len = a.len[mate][r];
@@ -296,10 +303,10 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
       if (strand == 1 && tot >= a.p.max_hits) break;  // 1658
       // ---- gather (get_mers 2158-2165, loop 1594-1612 / 1619-1637): per segment, every entry of its four buckets whose
       // tag is the segment's tag or one 2-bit field away from it
-      int cnt = 0;              // warp-uniform copy of sm.n_ent between segments
+      int cnt = 0;              // warp-uniform copy of sm.g.n_ent between segments
       uint32_t min_spots = 10000;
       bool overflow = false;
-      if (lane == 0) sm.n_ent = 0;
+      if (lane == 0) sm.g.n_ent = 0;
       __syncwarp();
       for (int s = 0; s < nseg; s++) {
         const int b = 4 * (strand * nseg + s) + rot;
@@ -315,8 +322,7 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
 #pragma unroll
           for (int u = 0; u < PM_RBI_UNROLL; u++) {
             const uint32_t q = q0 + (uint32_t)(8 * u + l8);
-            T[u] = etagx ^ 0x0F0F0F0Fu;  // two fields away: never qualifies
-            P[u] = make_uint4(PM_RBI_EMPTY, PM_RBI_EMPTY, PM_RBI_EMPTY, PM_RBI_EMPTY);
+            T[u] = etagx ^ 0x0F0F0F0Fu;  // two fields away: never qualifies (P[u] is then never looked at)
             if (q < n4) {
               P[u] = rbi_ld16(base + q);
               T[u] = rbi_ld4(tags + q);
@@ -331,12 +337,12 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
             uint32_t hit = ((Z + 0x7F7F7F7Fu) & 0x80808080u) ^ 0x80808080u;       // bit 7 of byte k: tag k qualifies
             hit &= ((D + 0x7F7F7F7Fu) & 0x80808080u) | keep_exact;                 // ... and it is not the exact tag (rot > 0)
             if (hit) {  // ~19 % of the quads: the lane reserves its slots in the strand's list and fills them, no loop
-              const uint32_t at = atomicAdd(&sm.n_ent, (uint32_t)__popc(hit));
+              const uint32_t at = atomicAdd(&sm.g.n_ent, (uint32_t)__popc(hit));
               if (at + 4u <= (uint32_t)cap) {
-                if (hit & 0x80u) { st_pos[at] = P[u].x; st_seg[at] = (uint8_t)s; }
-                if (hit & 0x8000u) { const uint32_t o = at + ((hit >> 7) & 1u); st_pos[o] = P[u].y; st_seg[o] = (uint8_t)s; }
-                if (hit & 0x800000u) { const uint32_t o = at + (uint32_t)__popc(hit & 0x8080u); st_pos[o] = P[u].z; st_seg[o] = (uint8_t)s; }
-                if (hit & 0x80000000u) { const uint32_t o = at + (uint32_t)__popc(hit & 0x808080u); st_pos[o] = P[u].w; st_seg[o] = (uint8_t)s; }
+                if (hit & 0x80u) st_pos[at] = P[u].x;
+                if (hit & 0x8000u) st_pos[at + ((hit >> 7) & 1u)] = P[u].y;
+                if (hit & 0x800000u) st_pos[at + (uint32_t)__popc(hit & 0x8080u)] = P[u].z;
+                if (hit & 0x80000000u) st_pos[at + (uint32_t)__popc(hit & 0x808080u)] = P[u].w;
               } else {
                 overflow = true;
               }
@@ -344,7 +350,7 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
           }
         }
         __syncwarp();
-        cnt = (int)sm.n_ent;
+        cnt = (int)sm.g.n_ent;
         if (cnt > cap) cnt = cap;  // (overflow is reported below; keep the reads in range)
         // markers of crowded k-mers and the padding of a bucket's last quad came along as positions: a marker empties
         // the segment's list (1602-1606), padding is dropped (only tags next to 0xFF ever pick it up)
@@ -353,19 +359,24 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
           const uint32_t v = st_pos[e];
           crowded |= v == PM_RBI_MARK;
           padded |= v == PM_RBI_EMPTY;
+          st_seg[e] = (uint8_t)s;
         }
         if (__any_sync(0xFFFFFFFFu, crowded)) cnt = cnt0;
-        else if (__any_sync(0xFFFFFFFFu, padded)) {
+        else if (__any_sync(0xFFFFFFFFu, padded)) {  // stable in-place compaction, 32 entries at a time
           int wr = cnt0;
-          if (lane == 0)
-            for (int e = cnt0; e < cnt; e++) {
-              const uint32_t v = st_pos[e];
-              if (v != PM_RBI_EMPTY) st_pos[wr++] = v;
-            }
-          cnt = __shfl_sync(0xFFFFFFFFu, wr, 0);
+          for (int e0 = cnt0; e0 < cnt; e0 += 32) {
+            const int e = e0 + lane;
+            const uint32_t v = e < cnt ? st_pos[e] : PM_RBI_EMPTY;
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, v != PM_RBI_EMPTY);
+            __syncwarp();
+            if (v != PM_RBI_EMPTY) st_pos[wr + __popc(bal & ((1u << lane) - 1u))] = v;
+            wr += __popc(bal);
+            __syncwarp();
+          }
+          cnt = wr;
         }
         __syncwarp();
-        if (lane == 0) sm.n_ent = (uint32_t)cnt;
+        if (lane == 0) sm.g.n_ent = (uint32_t)cnt;
         __syncwarp();
         min_spots = min(min_spots, (uint32_t)(cnt - cnt0));
       }
@@ -381,9 +392,9 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
         continue;
       }
 
-      // ---- hash the entries by diagonal / 16.  Fast path: a slot word holds the chain head (bits 0-9, 0x3FF = none)
-      // and the set of segments hashed into the slot (bit 13 + segment); BIG: the head index alone.
-      constexpr uint32_t HNIL = BIG ? 0xFFFFFFFFu : 0x3FFu;
+      // ---- hash the entries by diagonal / 16.  Shared-memory paths: a slot word holds the chain head (low bits, all
+      // ones = none) and the set of segments hashed into the slot (bit 13 + segment); BIG: the head index alone.
+      constexpr uint32_t HNIL = IMASK;
       for (uint32_t i = 4u * lane; i <= tab_mask; i += 128)
         *reinterpret_cast<uint4*>(st_head + i) = make_uint4(HNIL, HNIL, HNIL, HNIL);
       __syncwarp();
@@ -402,7 +413,7 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
             assumed = old;
             old = atomicCAS(hp, assumed, (assumed & 0xFFFFE000u) | (1u << (13 + s)) | (uint32_t)e);
           } while (old != assumed);
-          old &= 0x3FFu;
+          old &= IMASK;
         }
         st_next[e] = old == HNIL ? NIL : (NextT)old;
       }
@@ -420,7 +431,7 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
 #pragma unroll
         for (int db = 0; db < 3; db++) {
           const uint32_t hw = st_head[rbi_hash(bin + (uint32_t)(db - 1), tab_mask)];
-          uint32_t q = BIG ? hw : (hw & 0x3FFu);
+          uint32_t q = hw & IMASK;
           while (q != HNIL) {
             const int sq = st_seg[q];
             if (sq > s) {
@@ -455,19 +466,19 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
           if (!pass) st_found[e] = 0;
         }
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
-        if (pass) sm.pend[np + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)e;
+        if (pass) sm.g.pend[np + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)e;
         np += __popc(bal);
         __syncwarp();
         if (np >= 32) {
-          exact_found(sm.pend[lane]);
-          const uint32_t keep = lane < np - 32 ? sm.pend[32 + lane] : 0u;
+          exact_found(sm.g.pend[lane]);
+          const uint32_t keep = lane < np - 32 ? sm.g.pend[32 + lane] : 0u;
           __syncwarp();
-          if (lane < np - 32) sm.pend[lane] = keep;
+          if (lane < np - 32) sm.g.pend[lane] = keep;
           np -= 32;
           __syncwarp();
         }
       }
-      if (lane < np) exact_found(sm.pend[lane]);
+      if (lane < np) exact_found(sm.g.pend[lane]);
       __syncwarp();
       if (!__any_sync(0xFFFFFFFFu, relevant)) continue;  // the usual fate of the strand the read does not come from
 
@@ -550,45 +561,48 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
   return true;
 }
 
-template <int WARPS, bool BIG>
+// CAP > 0: stores in shared memory; CAP = 0: in the per-warp global scratch.  Work items are all read-mates of the
+// chunk (work_list == nullptr) or the ones an earlier pass could not hold; the ones this pass cannot hold go to next_list.
+template <int WARPS, int CAP>
 __global__ void __launch_bounds__(WARPS * 32) k_seed_rbi(SeedRbiArgs a) {
   extern __shared__ __align__(16) unsigned char rbi_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   RbiWarpSmem& sm = reinterpret_cast<RbiWarpSmem*>(rbi_smem)[warp];
   const int gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
   unsigned long long st_pos = 0, st_cand = 0, st_cells = 0, st_lookups = 0;
-  if (BIG) {
-    unsigned char* sc = a.big_scratch + (size_t)gw * PM_RBI_BIG_BYTES;
-    uint32_t* g_pos = reinterpret_cast<uint32_t*>(sc);
-    uint32_t* g_next = g_pos + PM_RBI_BIG_CAP;
-    uint32_t* g_head = g_next + PM_RBI_BIG_CAP;
-    uint8_t* g_seg = reinterpret_cast<uint8_t*>(g_head + PM_RBI_BIG_TAB);
-    uint8_t* g_found = g_seg + PM_RBI_BIG_CAP;
-    const int n_work = (int)*a.work_n;
-    for (int i = gw; i < n_work; i += nw)
-      rbi_map_read_mate<true, uint32_t>(a, sm, g_pos, g_head, g_next, g_seg, g_found, PM_RBI_BIG_CAP, PM_RBI_BIG_TAB - 1,
-                                        (int)a.work_list[i], lane, st_pos, st_cand, st_cells, st_lookups);
-  } else {
-    RbiFastStore& fs = reinterpret_cast<RbiFastStore*>(rbi_smem + WARPS * sizeof(RbiWarpSmem))[warp];
-    const int n_work = a.paired ? 2 * a.n_reads : a.n_reads;
-    for (int w = gw; w < n_work; w += nw) {
-      {  // the next read-mate of this warp: its row and length are cold in HBM; start fetching them now
-        const int wn = w + nw;
-        if (wn < n_work && lane < 4) {
-          const int rn = a.paired ? (wn >> 1) : wn, mn = a.paired ? (wn & 1) : 0;
-          const char* nxt = a.reads[mn] + (size_t)rn * a.stride;
-          if (lane < 3) {
-            if (lane * 128 < a.stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + lane * 128));
-          } else {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.len[mn] + rn));
-          }
+  const int n_work = a.work_list ? (int)*a.work_n : (a.paired ? 2 * a.n_reads : a.n_reads);
+  for (int i = gw; i < n_work; i += nw) {
+    const int w = a.work_list ? (int)a.work_list[i] : i;
+    if (!a.work_list) {  // the next read-mate of this warp: its row and length are cold in HBM; start fetching them now
+      const int wn = i + nw;
+      if (wn < n_work && lane < 4) {
+        const int rn = a.paired ? (wn >> 1) : wn, mn = a.paired ? (wn & 1) : 0;
+        const char* nxt = a.reads[mn] + (size_t)rn * a.stride;
+        if (lane < 3) {
+          if (lane * 128 < a.stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + lane * 128));
+        } else {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.len[mn] + rn));
         }
       }
-      const bool fit = rbi_map_read_mate<false, uint16_t>(a, sm, fs.pos, fs.head, fs.next, fs.seg, fs.found, a.fast_cap,
-                                                          PM_RBI_TAB - 1, w, lane, st_pos, st_cand, st_cells, st_lookups);
-      if (!fit && lane == 0) a.big_list[atomicAdd(a.big_cursor, 1u)] = (uint32_t)w;
-      __syncwarp();
     }
+    bool fit;
+    if (CAP == 0) {
+      unsigned char* sc = a.big_scratch + (size_t)gw * PM_RBI_BIG_BYTES;
+      uint32_t* g_pos = reinterpret_cast<uint32_t*>(sc);
+      uint32_t* g_next = g_pos + PM_RBI_BIG_CAP;
+      uint32_t* g_head = g_next + PM_RBI_BIG_CAP;
+      uint8_t* g_seg = reinterpret_cast<uint8_t*>(g_head + PM_RBI_BIG_TAB);
+      uint8_t* g_found = g_seg + PM_RBI_BIG_CAP;
+      fit = rbi_map_read_mate<0, uint32_t>(a, sm, g_pos, g_head, g_next, g_seg, g_found, PM_RBI_BIG_CAP, PM_RBI_BIG_TAB - 1, w,
+                                           lane, st_pos, st_cand, st_cells, st_lookups);
+    } else {
+      constexpr int C = CAP > 0 ? CAP : 1;
+      RbiSmemStore<C>& fs = reinterpret_cast<RbiSmemStore<C>*>(rbi_smem + WARPS * sizeof(RbiWarpSmem))[warp];
+      fit = rbi_map_read_mate<C, uint16_t>(a, sm, fs.pos, fs.head, fs.next, fs.seg, fs.found, a.fast_cap < C ? a.fast_cap : C,
+                                           (uint32_t)(C - 1), w, lane, st_pos, st_cand, st_cells, st_lookups);
+    }
+    if (!fit && lane == 0 && a.next_list) a.next_list[atomicAdd(a.next_cursor, 1u)] = (uint32_t)w;
+    __syncwarp();
   }
   // statistics: one atomic per counter per warp (lane 0 holds the totals)
   unsigned long long cells = st_cells;
@@ -601,9 +615,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_seed_rbi(SeedRbiArgs a) {
   }
 }
 
-template <int WARPS>
-constexpr size_t seed_rbi_smem(bool big) {
-  return WARPS * sizeof(RbiWarpSmem) + (big ? 0 : WARPS * sizeof(RbiFastStore));
+template <int WARPS, int CAP>
+constexpr size_t seed_rbi_smem() {
+  return WARPS * sizeof(RbiWarpSmem) + (CAP > 0 ? WARPS * sizeof(RbiSmemStore<(CAP > 0 ? CAP : 1)>) : 0);
 }
 
 }  // namespace pm

@@ -1,9 +1,13 @@
-"""GPU + big host: BASELINE.md section 3.4.  A prefix of the north-star configuration (3.1 Gb genome, 24 contigs) is
-mapped by the CUDA path and by the unmodified reference (libpemapper_ref.so) and must agree bit for bit: every
-read's .mfile values and mapping type, the sha256 of the pileup records, the insertion multiset.  The committed record
-of the full 2 M-pair run is profiles/cfg3_parity_r02.json (tools/cfg3_parity.py); this test repeats it on a shorter
-prefix so that the GPU suite stays within minutes.  Skipped without ~170 GB of host RAM or the reference library."""
+"""GPU + big host: BASELINE.md section 3.4 and its cfg5 counterpart.  A prefix of the north-star configuration (3.1 Gb
+genome, 24 contigs) and reads of the high-repeat genome (cfg5) are mapped by the CUDA path and by the unmodified
+reference (oracle/_ref/libpemapper_ref.so, pemapper.c's own map_everything on all host threads) and must agree bit for
+bit: every read's .mfile values and mapping type, the sha256 of the pileup records, the insertion multiset.
+tools/cfg3_parity.py does the work in a process of its own (the reference keeps its state in file-static globals, so a
+process can hold one genome); the committed records of the full-size runs are profiles/cfg3_parity_r02.json and
+profiles/cfg5_parity_r02.json.  Skipped without the reference library or enough host RAM."""
+import json
 import os
+import subprocess
 import sys
 
 import pytest
@@ -23,19 +27,35 @@ def _host_ram_gb():
     return 0.0
 
 
-def test_cfg3_prefix_equals_reference():
+def _parity(config, n, single, need_gb):
     import oracle_lib as ol
     if not ol.have_reference_lib():
         pytest.skip("oracle/_ref/libpemapper_ref.so was not built")
-    if _host_ram_gb() < 170:
-        pytest.skip("the reference needs 32 B per genome base (99 GB) + the 16 GiB table on the host")
-    if os.environ.get("PEMAP_SKIP_CFG3") == "1":
-        pytest.skip("PEMAP_SKIP_CFG3=1")
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import cfg3_parity
-    out = cfg3_parity.run(int(os.environ.get("PEMAP_CFG3_TEST_PAIRS", 500_000)))
-    assert out["identical"]["m1"] and out["identical"]["m2"], "a read maps elsewhere than in the reference"
-    assert out["identical"]["mapping_type"]
-    assert out["identical"]["pileup_records"], "pileup records differ from the reference's"
-    assert out["identical"]["insertions"]
+    if _host_ram_gb() < need_gb:
+        pytest.skip("the reference needs 32 B per genome base + the 16 GiB table on the host")
+    if os.environ.get("PEMAP_SKIP_BIG_PARITY") == "1":
+        pytest.skip("PEMAP_SKIP_BIG_PARITY=1")
+    env = dict(os.environ, PEMAP_PARITY_CONFIG=config, PEMAP_PARITY_SINGLE="1" if single else "0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cfg3_parity.py"), str(n)], env=env, capture_output=True,
+                       text=True, timeout=1500)
+    assert r.stdout.strip(), r.stderr[-2000:]
+    out = json.loads(r.stdout)
+    for k, v in out["identical"].items():
+        assert v, "%s: %s differs from the reference (%s)" % (config, k, json.dumps(out["cuda"])[:400])
+    return out
+
+
+def test_cfg3_prefix_equals_reference():
+    out = _parity("cfg3", int(os.environ.get("PEMAP_CFG3_TEST_PAIRS", 500_000)), False, 170)
     assert out["cuda"]["type_counts"][0] > 0.99 * out["pairs"]
+
+
+def test_cfg5_repeats_single_end_equals_reference():
+    """200 k single-end reads on the high-repeat genome: ~15 % tie between repeat copies, where the reference's rounded
+    doubles decide between "unique" and "discarded" - the narrowed fp64 replay must reproduce every one."""
+    out = _parity("cfg5", int(os.environ.get("PEMAP_CFG5_TEST_READS", 200_000)), True, 40)
+    assert out["cuda"]["replayed_fp64_read_mates"] > 0.05 * out["pairs"]
+
+
+def test_cfg5_repeats_paired_equals_reference():
+    _parity("cfg5", int(os.environ.get("PEMAP_CFG5_TEST_PAIRS", 100_000)), False, 40)
