@@ -293,6 +293,10 @@ def main():
     ap.add_argument("--cpu-sample-pairs", type=int, default=env_int("PEMAP_BENCH_CPU_PAIRS", 0),
                     help="pairs per CPU step (default: host threads x 20,000 = one full batch per worker thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reduce-every", type=int, default=env_int("PEMAP_BENCH_REDUCE_EVERY", 4),
+                    help="N > 1: steps between two sums of the per-GPU pileup counters in the device-resident leg.  The "
+                         "target run (30x = 310 M pairs) is 31 steps of 10 M pairs, i.e. ~4 per GPU at N = 8 and more at "
+                         "smaller N, with ONE sum at its end; the end-to-end leg sums (and hands over the pileup) every step")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
 
@@ -381,7 +385,8 @@ def main():
 
     lib_stream = torch.cuda.ExternalStream(mapper.stream_ptr(), device=dev)
     from pecaller_b200 import sharding
-    reducer = sharding.CountReducer(mapper, dev, contigs) if world > 1 else None
+    reducer = sharding.SliceReducer(mapper) if world > 1 else None
+    site_range = [None]
 
     def barrier():
         torch.cuda.synchronize()
@@ -389,11 +394,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
+    def step_device(i=0, last=True):
         mapper.map_device(n, d_r1.data_ptr(), d_len.data_ptr(), d_r2.data_ptr(), d_len.data_ptr(), STRIDE, READ_LEN,
                           d_m1.data_ptr(), d_m2.data_ptr(), d_ty.data_ptr())
-        if world > 1:
-            reducer.reduce(dst=0)
+        if world > 1 and (last or (i + 1) % a.reduce_every == 0):
+            # slice-wise sum over NVLink peer memory: rank r ends up with the final counters of its 1/N of the genome
+            site_range[0] = reducer.reduce_scatter()
+            mapper.reset_counts()
 
     fin = {"records": 0}
 
@@ -402,9 +409,10 @@ def main():
         mapper._ck(mapper._L.pemap_map_batch_rows(mapper._h, n, h_r1.data_ptr(), h_len.data_ptr(), h_r2.data_ptr(),
                                                   h_len.data_ptr(), STRIDE, h_m1.data_ptr(), h_m2.data_ptr(), h_ty.data_ptr()))
         if world > 1:
-            reducer.reduce(dst=0)
-        if rank == 0:  # the writer: every covered site of the step's pileup crosses to pinned host memory
-            fin["records"] = mapper.finish_stream(None)
+            site_range[0] = reducer.reduce_scatter()
+        # the writer's input: every covered site of the step's pileup crosses to pinned host memory (N > 1: every rank
+        # compacts and copies out its own slice of the genome, in parallel)
+        fin["records"] = mapper.finish_stream(None, site_range=site_range[0])
 
     # ---- device-resident leg
     for _ in range(a.warmup):
@@ -418,13 +426,13 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(lib_stream)
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        step_device()
+    for i in range(a.steps):
+        step_device(i, i == a.steps - 1)
     ev1.record(lib_stream)
     barrier()
     wall_dev = time.perf_counter() - t0
     ms_dev = ev0.elapsed_time(ev1)
-    if world > 1:  # the NCCL reduce runs on torch's stream after the library's blocking call: use the wall clock there
+    if world > 1:  # the barriers around the slice-wise sum are host-side: use the wall clock there
         ms_dev = max(ms_dev, 1000.0 * wall_dev)
     stats = mapper.stats()
     clocks = sampler.stop()
@@ -442,9 +450,12 @@ def main():
     same = bool((h_m1.to(dev) == d_m1).all().item() and (h_m2.to(dev) == d_m2).all().item())
 
     t = torch.tensor([ms_dev, 1000.0 * wall_e2e], dtype=torch.float64, device=dev)
+    nrec = torch.tensor([fin["records"]], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nrec, op=dist.ReduceOp.SUM)
     ms_dev, ms_e2e = t.tolist()
+    fin["records"] = int(nrec.item())
     reads_per_step = 2 * n * world
     value = reads_per_step * a.steps / (ms_dev / 1000.0)
     e2e = reads_per_step * a.steps / (ms_e2e / 1000.0)
@@ -501,13 +512,16 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": workload_text(a.config, contigs, n),
                            "l2": "inputs (%.1f GB of reads per step) and the index exceed the 126 MB L2" % (2 * n * STRIDE / 1e9),
-                           "parallelism": "reads sharded over %d GPU(s), index replicated, NCCL sum of pileup counters" % world,
+                           "parallelism": ("reads sharded over %d GPUs, index replicated, pileup counters summed slice-wise over NVLink peer "
+                                           "memory every %d steps (and at the end of the timed region), every GPU compacts its own "
+                                           "1/%d of the genome" % (world, a.reduce_every, world)) if world > 1 else "1 GPU",
                            "index_build_s": round(t_index, 2), "datagen_s": round(t_gen + t_genome, 2),
                            "hbm_used_gb": round((total_b - free_b) / 1e9, 1)},
                 "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": 2 * n * STRIDE + 2 * n * 4,
                         "d2h_bytes_per_step": 3 * n * 4 + 16 * fin["records"], "ms_per_step": ms_e2e / a.steps,
                         "matches_device_leg": same, "pileup_records_per_step": fin["records"],
-                        "includes": "pemap_reset_counts + pemap_map_batch_rows (pinned rows) + pemap_finish_stream per step"},
+                        "includes": "pemap_reset_counts + pemap_map_batch_rows (pinned rows)" +
+                                    (" + slice-wise counter sum" if world > 1 else "") + " + pemap_finish_stream per step"},
                 "gpu_launches": int(stats["launches"]),
                 "clocks": clocks,
                 "roofline": dominant, "roofline_seed": roof_seed, "roofline_sw": roof_sw,

@@ -191,6 +191,25 @@ int pemap_counts_device(pemap_t *h, void **d_counts, uint64_t *n_words);
    pemap_finish(dst); insertion strings stay with the handle that produced them. */
 int pemap_reduce_counts_peer(pemap_t *dst, pemap_t *src);
 
+/* The reduce SURVEY 8e calls for, as a reduce-scatter over NVLink peer memory instead of a reduce onto one GPU: the
+   genome is cut into n_ranks equal slices (at multiples of 2048 sites), and every GPU adds the other GPUs' counters of
+   ITS slice to its own with one kernel that reads their arrays through NVLink (16-byte loads).  Afterwards rank r holds
+   the final counters of slice r = [*site_first, *site_end) and compacts it itself with pemap_finish_stream_range, so the
+   writer receives the slices' records in rank order; no GPU ever holds or moves more than 1/n of the sum.
+   Callers must make sure that every rank has finished mapping before any rank starts (a barrier), and that no rank
+   resets or maps again before every rank is done (another barrier).
+     _ipc   : one process per GPU (torchrun / MPI): exchange pemap_counts_ipc_handle() blobs (64 bytes per rank, in
+              rank order) and pass them all; the mappings are cached in the handle.
+     _local : one process, one pemap_t per GPU (the C host): hs[which] pulls from the other handles. */
+int pemap_counts_ipc_handle(pemap_t *h, void *handle64);
+int pemap_reduce_scatter_ipc(pemap_t *h, const void *handles, int n_ranks, int rank, uint64_t *site_first,
+                             uint64_t *site_end);
+int pemap_reduce_scatter_local(pemap_t *const *hs, int n, int which, uint64_t *site_first, uint64_t *site_end);
+
+/* pemap_finish_stream restricted to the sites [site_first, site_end). */
+int pemap_finish_stream_range(pemap_t *h, uint64_t site_first, uint64_t site_end, pemap_site_cb cb, void *ctx,
+                              uint64_t *n_records);
+
 /* The CUDA stream (cudaStream_t as void*) all of this handle's work is issued on, so that a caller can bracket
    calls with its own events. */
 int pemap_stream(pemap_t *h, void **stream);

@@ -151,6 +151,9 @@ struct pemap_ctx {
   void* d_fin_tmp = nullptr;
   size_t fin_tmp_bytes = 0;
   cudaEvent_t ev_fin[2] = {nullptr, nullptr};
+  // counter arrays of the other ranks' GPUs opened through CUDA IPC (pemap_reduce_scatter_ipc), kept until destroy
+  std::vector<void*> ipc_open;
+  std::vector<std::string> ipc_keys;
   // insertion records drained from the device append buffer so far (same {pos, len, chars} layout)
   std::vector<unsigned char> ins_raw;
   unsigned long long* h_ins_used = nullptr;     // pinned: cursor value after each chunk, one per slot
@@ -1561,16 +1564,24 @@ int pemap_get_candidates(pemap_t* h, int i, int mate, uint32_t* spots, int8_t* o
 }
 
 int pemap_finish_stream(pemap_t* h, pemap_site_cb cb, void* ctx, uint64_t* n_records) {
+  if (!h) return PEMAP_ERR_ARG;
+  return pemap_finish_stream_range(h, 0, h->genome_size, cb, ctx, n_records);
+}
+
+int pemap_finish_stream_range(pemap_t* h, uint64_t site_first, uint64_t site_end, pemap_site_cb cb, void* ctx,
+                              uint64_t* n_records) {
   if (!h || !cb) return PEMAP_ERR_ARG;
   if (h->index_only) return fail(h, PEMAP_ERR_ARG, "handle was opened with PEMAP_INDEX_ONLY=1");
+  if (site_end > h->genome_size) site_end = h->genome_size;
+  if (site_first > site_end) return fail(h, PEMAP_ERR_ARG, "empty or reversed site range");
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  const uint64_t gs = h->genome_size;
+  const uint64_t gs = site_end - site_first;
   const uint64_t tile = (uint64_t)PM_COMPACT_BLOCK * PM_COMPACT_ITEMS;
   if (!h->fin_sites) {  // staging: two device and two pinned host buffers of one window each
     uint64_t w = 1ull << 24;  // 16 M sites = 256 MB of records per buffer
     if (const char* s = getenv("PEMAP_FINISH_SITES")) w = std::max<uint64_t>(tile, strtoull(s, nullptr, 10));
-    w = std::min(w, std::max<uint64_t>(gs, 1));
+    w = std::min(w, std::max<uint64_t>(h->genome_size, 1));
     w = (w + tile - 1) / tile * tile;
     const size_t n_tiles = (size_t)(w / tile);
     for (int k = 0; k < 2; k++) {
@@ -1597,7 +1608,7 @@ int pemap_finish_stream(pemap_t* h, pemap_site_cb cb, void* ctx, uint64_t* n_rec
   for (uint64_t w = 0; w <= n_win; w++) {
     const int slot = (int)(w & 1);
     if (w < n_win) {
-      const uint64_t s0 = w * W, ns = std::min(W, gs - s0);
+      const uint64_t s0 = site_first + w * W, ns = std::min(W, site_end - s0);
       const unsigned n_tiles = (unsigned)((ns + tile - 1) / tile);
       unsigned long long* d_off = h->d_fin_off + (size_t)slot * (W / tile + 1);
       CK(cudaMemsetAsync(h->d_fin_cnt + n_tiles, 0, 8, h->stream));
@@ -1729,6 +1740,93 @@ int pemap_reduce_counts_peer(pemap_t* h, pemap_t* src) {
   return PEMAP_OK;
 }
 
+namespace {
+// this rank's slice of the genome when the counters are summed slice-wise over n_ranks GPUs: equal shares cut at
+// compaction tiles, so that rank r's records follow rank r-1's in ascending coordinate
+void slice_of(const pemap_ctx* h, int n_ranks, int rank, uint64_t* s0, uint64_t* s1) {
+  const uint64_t tile = (uint64_t)PM_COMPACT_BLOCK * PM_COMPACT_ITEMS;
+  const uint64_t tiles = (h->genome_size + tile - 1) / tile, per = (tiles + n_ranks - 1) / n_ranks;
+  *s0 = std::min<uint64_t>(h->genome_size, (uint64_t)rank * per * tile);
+  *s1 = std::min<uint64_t>(h->genome_size, (uint64_t)(rank + 1) * per * tile);
+}
+
+int reduce_slice(pemap_ctx* h, const pm::PeerPtrs& peers, uint64_t s0, uint64_t s1) {
+  if (s1 > s0 && peers.n > 0) {
+    // word range [6 * s0, 6 * s1): s0 is a multiple of 2048; round the end up to 16 bytes (the array has 64 bytes of slack)
+    const uint64_t first = 6 * s0, n_words = (6 * (s1 - s0) + 3) & ~3ull;
+    pm::k_reduce_slice<<<h->sm_count * 8, 256, 0, h->stream>>>(h->d_counts, peers, first, n_words);
+    h->stats.launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return PEMAP_OK;
+}
+}  // namespace
+
+int pemap_counts_ipc_handle(pemap_t* h, void* handle64) {
+  if (!h || !handle64) return PEMAP_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  CK(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t hd;
+  CK(cudaIpcGetMemHandle(&hd, h->d_counts));
+  memcpy(handle64, &hd, 64);
+  return PEMAP_OK;
+}
+
+int pemap_reduce_scatter_ipc(pemap_t* h, const void* handles, int n_ranks, int rank, uint64_t* site_first, uint64_t* site_end) {
+  if (!h || !handles || n_ranks < 1 || n_ranks > 16 || rank < 0 || rank >= n_ranks) return PEMAP_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  pm::PeerPtrs peers;
+  peers.n = 0;
+  for (int r = 0; r < n_ranks; r++) {
+    if (r == rank) continue;
+    const std::string key((const char*)handles + 64 * (size_t)r, 64);
+    void* ptr = nullptr;
+    for (size_t k = 0; k < h->ipc_keys.size(); k++)
+      if (h->ipc_keys[k] == key) ptr = h->ipc_open[k];
+    if (!ptr) {
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, key.data(), 64);
+      CK(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+      h->ipc_keys.push_back(key);
+      h->ipc_open.push_back(ptr);
+    }
+    peers.p[peers.n++] = (const uint32_t*)ptr;
+  }
+  uint64_t s0, s1;
+  slice_of(h, n_ranks, rank, &s0, &s1);
+  if (site_first) *site_first = s0;
+  if (site_end) *site_end = s1;
+  return reduce_slice(h, peers, s0, s1);
+}
+
+int pemap_reduce_scatter_local(pemap_t* const* hs, int n, int which, uint64_t* site_first, uint64_t* site_end) {
+  if (!hs || n < 1 || n > 16 || which < 0 || which >= n || !hs[which]) return PEMAP_ERR_ARG;
+  pemap_ctx* h = hs[which];
+  CK(cudaSetDevice(h->device));
+  pm::PeerPtrs peers;
+  peers.n = 0;
+  for (int r = 0; r < n; r++) {
+    if (r == which) continue;
+    if (!hs[r] || hs[r]->genome_size != h->genome_size) return fail(h, PEMAP_ERR_ARG, "handles index different genomes");
+    if (hs[r]->device != h->device) {
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, h->device, hs[r]->device));
+      if (!can) return fail(h, PEMAP_ERR_UNSUPPORTED, "no peer access between the two devices");
+      cudaError_t e = cudaDeviceEnablePeerAccess(hs[r]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(h, PEMAP_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    peers.p[peers.n++] = hs[r]->d_counts;
+  }
+  uint64_t s0, s1;
+  slice_of(h, n, which, &s0, &s1);
+  if (site_first) *site_first = s0;
+  if (site_end) *site_end = s1;
+  return reduce_slice(h, peers, s0, s1);
+}
+
 int pemap_stream(pemap_t* h, void** stream) {
   if (!h || !stream) return PEMAP_ERR_ARG;
   *stream = (void*)h->stream;
@@ -1803,6 +1901,7 @@ void pemap_destroy(pemap_t* h) {
                    h->d_replay_tasks, h->d_diag_winners, h->d_exact_winners, h->d_oob_winners, h->d_flagq, h->d_walk_meta, h->d_pair_codes, h->d_sw_list};
     for (void* p : dev)
       if (p) cudaFree(p);
+    for (void* p : h->ipc_open) cudaIpcCloseMemHandle(p);
     void* rbi[] = {h->d_rbi_data[0], h->d_rbi_data[1], h->d_rbi_data[2], h->d_rbi_data[3], h->d_rbi_dir[0], h->d_rbi_dir[1],
                    h->d_rbi_dir[2], h->d_rbi_dir[3], h->d_big_list, h->d_big_list2, h->d_big_scratch};
     for (void* p : rbi)

@@ -250,6 +250,26 @@ __global__ void __launch_bounds__(256) k_add_peer_counts(uint32_t* counts, const
   for (uint64_t i = (n4 << 2) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) counts[i] += peer[i];
 }
 
+// counts[w] += sum over peers of peer[w] for the words [first, first + n) of this GPU's slice: the peers' arrays are
+// mapped through NVLink (CUDA IPC or in-process peer access), 16-byte loads, up to 15 peers
+struct PeerPtrs {
+  const uint32_t* p[15];
+  int n;
+};
+__global__ void __launch_bounds__(256) k_reduce_slice(uint32_t* counts, PeerPtrs peers, uint64_t first, uint64_t n_words) {
+  const uint64_t n4 = n_words >> 2;  // first and n_words are multiples of 4 (slices are cut at compaction tiles)
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint4* mine = reinterpret_cast<uint4*>(counts + first);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    uint4 c = mine[i];
+    for (int k = 0; k < peers.n; k++) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(peers.p[k] + first) + i);
+      c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+    }
+    mine[i] = c;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Device index build: what index_genome_whole.c computes (169-177 codes, 248-299 rolling k-mer with N reset,
 // 213-216/271 index coordinates, 334-342 prefix table), as data-parallel passes.

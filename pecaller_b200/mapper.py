@@ -58,7 +58,8 @@ SITE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)  # pemap_site
 
 EXPORTS = ["pemap_version", "pemap_default_params", "pemap_init", "pemap_init_from_genome", "pemap_set_params",
            "pemap_map_batch", "pemap_map_batch_rows", "pemap_map_batch_device", "pemap_keep", "pemap_get_detail",
-           "pemap_get_candidates", "pemap_finish", "pemap_finish_stream", "pemap_get_insertions", "pemap_reset_counts", "pemap_counts_device", "pemap_get_stats",
+           "pemap_get_candidates", "pemap_finish", "pemap_finish_stream", "pemap_finish_stream_range", "pemap_get_insertions", "pemap_counts_ipc_handle",
+           "pemap_reduce_scatter_ipc", "pemap_reduce_scatter_local", "pemap_reset_counts", "pemap_counts_device", "pemap_get_stats",
            "pemap_reset_stats", "pemap_stream", "pemap_reduce_counts_peer", "pemap_index_device", "pemap_read_pos_index", "pemap_read_mers", "pemap_last_error",
            "pemap_destroy"]
 
@@ -93,6 +94,10 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.pemap_finish.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.POINTER(Insertion)),
                                C.POINTER(C.c_uint64)]
     L.pemap_finish_stream.argtypes = [vp, SITE_CB, vp, C.POINTER(C.c_uint64)]
+    L.pemap_finish_stream_range.argtypes = [vp, C.c_uint64, C.c_uint64, SITE_CB, vp, C.POINTER(C.c_uint64)]
+    L.pemap_counts_ipc_handle.argtypes = [vp, vp]
+    L.pemap_reduce_scatter_ipc.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.pemap_reduce_scatter_local.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.pemap_get_insertions.argtypes = [vp, C.POINTER(C.POINTER(Insertion)), C.POINTER(C.c_uint64)]
     L.pemap_reset_counts.argtypes = [vp]
     L.pemap_counts_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
@@ -268,17 +273,40 @@ class PEMapper:
         insertions = [(int(ins[i].pos), ins[i].seq.decode()) for i in range(nins.value)]
         return records, insertions
 
-    def finish_stream(self, consume=None):
-        """pemap_finish_stream: `consume(records)` is called with every window's RECORD_DTYPE view (valid only during
-        the call) in ascending position; returns the number of records.  consume=None only counts."""
+    def finish_stream(self, consume=None, site_range=None):
+        """pemap_finish_stream(_range): `consume(records)` is called with every window's RECORD_DTYPE view (valid only
+        during the call) in ascending position; returns the number of records.  consume=None only counts."""
         def cb(_ctx, ptr, n):
             if consume is not None:
                 buf = (C.c_char * (16 * n)).from_address(ptr)
                 consume(np.frombuffer(buf, dtype=RECORD_DTYPE))
             return 0
         total = C.c_uint64()
-        self._ck(self._L.pemap_finish_stream(self._h, SITE_CB(cb), None, C.byref(total)))
+        if site_range is None:
+            self._ck(self._L.pemap_finish_stream(self._h, SITE_CB(cb), None, C.byref(total)))
+        else:
+            self._ck(self._L.pemap_finish_stream_range(self._h, site_range[0], site_range[1], SITE_CB(cb), None, C.byref(total)))
         return total.value
+
+    def counts_ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self._L.pemap_counts_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def reduce_scatter_ipc(self, handles: list, rank: int):
+        """handles: every rank's counts_ipc_handle() in rank order.  -> (site_first, site_end) of this rank's slice."""
+        blob = b"".join(handles)
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.pemap_reduce_scatter_ipc(self._h, blob, len(handles), rank, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    @staticmethod
+    def reduce_scatter_local(mappers: list, which: int):
+        L = mappers[0]._L
+        arr = (C.c_void_p * len(mappers))(*[m._h for m in mappers])
+        a, b = C.c_uint64(), C.c_uint64()
+        mappers[which]._ck(L.pemap_reduce_scatter_local(arr, len(mappers), which, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def insertions(self):
         ins = C.POINTER(Insertion)()

@@ -67,6 +67,30 @@ class CountReducer:
             w.wait()
 
 
+class SliceReducer:
+    """One process per GPU: the counters are summed slice-wise over NVLink peer memory (pemap_reduce_scatter_ipc) - every
+    rank pulls the other ranks' counters of ITS 1/world of the genome and then compacts that slice itself, so neither
+    the sum nor the writer's compaction is serialised on one GPU.  The 64-byte IPC handles are exchanged once."""
+
+    def __init__(self, mapper, group=None):
+        import torch.distributed as dist
+        self.mapper = mapper
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mapper.counts_ipc_handle(), group=group)
+        self.handles = handles
+
+    def reduce_scatter(self):
+        """-> (site_first, site_end) of this rank's slice, now holding the global sum.  Collective: every rank calls it."""
+        import torch.distributed as dist
+        dist.barrier(group=self.group)          # every rank has finished mapping into its own array
+        rng = self.mapper.reduce_scatter_ipc(self.handles, self.rank)
+        dist.barrier(group=self.group)          # nobody resets or maps again while a peer is still reading
+        return rng
+
+
 def gather_results(n_reads: int, ranges, m1, m2, mapping_type, dst: int = 0, group=None):
     """Rebuild the per-read arrays of the whole input on rank `dst` from every rank's shard results.
     ranges: this rank's [(start, stop)] from shard_batches; m1/m2/mapping_type: its results, concatenated in that

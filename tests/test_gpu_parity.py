@@ -344,13 +344,29 @@ def _two_gpu_worker(rank, world, port, out_path):
     ranges = sharding.shard_batches(n, rank, world, 4096)
     parts = [mapper.map_batch(run.reads1[a:b], run.reads2[a:b]) for a, b in ranges]
     m1, m2, ty = (np.concatenate([p[k] for p in parts]) for k in range(3))
-    sharding.reduce_counts(sharding.counts_tensor(mapper, torch.device("cuda", rank)), dst=0)
+    # (a) slice-wise sum over NVLink peer memory: every rank ends up with the final counters of its slice and compacts it
+    red = sharding.SliceReducer(mapper)
+    lo, hi = red.reduce_scatter()
+    parts_rec = []
+    mapper.finish_stream(lambda r: parts_rec.append(r.copy()), site_range=(lo, hi))
+    mine = np.concatenate(parts_rec) if parts_rec else np.zeros(0, dtype=pb.RECORD_DTYPE)
+    all_rec = [None] * world
+    dist.all_gather_object(all_rec, mine)
+    # (b) NCCL sum onto rank 0, chromosome by chromosome (the slices above already hold sums: undo nothing, the reduce
+    # below runs on a second mapper's counters)
+    mapper2 = pb.PEMapper.from_genome(fx.genome, device=rank)
+    mapper2.set_params(**kw)
+    for a, b in ranges:
+        mapper2.map_batch(run.reads1[a:b], run.reads2[a:b])
+    sharding.reduce_counts(sharding.counts_tensor(mapper2, torch.device("cuda", rank)), dst=0)
     torch.cuda.synchronize()
     res = sharding.gather_results(n, ranges, m1, m2, ty, dst=0)
-    rec, ins = mapper.finish()
+    rec, ins = mapper2.finish()
+    mapper2.close()
     all_ins = [None] * world
     dist.all_gather_object(all_ins, ins)
     if rank == 0:
+        assert np.concatenate(all_rec).tobytes() == rec.tobytes(), "slice-wise NVLink sum != NCCL reduce"
         np.savez(out_path, rec=rec, m1=res[0], m2=res[1], ty=res[2])
         import pickle
         pickle.dump(sorted(sum(all_ins, [])), open(out_path + ".ins", "wb"))
@@ -442,14 +458,28 @@ def test_peer_reduce_single_process(get_fixture):
     ra = a.map_batch(run.reads1[:n // 2], run.reads2[:n // 2])
     rb = b.map_batch(run.reads1[n // 2:n], run.reads2[n // 2:n])
     r1 = one.map_batch(run.reads1[:n], run.reads2[:n])
-    a.reduce_counts_from(b)
-    rec, ins_a = a.finish()
-    _, ins_b = b.finish()   # b's own records are not used; its insertion strings are
+    # slice-wise sum first (each GPU pulls its half from the other, then compacts it) ...
+    lo_a, hi_a = pb.PEMapper.reduce_scatter_local([a, b], 0)
+    lo_b, hi_b = pb.PEMapper.reduce_scatter_local([a, b], 1)
+    assert lo_a == 0 and hi_a == lo_b
+    sl = []
+    a.finish_stream(lambda r: sl.append(r.copy()), site_range=(lo_a, hi_a))
+    b.finish_stream(lambda r: sl.append(r.copy()), site_range=(lo_b, hi_b))
+    rec_slices = np.concatenate(sl)
+    ins_a, ins_b = a.insertions(), b.insertions()
     rec1, ins1 = one.finish()
     for k in range(3):
         assert np.array_equal(np.concatenate([ra[k], rb[k]]), r1[k])
-    assert rec.tobytes() == rec1.tobytes()
+    assert rec_slices.tobytes() == rec1.tobytes()
     assert sorted(ins_a + ins_b) == sorted(ins1)
+    # ... and the older whole-array form on fresh counters: b's array added onto a's
+    for m in (a, b):
+        m.reset_counts()
+    a.map_batch(run.reads1[:n // 2], run.reads2[:n // 2])
+    b.map_batch(run.reads1[n // 2:n], run.reads2[n // 2:n])
+    a.reduce_counts_from(b)
+    rec, _ = a.finish()
+    assert rec.tobytes() == rec1.tobytes()
     for m in (a, b, one):
         m.close()
 
