@@ -16,6 +16,7 @@
 #ifndef PEMAP_H
 #define PEMAP_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -209,6 +210,12 @@ int pemap_reduce_scatter_local(pemap_t *const *hs, int n, int which, uint64_t *s
 /* pemap_finish_stream restricted to the sites [site_first, site_end). */
 int pemap_finish_stream_range(pemap_t *h, uint64_t site_first, uint64_t site_end, pemap_site_cb cb, void *ctx,
                               uint64_t *n_records);
+
+/* Page-locked host memory for the batch buffers (read rows, lengths, m1/m2/mapping_type): buffers from here are DMA'd in
+   place by pemap_map_batch_rows instead of being staged through the library's own pinned buffers.  The FASTQ reader
+   of the C host fills such rows directly.  NULL when the allocation fails. */
+void *pemap_host_alloc(size_t bytes);
+void pemap_host_free(void *p);
 
 /* The CUDA stream (cudaStream_t as void*) all of this handle's work is issued on, so that a caller can bracket
    calls with its own events. */

@@ -1827,6 +1827,19 @@ int pemap_reduce_scatter_local(pemap_t* const* hs, int n, int which, uint64_t* s
   return reduce_slice(h, peers, s0, s1);
 }
 
+void* pemap_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void pemap_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int pemap_stream(pemap_t* h, void** stream) {
   if (!h || !stream) return PEMAP_ERR_ARG;
   *stream = (void*)h->stream;

@@ -30,6 +30,9 @@
 #define PM_RBI_EMPTY 0xFFFFFFFFu
 #define PM_RBI_MARK 0xFFFFFFFEu
 #define PM_RBI_CAP 512                  // entries of one strand kept in shared memory (a 150-bp read on 3.1 Gb has ~360)
+#ifndef PM_RBI_EXPERIMENT
+#define PM_RBI_EXPERIMENT 0
+#endif
 #define PM_RBI_CAP2 2048                // second pass: strands of reads that sit in repeats
 #define PM_RBI_MAXB (4 * PM_MAX_SEG)    // buckets per strand
 #define PM_RBI_BIG_CAP 98304            // >= 19 segments * 49 * 99 positions: the slow path holds any strand
@@ -324,10 +327,28 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
             const uint32_t q = q0 + (uint32_t)(8 * u + l8);
             T[u] = etagx ^ 0x0F0F0F0Fu;  // two fields away: never qualifies (P[u] is then never looked at)
             if (q < n4) {
+#if PM_RBI_EXPERIMENT == 2   /* timing experiment: no bucket loads, pseudo-random tags and positions */
+              uint32_t x = (q + sm.b_off[b]) * 0x9E3779B1u;
+              x ^= x >> 15;
+              x *= 0x85EBCA77u;
+              T[u] = x ^ (x >> 13);
+              P[u] = make_uint4(x & 0x7FFFFFFFu, (x * 3u) & 0x7FFFFFFFu, (x * 5u) & 0x7FFFFFFFu, (x * 7u) & 0x7FFFFFFFu);
+#else
               P[u] = rbi_ld16(base + q);
               T[u] = rbi_ld4(tags + q);
+#endif
             }
           }
+#if PM_RBI_EXPERIMENT == 1   /* timing experiment: the bucket loads alone */
+          {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int u = 0; u < PM_RBI_UNROLL; u++)
+              if (q0 + (uint32_t)(8 * u + l8) < n4) acc ^= P[u].x ^ P[u].y ^ P[u].z ^ P[u].w ^ T[u];
+            if (acc == 0x12345678u) overflow = true;
+            continue;
+          }
+#endif
 #pragma unroll
           for (int u = 0; u < PM_RBI_UNROLL; u++) {
             // per tag byte: fields that differ from the exact tag; a byte qualifies when at most one field differs
