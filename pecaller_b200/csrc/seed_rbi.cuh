@@ -304,8 +304,68 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
 
     for (int strand = 0; strand < 2; strand++) {
       if (strand == 1 && tot >= a.p.max_hits) break;  // 1658
+      // ---- hash of the entries by diagonal / 16.  Shared-memory paths: a slot word holds the chain head (low bits, all
+      // ones = none) and the set of segments hashed into the slot (bit 13 + segment); BIG: the head index alone.
+      constexpr uint32_t HNIL = IMASK;
+      auto build_hash = [&](const int n_entries) {
+        for (uint32_t i = 4u * lane; i <= tab_mask; i += 128)
+          *reinterpret_cast<uint4*>(st_head + i) = make_uint4(HNIL, HNIL, HNIL, HNIL);
+        __syncwarp();
+        for (int e = lane; e < n_entries; e += 32) {
+          const int s = st_seg[e];
+          const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
+          const uint32_t bin = (uint32_t)(((unsigned long long)st_pos[e] + 512ull - off) >> 4);
+          uint32_t* hp = &st_head[rbi_hash(bin, tab_mask)];
+          uint32_t old;
+          if (BIG) {
+            old = atomicExch(hp, (uint32_t)e);
+          } else {
+            old = *hp;
+            uint32_t assumed;
+            do {
+              assumed = old;
+              old = atomicCAS(hp, assumed, (assumed & 0xFFFFE000u) | (1u << (13 + s)) | (uint32_t)e);
+            } while (old != assumed);
+            old &= IMASK;
+          }
+          st_next[e] = old == HNIL ? NIL : (NextT)old;
+        }
+        __syncwarp();
+      };
+      // Is there a pair of entries of two different segments whose diagonals lie within 2 * (max_off - 1) of each other?
+      // An anchor with `found` = F has F of the nseg segments agreeing within max_off - 1 of its diagonal, so at most
+      // nseg - F segments are outside the chain and ANY nseg - F + 2 segments hold two of its members: without such a
+      // pair among the first nseg - F + 2 segments no anchor of the strand reaches F.
+      auto close_pair_exists = [&](const int n_entries) {
+        bool yes = false;
+        for (int e = lane; e < n_entries; e += 32) {
+          const int s = st_seg[e];
+          const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
+          const long long dg = (long long)st_pos[e] + 512ll - (long long)off;
+          const uint32_t bin = (uint32_t)(dg >> 4);
+#pragma unroll
+          for (int db = -2; db <= 2; db++) {
+            uint32_t q = st_head[rbi_hash(bin + (uint32_t)db, tab_mask)] & IMASK;
+            while (q != HNIL) {
+              const int sq = st_seg[q];
+              if (sq != s) {
+                const uint32_t offq = (sq < total_cuts) ? 16u * (uint32_t)sq : (uint32_t)(len - 16);
+                const long long d = (long long)st_pos[q] + 512ll - (long long)offq - dg;
+                if (d > -2ll * mo + 1 && d < 2ll * mo - 1) yes = true;
+              }
+              const NextT nx = st_next[q];
+              q = nx == NIL ? HNIL : (uint32_t)nx;
+            }
+          }
+        }
+        return __any_sync(0xFFFFFFFFu, yes) != 0;
+      };
       // ---- gather (get_mers 2158-2165, loop 1594-1612 / 1619-1637): per segment, every entry of its four buckets whose
       // tag is the segment's tag or one 2-bit field away from it
+      // With the running min_match at F the first nseg - F + 2 segments decide whether the strand can matter at all (see
+      // close_pair_exists): after a full-length hit on the forward strand the reverse strand is settled by two segments.
+      const int k_probe = nseg - min_match + 2 <= nseg / 2 ? nseg - min_match + 2 : 0;
+      bool strand_dead = false;
       int cnt = 0;              // warp-uniform copy of sm.g.n_ent between segments
       uint32_t min_spots = 10000;
       bool overflow = false;
@@ -400,6 +460,18 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
         if (lane == 0) sm.g.n_ent = (uint32_t)cnt;
         __syncwarp();
         min_spots = min(min_spots, (uint32_t)(cnt - cnt0));
+        if (s + 1 == k_probe && min_spots <= (uint32_t)a.p.max_hits && !__any_sync(0xFFFFFFFFu, overflow)) {
+          // (min_spots <= max_hits: the rule of 2200-2207 cannot fire whatever the other segments hold)
+          build_hash(cnt);
+          if (!close_pair_exists(cnt)) {
+            strand_dead = true;
+            break;
+          }
+        }
+      }
+      if (strand_dead) {  // no anchor of this strand reaches min_match: the strand leaves the hit list as it is
+        l_pos += (unsigned long long)cnt;
+        continue;
       }
       if (__any_sync(0xFFFFFFFFu, overflow)) {
         if (!BIG) return false;  // the BIG stores hold 19 * 49 * 99 entries
@@ -413,32 +485,7 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
         continue;
       }
 
-      // ---- hash the entries by diagonal / 16.  Shared-memory paths: a slot word holds the chain head (low bits, all
-      // ones = none) and the set of segments hashed into the slot (bit 13 + segment); BIG: the head index alone.
-      constexpr uint32_t HNIL = IMASK;
-      for (uint32_t i = 4u * lane; i <= tab_mask; i += 128)
-        *reinterpret_cast<uint4*>(st_head + i) = make_uint4(HNIL, HNIL, HNIL, HNIL);
-      __syncwarp();
-      for (int e = lane; e < N; e += 32) {
-        const int s = st_seg[e];
-        const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
-        const uint32_t bin = (uint32_t)(((unsigned long long)st_pos[e] + 512ull - off) >> 4);
-        uint32_t* hp = &st_head[rbi_hash(bin, tab_mask)];
-        uint32_t old;
-        if (BIG) {
-          old = atomicExch(hp, (uint32_t)e);
-        } else {
-          old = *hp;
-          uint32_t assumed;
-          do {
-            assumed = old;
-            old = atomicCAS(hp, assumed, (assumed & 0xFFFFE000u) | (1u << (13 + s)) | (uint32_t)e);
-          } while (old != assumed);
-          old &= IMASK;
-        }
-        st_next[e] = old == HNIL ? NIL : (NextT)old;
-      }
-      __syncwarp();
+      build_hash(N);
       // ---- found count of every entry as an anchor (2230-2249): later segments with a position whose diagonal is
       // within max_off - 1 of the anchor's.  The segments present in the three slots around the anchor bound it from
       // above; only anchors whose bound reaches min_match (the read's true locus, rarely a chance cluster) walk the chains.

@@ -156,3 +156,14 @@ def test_index_genome_gpu_files_match_reference(get_fixture, tmp_path):
                     h.update(b)
                     n += len(b)
             assert n == meta["idx_bytes"] and h.hexdigest() == meta["idx_sha256"], name + ": inflated .idx"
+            # the drop-in path: pemapper_gpu WITHOUT PEMAP_DEVICE_INDEX loads these .idx / .mdx files as the reference's
+            # init_index_buffer does (pemapper.c:2129-2155) and hands the host arrays to pemap_init
+            run = next(r for r in fx.runs if gio.have(name, r.name) and not r.paired)
+            synth.write_fastq(os.path.join(work, "q.fq"), run.reads1)
+            env2 = {k: v for k, v in os.environ.items() if k != "PEMAP_DEVICE_INDEX"}
+            r = subprocess.run([CLI, "q", "g.sdx", "s", "q.fq", "y" if run.bisulfite else "n", repr(run.min_align), "4",
+                                str(run.reads1.shape[0] + 8)], cwd=work, env=env2, capture_output=True, text=True, timeout=900)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            assert np.array_equal(np.fromfile(os.path.join(work, "q.fq.mfile"), dtype=np.uint32), gio.mfile(name, run.name, 1))
+            raw = gzip.open(os.path.join(work, "q.pileup.gz"), "rb").read()
+            assert hashlib.sha256(raw).hexdigest() == gio.pileup_meta(name, run.name)["sha256"], "pileup through pemap_init"
