@@ -211,6 +211,17 @@ int pemap_reduce_scatter_local(pemap_t *const *hs, int n, int which, uint64_t *s
 int pemap_finish_stream_range(pemap_t *h, uint64_t site_first, uint64_t site_end, pemap_site_cb cb, void *ctx,
                               uint64_t *n_records);
 
+/* BASELINE configs[3], the Smith-Waterman kernel alone: read i (forward orientation) is scored against the window
+   genome[win_start[i] .. win_start[i] + win_len[i]) with the mapper's own integer kernel (smith_waterman_align,
+   pemapper.c:1694-1748, in units of 1/36), for windows of up to PEMAP_SW_MAX_WINDOW rows - the reference's 300 x 300
+   buffers stop at len + 21.  All pointers are device pointers; outputs are the score * 36, start[1] (maxi), start[0]
+   (maxk) and the tie flags (bit 0: the last-column maximum is not unique in exact arithmetic; may be NULL); *ms is the
+   kernel's time from CUDA events.  Does not touch the pileup counters. */
+#define PEMAP_SW_MAX_WINDOW 1056
+int pemap_sw_score_device(pemap_t *h, int n, const char *d_reads, const int *d_len, int stride, int max_len,
+                          const uint32_t *d_win_start, const int *d_win_len, int max_window, int32_t *d_score36,
+                          int32_t *d_maxi, int32_t *d_maxk, int32_t *d_flags, float *ms);
+
 /* Page-locked host memory for the batch buffers (read rows, lengths, m1/m2/mapping_type): buffers from here are DMA'd in
    place by pemap_map_batch_rows instead of being staged through the library's own pinned buffers.  The FASTQ reader
    of the C host fills such rows directly.  NULL when the allocation fails. */

@@ -561,6 +561,49 @@ double orc_sw_align(const orc_ctx *c, uint32_t win_start, int blen, const char *
   return r;
 }
 
+/* smith_waterman_align (pemapper.c:1694-1748) for windows beyond the reference's 300 x 300 buffers: the same
+   recurrence (1710-1713), borders (2062-2081: column 0 = 0 / 0 / -go, row 0 = the c->border values, which the
+   reference only defines for j < 300, i.e. reads up to 299 bases) and last-column scan (1717-1742), with the three
+   matrices allocated for the window at hand.  BASELINE configs[3] (1000-bp windows) has no reference result to be
+   pinned to - the reference overruns its buffers there - so this restatement IS the checker for that shape; for
+   windows that fit it returns what orc_sw_align returns (tests/test_oracle_golden.py). */
+double orc_sw_align_long(const orc_ctx *c, uint32_t win_start, int blen, const char *seq, int mm, int *start3) {
+  const double go = c->go, ge = c->ge;
+  const size_t W = (size_t)mm + 1;
+  double *S0 = malloc(sizeof(double) * 3 * W * ((size_t)blen + 1));
+  double *S1 = S0 + W * ((size_t)blen + 1), *S2 = S1 + W * ((size_t)blen + 1);
+  const char *ref = c->genome + win_start;
+  for (int i = 0; i <= blen; i++) {
+    S0[i * W] = 0.0;
+    S1[i * W] = 0.0;
+    S2[i * W] = -1.0 * go;
+  }
+  for (int j = 1; j <= mm; j++) S0[j] = S1[j] = S2[j] = c->border[j];
+  for (int i = 1; i <= blen; i++) {
+    const double *brow = c->bonus[(unsigned char)ref[i - 1] & 127];
+    for (int j = 1; j <= mm; j++) {
+      S2[i * W + j] = MAXD(S0[i * W + j - 1] - go, S2[i * W + j - 1] - ge);
+      S1[i * W + j] = MAXD(S0[(i - 1) * W + j] - go, S1[(i - 1) * W + j] - ge);
+      const double bump = brow[(unsigned char)seq[j - 1] & 127];
+      S0[i * W + j] = MAXD(MAXD(S0[(i - 1) * W + j - 1] + bump, S1[(i - 1) * W + j - 1] + bump), S2[(i - 1) * W + j - 1] + bump);
+    }
+  }
+  const double *M[3] = {S0, S1, S2};
+  int bk = 0, bi = 0;
+  for (int i = 1; i <= blen; i++)
+    for (int k = 0; k < 3; k++)
+      if (M[k][i * W + mm] > M[bk][bi * W + mm]) {
+        bk = k;
+        bi = i;
+      }
+  start3[0] = bk;
+  start3[1] = bi;
+  start3[2] = mm;
+  const double r = M[bk][bi * W + mm];
+  free(S0);
+  return r;
+}
+
 /* ---------------------------------------------------------------- traceback + pileup */
 
 static void add_insertion(orc_ctx *c, uint32_t pos, const char *rev_buf, int n) {

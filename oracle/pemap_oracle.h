@@ -71,6 +71,8 @@ int orc_write_index(const orc_ctx *c, const char *base, const char *const *names
 int orc_initial_map(const orc_ctx *c, const char *read, int len, uint32_t *spots, char *orients);
 int orc_window(const orc_ctx *c, uint32_t spot, int len, uint32_t *start, int *blen);
 double orc_sw_align(const orc_ctx *c, uint32_t win_start, int blen, const char *seq, int mm, int *start3);
+/* the same for windows longer than the reference's 300 x 300 buffers (BASELINE configs[3]) */
+double orc_sw_align_long(const orc_ctx *c, uint32_t win_start, int blen, const char *seq, int mm, int *start3);
 
 /* whole batch: reads are rows of a (n x stride) char matrix, NUL-terminated at len[i].
    reads2/len2 NULL for single-end.  Accumulates pileup counters + insertions in the context.

@@ -495,7 +495,7 @@ int build_rbi(pemap_ctx* h, uint32_t* code, const uint32_t* val, uint64_t n) {
     uint32_t total_units = 0;
     CKB(cudaMemcpyAsync(&total_units, h->d_rbi_dir[g] + (1u << 24), 4, cudaMemcpyDeviceToHost, h->stream));
     CKB(cudaStreamSynchronize(h->stream));
-    const size_t bytes = ((size_t)total_units + 4) * 16;  // the gather may touch the unit after a bucket's last tag word
+    const size_t bytes = ((size_t)total_units + 1) * PM_RBI_BLOCK_BYTES;
     CKB(cudaMalloc(&h->d_rbi_data[g], bytes));
     CKB(cudaMemsetAsync(h->d_rbi_data[g], 0xFF, bytes, h->stream));
     if (ne) pm::k_rbi_fill<<<eblk, 256, 0, h->stream>>>(kk, vv, ne, bstart, h->d_rbi_dir[g], h->d_rbi_data[g]);
@@ -1310,6 +1310,17 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
 
 }  // namespace
 
+namespace {
+template <int G, int WD>
+void launch_sw_long(pemap_ctx* h, const pm::SwIntArgs& a) {
+  static int grids[kMaxDev] = {};
+  int& grid = grids[h->device % kMaxDev];
+  if (!grid) grid = one_wave_grid(h, pm::k_sw_i16<G, WD, -1, PEMAP_SW_MAX_WINDOW>, 128, 0);
+  pm::k_sw_i16<G, WD, -1, PEMAP_SW_MAX_WINDOW><<<grid, 128, 0, h->stream>>>(a);
+}
+}  // namespace
+
+
 // ------------------------------------------------------------------------------------------------- C-ABI
 
 extern "C" {
@@ -1825,6 +1836,49 @@ int pemap_reduce_scatter_local(pemap_t* const* hs, int n, int which, uint64_t* s
   if (site_first) *site_first = s0;
   if (site_end) *site_end = s1;
   return reduce_slice(h, peers, s0, s1);
+}
+
+int pemap_sw_score_device(pemap_t* h, int n, const char* d_reads, const int* d_len, int stride, int max_len,
+                          const uint32_t* d_win_start, const int* d_win_len, int max_window, int32_t* d_score36, int32_t* d_maxi,
+                          int32_t* d_maxk, int32_t* d_flags, float* ms) {
+  if (!h || n < 0 || !d_reads || !d_len || !d_win_start || !d_win_len || !d_score36 || !d_maxi || !d_maxk)
+    return fail(h, PEMAP_ERR_ARG, "NULL argument");
+  if (h->index_only) return fail(h, PEMAP_ERR_ARG, "handle was opened with PEMAP_INDEX_ONLY=1");
+  if (max_len < 16 || max_len > PM_DP_MAX - 22) return fail(h, PEMAP_ERR_ARG, "max_len out of range");
+  if (max_window < 1 || max_window > PEMAP_SW_MAX_WINDOW) return fail(h, PEMAP_ERR_ARG, "window longer than PEMAP_SW_MAX_WINDOW");
+  if ((uint32_t)n > h->task_cap) return fail(h, PEMAP_ERR_ARG, "more pairs than the task buffers of a chunk hold");
+  CK(cudaSetDevice(h->device));
+  const uint32_t nn = (uint32_t)n;
+  CK(cudaMemsetAsync(h->d_cursors, 0, 128, h->stream));
+  CK(cudaMemcpyAsync(h->d_cursors, &nn, 4, cudaMemcpyHostToDevice, h->stream));
+  if (n) pm::k_sw_bench_tasks<<<(n + 255) / 256, 256, 0, h->stream>>>(n, d_win_start, d_win_len, h->d_tasks);
+  pm::SwIntArgs ia;
+  ia.tasks = h->d_tasks;
+  ia.results = h->d_ires;
+  ia.n_items = h->d_cursors;
+  ia.work = h->d_cursors + 10;
+  ia.reads[0] = d_reads;
+  ia.reads[1] = d_reads;
+  ia.len[0] = d_len;
+  ia.len[1] = d_len;
+  ia.stride = stride;
+  ia.genome = h->d_genome;
+  ia.lane_mm = -1;
+  ia.p = h->dp;
+  ia.list = nullptr;
+  cudaEvent_t e0 = h->slots[0].ev[0], e1 = h->slots[0].ev[1];
+  CK(cudaEventRecord(e0, h->stream));
+  if (max_len <= 112) launch_sw_long<16, 7>(h, ia);
+  else if (max_len <= 160) launch_sw_long<16, 10>(h, ia);
+  else if (max_len <= 256) launch_sw_long<32, 8>(h, ia);
+  else launch_sw_long<32, 10>(h, ia);
+  CK(cudaEventRecord(e1, h->stream));
+  if (n) pm::k_sw_bench_results<<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->d_ires, d_score36, d_maxi, d_maxk, d_flags);
+  h->stats.launches += 3;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  if (ms) CK(cudaEventElapsedTime(ms, e0, e1));
+  return PEMAP_OK;
 }
 
 void* pemap_host_alloc(size_t bytes) {

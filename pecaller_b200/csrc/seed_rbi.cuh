@@ -15,9 +15,10 @@
 // isolated accesses.  A k-mer with >= too_many_spots positions is stored as ONE marker entry (its positions are never
 // used: 1602-1606 empties the segment).  Nothing is approximated: every position of every one of the 49 lists comes out.
 //
-// Bucket layout (16-byte units): n4 = ceil(n / 4) units of 4 positions each, then ceil(n4 / 4) units holding the n tags
-// (unit S = n4 + ceil(n4/4) per bucket, so n4 = S - ceil(S/5) follows from two directory words).  Unused slots hold
-// PM_RBI_EMPTY.
+// Bucket layout: 80-byte blocks of 16 entries - four quads of positions (64 bytes) followed by their 16 tags - so that
+// a bucket is ONE contiguous run that the lanes read front to back (isolated pieces are what HBM serves slowly:
+// chunk_probe_r02.json; with tags behind all positions the same loads ran at 3.2 TB/s, profiles/README_r02.md).  The
+// directory counts blocks.  Unused slots of the last block hold PM_RBI_EMPTY.
 //
 // Chaining: the reference sorts every segment list and, per anchor, scans the later lists for a position whose
 // diagonal (pos - segment offset) is within +-11 of the anchor's.  Here the entries of a strand are hashed by
@@ -30,6 +31,9 @@
 #define PM_RBI_EMPTY 0xFFFFFFFFu
 #define PM_RBI_MARK 0xFFFFFFFEu
 #define PM_RBI_CAP 512                  // entries of one strand kept in shared memory (a 150-bp read on 3.1 Gb has ~360)
+#ifndef PM_RBI_PREFETCH
+#define PM_RBI_PREFETCH 2               // segments whose buckets are prefetched into L2 ahead of the one being read
+#endif
 #ifndef PM_RBI_EXPERIMENT
 #define PM_RBI_EXPERIMENT 0
 #endif
@@ -49,14 +53,14 @@ __host__ __device__ __forceinline__ uint32_t rbi_bucket(uint32_t code, int g) {
   const uint32_t hi = g == 3 ? 0u : (code >> (8 * g + 8));
   return (hi << (8 * g)) | lo;
 }
-__host__ __device__ __forceinline__ uint32_t rbi_units(uint32_t n) {  // 16-byte units of a bucket with n entries
-  const uint32_t n4 = (n + 3u) >> 2;
-  return n4 + ((n4 + 3u) >> 2);
+#define PM_RBI_BLOCK_BYTES 80            // 16 positions + 16 tags
+__host__ __device__ __forceinline__ uint32_t rbi_units(uint32_t n) {  // blocks of a bucket with n entries
+  return (n + 15u) >> 4;
 }
 
 struct RbiIndex {
   const uint4* data[4];     // bucket arrays of the four rotations
-  const uint32_t* dir[4];   // 2^24+1 offsets each, in 16-byte units
+  const uint32_t* dir[4];   // 2^24+1 offsets each, in 80-byte blocks
 };
 
 // ------------------------------------------------------------------------------------------------ builder kernels
@@ -126,10 +130,10 @@ __global__ void __launch_bounds__(256) k_rbi_fill(const uint32_t* key, const uin
   if (i >= n) return;
   const uint32_t k = key[i], b = k >> 8;
   const uint32_t first = bstart[b], nb = bstart[b + 1] - first, r = (uint32_t)(i - first);
-  const uint64_t base = dir[b];
-  const uint32_t n4 = (nb + 3u) >> 2;
-  reinterpret_cast<uint32_t*>(data)[base * 4 + r] = val[i];
-  reinterpret_cast<unsigned char*>(data)[(base + n4) * 16 + r] = (unsigned char)(k & 255u);
+  (void)nb;
+  unsigned char* blk = reinterpret_cast<unsigned char*>(data) + ((uint64_t)dir[b] + (r >> 4)) * PM_RBI_BLOCK_BYTES;
+  reinterpret_cast<uint32_t*>(blk)[r & 15u] = val[i];
+  blk[64 + (r & 15u)] = (unsigned char)(k & 255u);
 }
 
 // ------------------------------------------------------------------------------------------------ seed kernel
@@ -292,9 +296,8 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
       const uint32_t code = sm.kcode[b >> 2];
       const uint32_t bk = rbi_bucket(code, g);
       const uint32_t d0 = __ldg(a.ix.dir[g] + bk), d1 = __ldg(a.ix.dir[g] + bk + 1);
-      const uint32_t S = d1 - d0;
       sm.b_off[b] = d0;
-      sm.b_n4[b] = S - (S + 4u) / 5u;
+      sm.b_n4[b] = (uint16_t)(4u * (d1 - d0));  // quads of positions: four per block
     }
     __syncwarp();
     // lanes 8g..8g+7 read the bucket of rotation g
@@ -371,11 +374,29 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
       bool overflow = false;
       if (lane == 0) sm.g.n_ent = 0;
       __syncwarp();
+      // Bytes in flight, not bandwidth, bound the bucket reads (24 warps x 32 lanes x a few 16-byte registers keep
+      // HBM's queues too short for it to schedule well: 3.2 TB/s; the same reads issued 250 KB deep per SM reach
+      // 5.5-6 TB/s, tools/chunk_probe.cu).  So the buckets of the segments ahead are pulled into L2 by prefetches, one
+      // 128-byte line per lane and instruction, which cost neither registers nor shared memory.
+      auto prefetch_segment = [&](const int sp) {
+        if (sp >= nseg) return;
+        const int bp = 4 * (strand * nseg + sp) + rot;
+        const char* p0 = reinterpret_cast<const char*>(rdata + 5ull * sm.b_off[bp]);
+        const uint32_t bytes = 20u * sm.b_n4[bp];  // 80 bytes per block = 20 per quad
+        const char* line = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)127) + 128 * l8;
+        for (; line < p0 + bytes; line += 1024) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+      };
+#if PM_RBI_PREFETCH > 0
+      for (int sp = 0; sp < PM_RBI_PREFETCH; sp++)
+        if (k_probe == 0 || sp < k_probe) prefetch_segment(sp);
+#endif
       for (int s = 0; s < nseg; s++) {
+#if PM_RBI_PREFETCH > 0
+        if (k_probe == 0 || s + PM_RBI_PREFETCH < k_probe || s >= k_probe) prefetch_segment(s + PM_RBI_PREFETCH);
+#endif
         const int b = 4 * (strand * nseg + s) + rot;
         const uint32_t n4 = sm.b_n4[b];
-        const uint4* base = rdata + sm.b_off[b];
-        const uint32_t* tags = reinterpret_cast<const uint32_t*>(base + n4);
+        const uint4* base = rdata + 5ull * sm.b_off[b];  // 80-byte blocks
         const uint32_t etagx = ((sm.kcode[strand * nseg + s] >> (8 * rot)) & 255u) * 0x01010101u;
         const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, n4);
         const int cnt0 = cnt;
@@ -394,8 +415,9 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
               T[u] = x ^ (x >> 13);
               P[u] = make_uint4(x & 0x7FFFFFFFu, (x * 3u) & 0x7FFFFFFFu, (x * 5u) & 0x7FFFFFFFu, (x * 7u) & 0x7FFFFFFFu);
 #else
-              P[u] = rbi_ld16(base + q);
-              T[u] = rbi_ld4(tags + q);
+              const uint4* blk = base + 5u * (q >> 2);  // quad q: positions at 16 * (q & 3), its four tags at 64 + 4 * (q & 3)
+              P[u] = rbi_ld16(blk + (q & 3u));
+              T[u] = rbi_ld4(reinterpret_cast<const uint32_t*>(blk + 4) + (q & 3u));
 #endif
             }
           }

@@ -74,10 +74,12 @@ __device__ __forceinline__ void track_best(int v0, int v1, int v2, int dq, int i
 
 // CMM >= 0: every task of the launch has (len-1) % WD == CMM and (len-1) / WD == lane_mm (uniform read length);
 // CMM < 0: per-task lengths.
-template <int G, int WD, int CMM>
+// ROWCAP > 0: windows of up to ROWCAP rows (BASELINE configs[3] scores reads against 1000-bp windows; the mapper's
+// own windows are len + 21 rows).  The rows stream through the wavefront, so only the staged window grows.
+template <int G, int WD, int CMM, int ROWCAP = 0>
 __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
   constexpr int GPB = 128 / G;
-  constexpr int ROWS = (G * WD + 24 < PM_DP_MAX) ? G * WD + 24 : PM_DP_MAX;  // window rows: nn <= len + 21
+  constexpr int ROWS = ROWCAP > 0 ? ROWCAP : ((G * WD + 24 < PM_DP_MAX) ? G * WD + 24 : PM_DP_MAX);  // window rows: nn <= len + 21
   __shared__ uint32_t s_win[GPB][ROWS];
   __shared__ __align__(16) uint32_t s_last[CMM >= 0 ? GPB : 1][CMM >= 0 ? 4 * ROWS : 4];  // last read column of every row
   const int tid = threadIdx.x, grp = tid / G, gl = tid % G;
@@ -257,6 +259,28 @@ __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
       a.results[idB] = r;
     }
   }
+}
+
+// (read i, window i) -> Task i, and back: the microbenchmark entry pemap_sw_score_device
+__global__ void __launch_bounds__(256) k_sw_bench_tasks(int n, const uint32_t* win_start, const int* win_len, Task* tasks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Task t;
+  t.rm = 2u * (uint32_t)i;  // mate 0, forward orientation
+  t.spot = win_start[i];
+  t.wstart = win_start[i];
+  t.blen = win_len[i];
+  tasks[i] = t;
+}
+__global__ void __launch_bounds__(256) k_sw_bench_results(int n, const ITaskResult* res, int32_t* score36, int32_t* maxi, int32_t* maxk,
+                                                          int32_t* flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const ITaskResult r = res[i];
+  score36[i] = r.score36;
+  maxi[i] = r.maxi;
+  maxk[i] = r.maxk;
+  if (flags) flags[i] = r.flags;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -59,7 +59,7 @@ SITE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)  # pemap_site
 EXPORTS = ["pemap_version", "pemap_default_params", "pemap_init", "pemap_init_from_genome", "pemap_set_params",
            "pemap_map_batch", "pemap_map_batch_rows", "pemap_map_batch_device", "pemap_keep", "pemap_get_detail",
            "pemap_get_candidates", "pemap_finish", "pemap_finish_stream", "pemap_finish_stream_range", "pemap_get_insertions", "pemap_counts_ipc_handle",
-           "pemap_reduce_scatter_ipc", "pemap_reduce_scatter_local", "pemap_host_alloc", "pemap_host_free", "pemap_reset_counts", "pemap_counts_device", "pemap_get_stats",
+           "pemap_reduce_scatter_ipc", "pemap_reduce_scatter_local", "pemap_host_alloc", "pemap_host_free", "pemap_sw_score_device", "pemap_reset_counts", "pemap_counts_device", "pemap_get_stats",
            "pemap_reset_stats", "pemap_stream", "pemap_reduce_counts_peer", "pemap_index_device", "pemap_read_pos_index", "pemap_read_mers", "pemap_last_error",
            "pemap_destroy"]
 
@@ -98,6 +98,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.pemap_counts_ipc_handle.argtypes = [vp, vp]
     L.pemap_reduce_scatter_ipc.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.pemap_reduce_scatter_local.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.pemap_sw_score_device.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_float)]
     L.pemap_host_alloc.restype = vp
     L.pemap_host_alloc.argtypes = [C.c_size_t]
     L.pemap_host_free.argtypes = [vp]
@@ -248,6 +249,14 @@ class PEMapper:
     def map_device(self, n, d_r1, d_l1, d_r2, d_l2, stride, max_len, d_m1, d_m2, d_ty):
         """All arguments are raw device pointers (ints)."""
         self._ck(self._L.pemap_map_batch_device(self._h, n, d_r1, d_l1, d_r2, d_l2, stride, max_len, d_m1, d_m2, d_ty))
+
+    def sw_score_device(self, n, d_reads, d_len, stride, max_len, d_win_start, d_win_len, max_window, d_score36, d_maxi,
+                        d_maxk, d_flags=None) -> float:
+        """pemap_sw_score_device (raw device pointers); returns the kernel's milliseconds."""
+        ms = C.c_float()
+        self._ck(self._L.pemap_sw_score_device(self._h, n, d_reads, d_len, stride, max_len, d_win_start, d_win_len, max_window,
+                                               d_score36, d_maxi, d_maxk, d_flags, C.byref(ms)))
+        return ms.value
 
     def detail(self, n) -> np.ndarray:
         out = np.zeros(n, dtype=DETAIL_DTYPE)

@@ -68,6 +68,8 @@ def lib():
         L.orc_window.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
         L.orc_sw_align.restype = C.c_double
         L.orc_sw_align.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+        L.orc_sw_align_long.restype = C.c_double
+        L.orc_sw_align_long.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
         L.orc_map_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_count_sites.restype = C.c_uint64
@@ -169,6 +171,12 @@ class Oracle:
     def sw_align(self, win_start: int, blen: int, seq: bytes):
         st = (C.c_int * 3)()
         sc = self.L.orc_sw_align(self.ctx, win_start, blen, seq, len(seq), st)
+        return sc, (st[0], st[1], st[2])
+
+    def sw_align_long(self, win_start: int, blen: int, seq: bytes):
+        """the same recurrence for windows beyond the reference's 300 x 300 buffers (cfg4's 1000-bp windows)"""
+        st = (C.c_int * 3)()
+        sc = self.L.orc_sw_align_long(self.ctx, win_start, blen, seq, len(seq), st)
         return sc, (st[0], st[1], st[2])
 
     def map_batch(self, reads1, reads2=None, nthreads=1, detail=False):

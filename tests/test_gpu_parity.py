@@ -484,6 +484,57 @@ def test_peer_reduce_single_process(get_fixture):
         m.close()
 
 
+def test_cfg4_long_windows_match_oracle(oracle_built):
+    """BASELINE configs[3]: reads of 100 / 150 / 250 bp against 1000-bp windows through pemap_sw_score_device.  The
+    reference's 300 x 300 buffers cannot hold that shape, so the checker is the oracle's restatement of
+    smith_waterman_align with enlarged buffers (orc_sw_align_long, equal to the pinned orc_sw_align wherever both
+    apply): score bit-exact in units of 1/36 for every pair, start row / state equal unless the kernel flags an exact
+    tie of the last-column maximum.  Shapes include ragged windows (1 .. 1056 rows) and windows at the genome's end."""
+    import torch
+    from pecaller_b200 import synth
+    dev = torch.device("cuda", 0)
+    genome = synth.random_genome(44, [300_000])
+    g = genome[0]
+    mapper = pb.PEMapper.from_genome(genome, pb.default_params(pair_flag=0))
+    oracle = ol.Oracle(genome)
+    rng = np.random.default_rng(4)
+    for L in (100, 150, 250):
+        n = 600
+        win_len = rng.integers(1, 1057, size=n).astype(np.int32)
+        win_len[:200] = 1000
+        win_len[200:230] = L + 21
+        ws = rng.integers(0, g.shape[0] - 1100, size=n).astype(np.int32)
+        ws[-1] = g.shape[0] - win_len[-1]
+        stride = (L + 15) // 16 * 16
+        reads = np.zeros((n, stride), dtype=np.uint8)
+        for i in range(n):
+            w = g[ws[i]:ws[i] + win_len[i]]
+            if win_len[i] > L + 8 and i % 5:
+                o = int(rng.integers(0, win_len[i] - L - 4))
+                r = w[o:o + L].copy()
+                k = rng.integers(0, L, size=3)
+                r[k] = synth.ACGT[rng.integers(0, 4, size=3)]
+                if i % 3 == 0:
+                    r = np.concatenate([r[:L // 2], r[L // 2 + 2:], w[o + L:o + L + 2]])   # a 2-base deletion in the read
+            else:
+                r = synth.ACGT[rng.integers(0, 4, size=L)]
+            reads[i, :L] = r[:L]
+        t = lambda a: torch.from_numpy(a).to(dev)
+        d_reads, d_len, d_ws, d_wl = t(reads), t(np.full(n, L, np.int32)), t(ws), t(win_len)
+        sc, mi, mk, fl = (torch.zeros(n, dtype=torch.int32, device=dev) for _ in range(4))
+        torch.cuda.synchronize()
+        mapper.sw_score_device(n, d_reads.data_ptr(), d_len.data_ptr(), stride, L, d_ws.data_ptr(), d_wl.data_ptr(), 1056,
+                               sc.data_ptr(), mi.data_ptr(), mk.data_ptr(), fl.data_ptr())
+        sc, mi, mk, fl = (x.cpu().numpy() for x in (sc, mi, mk, fl))
+        for i in range(n):
+            s, (k, ii, _) = oracle.sw_align_long(int(ws[i]), int(win_len[i]), reads[i, :L].tobytes())
+            assert round(s * 36) == sc[i], "L=%d pair %d (window %d): score %r vs %d/36" % (L, i, win_len[i], s, sc[i])
+            if not fl[i] & 1:
+                assert (ii, k) == (mi[i], mk[i]), "L=%d pair %d: start (%d,%d) vs (%d,%d)" % (L, i, ii, k, mi[i], mk[i])
+    mapper.close()
+    oracle.close()
+
+
 def test_contig_count_quirk_is_refused():
     """2..7 contigs: find_chrom reads out of bounds in the reference; we refuse instead of guessing."""
     from pecaller_b200 import synth
