@@ -135,6 +135,20 @@ int pemap_map_batch(pemap_t *h, int n, const char *const *read1, const int *len1
 int pemap_map_batch_rows(pemap_t *h, int n, const char *reads1, const int *len1, const char *reads2,
                          const int *len2, int stride, uint32_t *m1, uint32_t *m2, int *mapping_type);
 
+/* Same with 2-bit packed reads - what a FASTQ decoder thread can emit as it copies a read, and 64 bytes per 150-bp
+   read on the host-to-device link instead of 160.  A packed row holds ceil(max_len / 16) code words (base i at bits
+   31-2(i%16), 30-2(i%16) of word i/16, first base on top exactly as convert_seq_int builds a k-mer, pemapper.c:2408-2423;
+   A 0, C 1, G 2, T 3, N stored as 0) followed by ceil(max_len / 32) N-mask words (bit i%32 of word i/32), padded to a
+   multiple of 16 bytes = pemap_packed_stride(max_len); every row of a batch uses the same max_len.  The seed kernel cuts
+   its k-mers out of the code words with funnel shifts (reverse strand: bit reversal + complement) and the DP kernels
+   read ASCII rows restored on the device.  pemap_pack_read returns PEMAP_ERR_UNSUPPORTED for a read with any character
+   other than upper-case A C G T N (IUPAC codes, lower case: the reference scores those by exact character): such a
+   batch goes through pemap_map_batch_rows.  Lengths still travel as an int array. */
+size_t pemap_packed_stride(int max_len);
+int pemap_pack_read(const char *read, int len, int max_len, void *dst);
+int pemap_map_batch_packed(pemap_t *h, int n, const void *packed1, const int *len1, const void *packed2,
+                           const int *len2, int max_len, uint32_t *m1, uint32_t *m2, int *mapping_type);
+
 /* Same with inputs and outputs already in device memory (device pointers); used to time the kernels alone. */
 int pemap_map_batch_device(pemap_t *h, int n, const char *d_reads1, const int *d_len1, const char *d_reads2,
                            const int *d_len2, int stride, int max_len, uint32_t *d_m1, uint32_t *d_m2,

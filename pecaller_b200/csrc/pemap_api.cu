@@ -92,6 +92,14 @@ struct pemap_ctx {
     int n = 0, first = 0;
     bool paired = false, direct = false;
   } slots[2];
+  // 2-bit packed input (pemap_map_batch_packed): device copies of the packed rows, per slot and mate, allocated at the
+  // first packed batch; cur_packed describes the chunk being submitted to run_chunk
+  unsigned char* d_packed[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  size_t packed_cap = 0;
+  struct {
+    const unsigned char* rows[2] = {nullptr, nullptr};
+    int stride = 0, code_words = 0, mask_words = 0;
+  } cur_packed;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaStream_t s_aux = nullptr;            // the pure-diagonal pileup runs beside the integer traceback
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -775,6 +783,11 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     ra.len[0] = d_l1;
     ra.len[1] = d_l2;
     ra.stride = stride;
+    ra.packed[0] = h->cur_packed.rows[0];
+    ra.packed[1] = h->cur_packed.rows[1];
+    ra.pstride = h->cur_packed.stride;
+    ra.pcode_words = h->cur_packed.code_words;
+    ra.pmask_words = h->cur_packed.mask_words;
     ra.n_reads = n;
     ra.paired = paired ? 1 : 0;
     ra.tasks = h->d_tasks;
@@ -1205,8 +1218,10 @@ int finish_slot(pemap_ctx* h, pemap_ctx::Slot& sl, uint32_t* m1, uint32_t* m2, i
 }
 
 // rows: reads as (n x stride) matrices on the host, or, when ptrs != nullptr, as arrays of pointers
+// packed_max_len > 0: rows1 / rows2 are 2-bit packed rows (pemap_pack_read) laid out for that batch maximum
 int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, const int* len1, const char* rows2,
-             const char* const* ptr2, const int* len2, int stride, uint32_t* m1, uint32_t* m2, int* mapping_type) {
+             const char* const* ptr2, const int* len2, int stride, uint32_t* m1, uint32_t* m2, int* mapping_type,
+             int packed_max_len = 0) {
   if (!h) return PEMAP_ERR_ARG;
   if (h->index_only) return fail(h, PEMAP_ERR_ARG, "handle was opened with PEMAP_INDEX_ONLY=1");
   if (n < 0 || (!rows1 && !ptr1) || !len1 || !m1 || !m2 || !mapping_type) return fail(h, PEMAP_ERR_ARG, "NULL argument");
@@ -1222,6 +1237,22 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
   }
   if (rows1 && !ptr1 && stride > h->stride_cap && is_pinned(rows1))
     return fail(h, PEMAP_ERR_ARG, "row stride larger than 320 bytes");
+  const bool packed = packed_max_len > 0;
+  if (packed) {
+    if (packed_max_len > PM_DP_MAX - 22 || stride != (int)pemap_packed_stride(packed_max_len))
+      return fail(h, PEMAP_ERR_ARG, "packed rows: stride must be pemap_packed_stride(max_len)");
+    if (h->seed_legacy) return fail(h, PEMAP_ERR_UNSUPPORTED, "PEMAP_SEED=legacy reads ASCII rows only");
+    const size_t need = (size_t)h->chunk * (size_t)pemap_packed_stride(PM_DP_MAX - 22);
+    if (h->packed_cap < need) {
+      for (auto& sl : h->d_packed)
+        for (auto& p : sl) {
+          if (p) cudaFree(p);
+          p = nullptr;
+          CK(cudaMalloc(&p, need));
+        }
+      h->packed_cap = need;
+    }
+  }
   begin_batch(h, n);
   SlotGuard guard{h};
   const bool direct = rows1 && is_pinned(rows1) && is_pinned(len1) && (!paired || (is_pinned(rows2) && is_pinned(len2))) &&
@@ -1249,7 +1280,36 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
     }
     int dstride = stride;
     const char* src_rows[2] = {rows1 ? rows1 + (size_t)first * stride : nullptr, rows2 ? rows2 + (size_t)first * stride : nullptr};
-    if (!direct || ptr1) {  // stage through the library's pinned buffers, packed at a 16-byte multiple
+    if (packed) {
+      // packed rows: copied as they are (staged through the pinned buffers when the caller's are pageable), then
+      // unpacked on the device into the ASCII rows the DP kernels read; the seed kernel reads the packed words
+      if (max_len > packed_max_len) return fail(h, PEMAP_ERR_ARG, "a read is longer than the packed rows' max_len");
+      const int code_words = (packed_max_len + 15) / 16, mask_words = (packed_max_len + 31) / 32;
+      dstride = (packed_max_len + 15) & ~15;
+      for (int m = 0; m < (paired ? 2 : 1); m++) {
+        const int* len = (m ? len2 : len1) + first;
+        const void* src = src_rows[m];
+        const int* lsrc = len;
+        if (!direct) {
+          memcpy(sl.h_reads[m], src_rows[m], (size_t)cn * stride);
+          memcpy(sl.h_len[m], len, (size_t)cn * sizeof(int));
+          src = sl.h_reads[m];
+          lsrc = sl.h_len[m];
+        }
+        unsigned char* dp = h->d_packed[chunk_no & 1][m];
+        CK(cudaMemcpyAsync(dp, src, (size_t)cn * stride, cudaMemcpyHostToDevice, h->s_h2d));
+        CK(cudaMemcpyAsync(sl.d_len[m], lsrc, (size_t)cn * sizeof(int), cudaMemcpyHostToDevice, h->s_h2d));
+        const long long threads = (long long)cn * (dstride / 16);
+        pm::k_unpack_reads<<<(unsigned)((threads + 255) / 256), 256, 0, h->s_h2d>>>(dp, stride, code_words, sl.d_len[m], cn,
+                                                                                  sl.d_reads[m], dstride);
+        h->stats.launches++;
+        h->cur_packed.rows[m] = dp;
+      }
+      if (!paired) h->cur_packed.rows[1] = nullptr;
+      h->cur_packed.stride = stride;
+      h->cur_packed.code_words = code_words;
+      h->cur_packed.mask_words = mask_words;
+    } else if (!direct || ptr1) {  // stage through the library's pinned buffers, packed at a 16-byte multiple
       dstride = (max_len + 15) & ~15;
       if (dstride < 16) dstride = 16;
       for (int m = 0; m < (paired ? 2 : 1); m++) {
@@ -1267,7 +1327,7 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
       }
     }
     if (dstride > h->stride_cap) return fail(h, PEMAP_ERR_ARG, "row stride larger than 320 bytes");
-    for (int m = 0; m < (paired ? 2 : 1); m++) {
+    for (int m = 0; m < (paired ? 2 : 1) && !packed; m++) {
       const int* lsrc = (!direct || ptr1) ? sl.h_len[m] : (m ? len2 : len1) + first;
       CK(cudaMemcpyAsync(sl.d_reads[m], src_rows[m], (size_t)cn * dstride, cudaMemcpyHostToDevice, h->s_h2d));
       CK(cudaMemcpyAsync(sl.d_len[m], lsrc, (size_t)cn * sizeof(int), cudaMemcpyHostToDevice, h->s_h2d));
@@ -1276,6 +1336,7 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
     CK(cudaStreamWaitEvent(h->stream, sl.ev_h2d, 0));
     int rc = run_chunk(h, cn, sl.d_reads[0], sl.d_len[0], paired ? sl.d_reads[1] : nullptr, paired ? sl.d_len[1] : nullptr,
                        dstride, max_len, min_len == max_len ? max_len : 0, sl.d_m1, sl.d_m2, sl.d_type, sl.ev);
+    h->cur_packed.rows[0] = h->cur_packed.rows[1] = nullptr;
     if (rc) return rc;
     CK(cudaStreamWaitEvent(h->s_d2h, sl.ev[4], 0));
     uint32_t* o1 = direct ? m1 + first : sl.h_m1;
@@ -1311,15 +1372,26 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
 }  // namespace
 
 namespace {
+// BASELINE configs[3]: k_sw_i16 with windows of up to PEMAP_SW_MAX_WINDOW rows; uniform read lengths get the
+// instantiation whose last read column is a compile-time constant
+template <int G, int WD, int CMM>
+struct LongDispatch {
+  static void go(pemap_ctx* h, const pm::SwIntArgs& a, int cmm) {
+    if (cmm == CMM) {
+      static int grids[kMaxDev] = {};
+      int& grid = grids[h->device % kMaxDev];
+      if (!grid) grid = one_wave_grid(h, pm::k_sw_i16<G, WD, CMM, PEMAP_SW_MAX_WINDOW>, 128, 0);
+      pm::k_sw_i16<G, WD, CMM, PEMAP_SW_MAX_WINDOW><<<grid, 128, 0, h->stream>>>(a);
+    } else {
+      LongDispatch<G, WD, CMM - 1>::go(h, a, cmm);
+    }
+  }
+};
 template <int G, int WD>
-void launch_sw_long(pemap_ctx* h, const pm::SwIntArgs& a) {
-  static int grids[kMaxDev] = {};
-  int& grid = grids[h->device % kMaxDev];
-  if (!grid) grid = one_wave_grid(h, pm::k_sw_i16<G, WD, -1, PEMAP_SW_MAX_WINDOW>, 128, 0);
-  pm::k_sw_i16<G, WD, -1, PEMAP_SW_MAX_WINDOW><<<grid, 128, 0, h->stream>>>(a);
-}
+struct LongDispatch<G, WD, -2> {
+  static void go(pemap_ctx*, const pm::SwIntArgs&, int) {}
+};
 }  // namespace
-
 
 // ------------------------------------------------------------------------------------------------- C-ABI
 
@@ -1503,6 +1575,39 @@ int pemap_map_batch(pemap_t* h, int n, const char* const* read1, const int* len1
 int pemap_map_batch_rows(pemap_t* h, int n, const char* reads1, const int* len1, const char* reads2, const int* len2,
                          int stride, uint32_t* m1, uint32_t* m2, int* mapping_type) {
   return map_host(h, n, reads1, nullptr, len1, reads2, nullptr, len2, stride, m1, m2, mapping_type);
+}
+
+size_t pemap_packed_stride(int max_len) {
+  if (max_len < 1) max_len = 1;
+  const size_t bytes = 4u * (size_t)((max_len + 15) / 16) + 4u * (size_t)((max_len + 31) / 32);
+  return (bytes + 15u) & ~(size_t)15u;
+}
+
+int pemap_pack_read(const char* read, int len, int max_len, void* dst) {
+  if (!read || !dst || len < 0 || len > max_len) return PEMAP_ERR_ARG;
+  uint32_t* w = static_cast<uint32_t*>(dst);
+  const int code_words = (max_len + 15) / 16;
+  const size_t words = pemap_packed_stride(max_len) / 4;
+  for (size_t i = 0; i < words; i++) w[i] = 0u;
+  for (int i = 0; i < len; i++) {
+    uint32_t c;
+    switch (read[i]) {
+      case 'A': c = 0; break;
+      case 'C': c = 1; break;
+      case 'G': c = 2; break;
+      case 'T': c = 3; break;
+      case 'N': c = 0; w[code_words + (i >> 5)] |= 1u << (i & 31); break;
+      default: return PEMAP_ERR_UNSUPPORTED;  // lower case, IUPAC codes ...: such a read goes through the ASCII entry points
+    }
+    w[i >> 4] |= c << (30 - 2 * (i & 15));
+  }
+  return PEMAP_OK;
+}
+
+int pemap_map_batch_packed(pemap_t* h, int n, const void* packed1, const int* len1, const void* packed2, const int* len2,
+                           int max_len, uint32_t* m1, uint32_t* m2, int* mapping_type) {
+  return map_host(h, n, static_cast<const char*>(packed1), nullptr, len1, static_cast<const char*>(packed2), nullptr, len2,
+                  (int)pemap_packed_stride(max_len), m1, m2, mapping_type, max_len);
 }
 
 int pemap_map_batch_device(pemap_t* h, int n, const char* d_reads1, const int* d_len1, const char* d_reads2,
@@ -1866,12 +1971,25 @@ int pemap_sw_score_device(pemap_t* h, int n, const char* d_reads, const int* d_l
   ia.lane_mm = -1;
   ia.p = h->dp;
   ia.list = nullptr;
+  int uniform_len = 0;
+  {
+    unsigned mm[2] = {0xFFFFFFFFu, 0u};
+    CK(cudaMemcpyAsync(h->d_cursors + 4, mm, 8, cudaMemcpyHostToDevice, h->stream));
+    if (n > 0) k_len_range<<<h->sm_count * 4, 256, 0, h->stream>>>(d_len, nullptr, n, h->d_cursors + 4);
+    CK(cudaMemcpyAsync(mm, h->d_cursors + 4, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n > 0 && mm[0] == mm[1]) uniform_len = (int)mm[0];
+    if (n > 0 && (int)mm[1] > max_len) return fail(h, PEMAP_ERR_ARG, "a read is longer than max_len");
+  }
+  const int wd = max_len <= 112 ? 7 : max_len <= 160 ? 10 : max_len <= 256 ? 8 : 10;
+  const int cmm = uniform_len > 0 ? (uniform_len - 1) % wd : -1;
+  ia.lane_mm = uniform_len > 0 ? (uniform_len - 1) / wd : -1;
   cudaEvent_t e0 = h->slots[0].ev[0], e1 = h->slots[0].ev[1];
   CK(cudaEventRecord(e0, h->stream));
-  if (max_len <= 112) launch_sw_long<16, 7>(h, ia);
-  else if (max_len <= 160) launch_sw_long<16, 10>(h, ia);
-  else if (max_len <= 256) launch_sw_long<32, 8>(h, ia);
-  else launch_sw_long<32, 10>(h, ia);
+  if (max_len <= 112) LongDispatch<16, 7, 6>::go(h, ia, cmm);
+  else if (max_len <= 160) LongDispatch<16, 10, 9>::go(h, ia, cmm);
+  else if (max_len <= 256) LongDispatch<32, 8, 7>::go(h, ia, cmm);
+  else LongDispatch<32, 10, 9>::go(h, ia, cmm);
   CK(cudaEventRecord(e1, h->stream));
   if (n) pm::k_sw_bench_results<<<(n + 255) / 256, 256, 0, h->stream>>>(n, h->d_ires, d_score36, d_maxi, d_maxk, d_flags);
   h->stats.launches += 3;
@@ -1969,6 +2087,9 @@ void pemap_destroy(pemap_t* h) {
     for (void* p : dev)
       if (p) cudaFree(p);
     for (void* p : h->ipc_open) cudaIpcCloseMemHandle(p);
+    for (auto& sl : h->d_packed)
+      for (auto& p : sl)
+        if (p) cudaFree(p);
     void* rbi[] = {h->d_rbi_data[0], h->d_rbi_data[1], h->d_rbi_data[2], h->d_rbi_data[3], h->d_rbi_dir[0], h->d_rbi_dir[1],
                    h->d_rbi_dir[2], h->d_rbi_dir[3], h->d_big_list, h->d_big_list2, h->d_big_scratch};
     for (void* p : rbi)

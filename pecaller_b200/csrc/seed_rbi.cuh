@@ -32,7 +32,13 @@
 #define PM_RBI_MARK 0xFFFFFFFEu
 #define PM_RBI_CAP 512                  // entries of one strand kept in shared memory (a 150-bp read on 3.1 Gb has ~360)
 #ifndef PM_RBI_PREFETCH
-#define PM_RBI_PREFETCH 2               // segments whose buckets are prefetched into L2 ahead of the one being read
+#define PM_RBI_PREFETCH 1               // segments whose buckets are prefetched into L2 ahead of the one being read
+#endif
+#ifndef PM_RBI_PREFETCH_MODE
+#define PM_RBI_PREFETCH_MODE 0
+#endif
+#ifndef PM_RBI_PREFETCH_STRIDE
+#define PM_RBI_PREFETCH_STRIDE 128
 #endif
 #ifndef PM_RBI_EXPERIMENT
 #define PM_RBI_EXPERIMENT 0
@@ -136,14 +142,49 @@ __global__ void __launch_bounds__(256) k_rbi_fill(const uint32_t* key, const uin
   blk[64 + (r & 15u)] = (unsigned char)(k & 255u);
 }
 
+// ------------------------------------------------------------------------------------------------ packed reads
+// Row of a packed read (pemap.h: pemap_pack_read): code words (base i at bits 31-2(i%16), 30-2(i%16) of word i/16; A 0,
+// C 1, G 2, T 3 as convert_seq_int codes them, N stored as 0), then N-mask words (bit i%32 of word i/32).
+// k_unpack_reads restores the ASCII rows the DP kernels read; the seed kernel works on the packed words directly.
+__global__ void __launch_bounds__(256) k_unpack_reads(const unsigned char* packed, int pstride, int code_words, const int* len, int n,
+                                                      char* rows, int stride) {
+  const int words = stride / 16;  // 16 bases per thread
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * words) return;
+  const int r = (int)(t / words), w = (int)(t % words);
+  uint4 out = make_uint4(0, 0, 0, 0);
+  if (16 * w < len[r] && w < code_words) {
+    const uint32_t* prow = reinterpret_cast<const uint32_t*>(packed + (size_t)r * pstride);
+    const uint32_t c = prow[w];
+    const uint32_t m = (prow[code_words + (w >> 1)] >> (16 * (w & 1))) & 0xFFFFu;
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t x = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int i = 4 * k + j;
+        const uint32_t code = (c >> (30 - 2 * i)) & 3u;
+        const uint32_t ch = ((m >> i) & 1u) ? 'N' : (code == 0 ? 'A' : code == 1 ? 'C' : code == 2 ? 'G' : 'T');
+        x |= ch << (8 * j);
+      }
+      o[k] = x;
+    }
+    out = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  *reinterpret_cast<uint4*>(rows + (size_t)r * stride + 16 * w) = out;
+}
+
 // ------------------------------------------------------------------------------------------------ seed kernel
 
 struct SeedRbiArgs {
   RbiIndex ix;
   const uint32_t* cstart;      // n_contigs+1 (padded to >= 9 entries)
-  const char* reads[2];        // [n][stride] each
+  const char* reads[2];        // [n][stride] each (ASCII)
   const int* len[2];
   int stride;
+  const unsigned char* packed[2];  // the same reads 2-bit packed (pemap.h: pemap_pack_read), or nullptr: then `reads` is decoded
+  int pstride, pcode_words, pmask_words;
   int n_reads;                 // reads (pairs) in this chunk
   int paired;
   Task* tasks;
@@ -171,6 +212,7 @@ struct RbiWarpSmem {           // per warp, every path
   uint16_t hit_off[PM_MAX_HITS];
   uint8_t hit_or[PM_MAX_HITS];
   union {
+    uint32_t rd_words[36];           // packed input: code words [0, 19], N-mask words after them, one guard word at [32]
     char rd[2][PM_DP_MAX];           // forward read and its reverse_transcribe (C->T converted when bisulfite): until the k-mers are cut
     struct {
       uint32_t n_ent;                // entries of the strand gathered so far (appended to by the lanes that hold a match)
@@ -248,8 +290,22 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
   int tot = 0;
   unsigned long long l_pos = 0, l_lookups = 0;  // booked when the read-mate is finished (not when it is handed to the BIG pass)
   bool ok = (len >= 16 && len < PM_DP_MAX - 21);
-  // N filter (1552-1559) + forward / reverse-transcribed copies (1019-1021, 1561-1570)
-  if (ok) {
+  const bool from_packed = a.packed[0] != nullptr;
+  uint32_t* const pw = reinterpret_cast<uint32_t*>(&sm.rd[0][0]);  // packed input: code words, then N-mask words
+  int n_masked = 0;
+  if (ok && from_packed) {
+    // 2-bit packed read: one coalesced 4-byte load per lane brings codes and N mask (<= 30 words); the N filter
+    // (1552-1559) is a population count, the k-mers are funnel shifts of the code words
+    const uint32_t* prow = reinterpret_cast<const uint32_t*>(a.packed[mate] + (size_t)r * a.pstride);
+    const int nw = a.pcode_words + a.pmask_words;
+    uint32_t v = lane < nw ? __ldg(prow + lane) : 0u;
+    n_masked = __reduce_add_sync(0xFFFFFFFFu, (lane >= a.pcode_words && lane < nw) ? __popc(v) : 0);
+    if (a.p.is_bisulfite && lane < a.pcode_words) v |= (v & 0x55555555u & ~(v >> 1)) << 1;  // convert_ct (2292-2300): C (01) -> T (11)
+    pw[lane] = v;
+    if (lane == 0) pw[32] = 0u;
+    if (n_masked >= 1 + len / 10) ok = false;
+  } else if (ok) {
+    // N filter (1552-1559) + forward / reverse-transcribed copies (1019-1021, 1561-1570)
     int n_count = 0;
     for (int i = lane; i < len; i += 32) {
       const char ch = read[i];
@@ -275,13 +331,35 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
     for (int ss = lane; ss < 2 * nseg; ss += 32) {
       const int strand = ss >= nseg, s = strand ? ss - nseg : ss;
       const int off = (s < total_cuts) ? 16 * s : len - 16;
-      const char* q = sm.rd[strand] + off;
       uint32_t code = 0;
+      if (from_packed) {
+        // base i of the read sits at bits 31-2(i%16), 30-2(i%16) of code word i/16: 16 bases from any offset are one funnel
+        // shift, first base on top as convert_seq_int has it; N is packed as A (cv[], 2379-2383)
+        const int fo = strand ? len - off - 16 : off;  // the reverse strand's segment covers these forward bases
+        code = __funnelshift_l(pw[(fo >> 4) + 1], pw[fo >> 4], 2 * (fo & 15));
+        if (strand) {  // reverse_transcribe (2303-2337): field order reversed, every base complemented (3 - c = ~c), N stays N = 0
+          uint32_t y = __brev(code);
+          y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+          code = ~y;
+          if (n_masked) {
+            const uint32_t* mw = pw + a.pcode_words;
+            uint32_t m = __funnelshift_r(mw[fo >> 5], (fo >> 5) + 1 < a.pmask_words ? mw[(fo >> 5) + 1] : 0u, fo & 31) & 0xFFFFu;
+            m = (m | (m << 8)) & 0x00FF00FFu;  // forward base fo + i is field i from the bottom of the reversed word
+            m = (m | (m << 4)) & 0x0F0F0F0Fu;
+            m = (m | (m << 2)) & 0x33333333u;
+            m = (m | (m << 1)) & 0x55555555u;
+            code &= ~(m | (m << 1));
+          }
+          if (a.p.is_bisulfite) code |= (code & 0x55555555u & ~(code >> 1)) << 1;
+        }
+      } else {
+        const char* q = sm.rd[strand] + off;
 #pragma unroll
-      for (int i = 0; i < 16; i++) code = (code << 2) | base_code(q[i]);
+        for (int i = 0; i < 16; i++) code = (code << 2) | base_code(q[i]);
+      }
       sm.kcode[ss] = code;
     }
-    __syncwarp();
+    __syncwarp();  // every lane is done with the read's staging (it shares its shared memory with the gather's scratch)
     l_lookups = (unsigned long long)(2 * nseg * PM_KV);
 
     int min_match = total_cuts > 1 ? total_cuts : 1;  // 1642-1645
@@ -383,8 +461,13 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
         const int bp = 4 * (strand * nseg + sp) + rot;
         const char* p0 = reinterpret_cast<const char*>(rdata + 5ull * sm.b_off[bp]);
         const uint32_t bytes = 20u * sm.b_n4[bp];  // 80 bytes per block = 20 per quad
-        const char* line = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)127) + 128 * l8;
-        for (; line < p0 + bytes; line += 1024) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+#if PM_RBI_PREFETCH_MODE == 1   /* one bulk prefetch per bucket (TMA unit): the whole byte range at once */
+        if (l8 == 0 && bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"(bytes) : "memory");
+#else                           /* one line-sized piece per lane and instruction */
+        const char* line = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)(PM_RBI_PREFETCH_STRIDE - 1)) +
+                           PM_RBI_PREFETCH_STRIDE * l8;
+        for (; line < p0 + bytes; line += 8 * PM_RBI_PREFETCH_STRIDE) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+#endif
       };
 #if PM_RBI_PREFETCH > 0
       for (int sp = 0; sp < PM_RBI_PREFETCH; sp++)

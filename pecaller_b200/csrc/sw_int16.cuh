@@ -80,13 +80,16 @@ template <int G, int WD, int CMM, int ROWCAP = 0>
 __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
   constexpr int GPB = 128 / G;
   constexpr int ROWS = ROWCAP > 0 ? ROWCAP : ((G * WD + 24 < PM_DP_MAX) ? G * WD + 24 : PM_DP_MAX);  // window rows: nn <= len + 21
+  // uniform read length: the last read column of every row is parked and scanned after the sweep; with long windows
+  // (ROWCAP) that buffer would not fit, the owner lane then tracks the maximum row by row at its compile-time column
+  constexpr bool PARK = CMM >= 0 && ROWCAP == 0;
   __shared__ uint32_t s_win[GPB][ROWS];
-  __shared__ __align__(16) uint32_t s_last[CMM >= 0 ? GPB : 1][CMM >= 0 ? 4 * ROWS : 4];  // last read column of every row
+  __shared__ __align__(16) uint32_t s_last[PARK ? GPB : 1][PARK ? 4 * ROWS : 4];  // last read column of every row
   const int tid = threadIdx.x, grp = tid / G, gl = tid % G;
   const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) / G * G));
   const uint32_t n_items = *a.n_items, n_pairs = (n_items + 1) >> 1;
   uint32_t* win = s_win[grp];
-  uint32_t* last = s_last[CMM >= 0 ? grp : 0];
+  uint32_t* last = s_last[PARK ? grp : 0];
   constexpr uint32_t K1 = 0x00010001u, K12 = 0x000C000Cu, NEG72 = 0xFFB8FFB8u;
   constexpr uint32_t BIASP = (PM_IBIAS << 16) | PM_IBIAS;
 
@@ -176,9 +179,17 @@ __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
           diag = mu[c];
           const uint32_t m12 = __vmaxs2(s1, s2);
           const uint32_t m = __vmaxs2(s0, m12);
-          if (CMM >= 0) {
+          if (PARK) {
             if (c == CMM && ownA) {  // uniform read length: park the last column, scan it after the sweep
               *reinterpret_cast<uint4*>(&last[4 * (i - 1)]) = make_uint4(s0, s1, s2, dvd);
+            }
+          } else if (CMM >= 0) {
+            if (c == CMM && ownA) {
+              if (i <= nnA)
+                track_best((int)(s0 & 0xFFFFu), (int)(s1 & 0xFFFFu), (int)(s2 & 0xFFFFu), (int)(dvd & 0xFFFFu), i, bestA, bkA,
+                           biA, tieA, dqA);
+              if (i <= nnB)
+                track_best((int)(s0 >> 16), (int)(s1 >> 16), (int)(s2 >> 16), (int)(dvd >> 16), i, bestB, bkB, biB, tieB, dqB);
             }
           } else {
             if (c == colA && ownA && i <= nnA)
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
         out_dv = dvd;
       }
     }
-    if (CMM >= 0) {
+    if (PARK) {
       // scan of the last column (1717-1742) by the whole group.  key = value<<10 | (1023 - order) keeps the FIRST
       // row/state of the maximum (strict '>' in scan order); the mirrored key keeps the LAST one; they differ
       // exactly when the maximum occurs more than once.  order = 3*i + k <= 3*320+2 < 1024.

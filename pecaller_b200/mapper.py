@@ -59,7 +59,8 @@ SITE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)  # pemap_site
 EXPORTS = ["pemap_version", "pemap_default_params", "pemap_init", "pemap_init_from_genome", "pemap_set_params",
            "pemap_map_batch", "pemap_map_batch_rows", "pemap_map_batch_device", "pemap_keep", "pemap_get_detail",
            "pemap_get_candidates", "pemap_finish", "pemap_finish_stream", "pemap_finish_stream_range", "pemap_get_insertions", "pemap_counts_ipc_handle",
-           "pemap_reduce_scatter_ipc", "pemap_reduce_scatter_local", "pemap_host_alloc", "pemap_host_free", "pemap_sw_score_device", "pemap_reset_counts", "pemap_counts_device", "pemap_get_stats",
+           "pemap_reduce_scatter_ipc", "pemap_reduce_scatter_local", "pemap_host_alloc", "pemap_host_free", "pemap_sw_score_device", "pemap_packed_stride", "pemap_pack_read",
+           "pemap_map_batch_packed", "pemap_reset_counts", "pemap_counts_device", "pemap_get_stats",
            "pemap_reset_stats", "pemap_stream", "pemap_reduce_counts_peer", "pemap_index_device", "pemap_read_pos_index", "pemap_read_mers", "pemap_last_error",
            "pemap_destroy"]
 
@@ -99,6 +100,10 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.pemap_reduce_scatter_ipc.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.pemap_reduce_scatter_local.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.pemap_sw_score_device.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_float)]
+    L.pemap_packed_stride.restype = C.c_size_t
+    L.pemap_packed_stride.argtypes = [C.c_int]
+    L.pemap_pack_read.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.pemap_map_batch_packed.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp]
     L.pemap_host_alloc.restype = vp
     L.pemap_host_alloc.argtypes = [C.c_size_t]
     L.pemap_host_free.argtypes = [vp]
@@ -134,6 +139,37 @@ def rows_from_reads(reads: np.ndarray, stride: int | None = None):
     buf = np.zeros((n, stride), dtype=np.uint8)
     buf[:, :L] = reads
     return buf, np.full(n, L, dtype=np.int32)
+
+
+def pack_reads(reads: np.ndarray, lens: np.ndarray | None = None, max_len: int | None = None):
+    """(n, L) uint8 ASCII reads -> ((n, pemap_packed_stride(max_len)) uint8 packed rows, int32 lengths), the layout of
+    pemap_pack_read, vectorised in numpy (bench and tests; a C caller packs read by read with pemap_pack_read).
+    Raises PemapError for characters other than upper-case ACGTN."""
+    L = load_library()
+    n, width = reads.shape
+    lens = np.full(n, width, dtype=np.int32) if lens is None else np.asarray(lens, dtype=np.int32)
+    max_len = max_len or int(lens.max() if n else 1)
+    stride = L.pemap_packed_stride(max_len)
+    code_words, mask_words = (max_len + 15) // 16, (max_len + 31) // 32
+    code = np.full(256, 255, dtype=np.uint8)
+    for ch, c in zip(b"ACGTN", (0, 1, 2, 3, 0)):
+        code[ch] = c
+    valid = np.arange(width)[None, :] < lens[:, None]
+    c = code[reads]
+    if (c[valid] == 255).any():
+        raise PemapError("pack_reads: a read holds characters other than ACGTN")
+    c = np.where(valid, c, 0).astype(np.uint32)
+    isn = (reads == ord("N")) & valid
+    pad = (-width) % 32
+    if pad:
+        c = np.concatenate([c, np.zeros((n, pad), np.uint32)], axis=1)
+        isn = np.concatenate([isn, np.zeros((n, pad), bool)], axis=1)
+    cw = (c.reshape(n, -1, 16) << (30 - 2 * np.arange(16, dtype=np.uint32))[None, None, :]).sum(axis=2, dtype=np.uint32)
+    mw = (isn.reshape(n, -1, 32).astype(np.uint32) << np.arange(32, dtype=np.uint32)[None, None, :]).sum(axis=2, dtype=np.uint32)
+    out = np.zeros((n, stride // 4), dtype=np.uint32)
+    out[:, :code_words] = cw[:, :code_words]
+    out[:, code_words:code_words + mask_words] = mw[:, :mask_words]
+    return out.view(np.uint8).reshape(n, stride), lens
 
 
 class PEMapper:
@@ -225,6 +261,18 @@ class PEMapper:
                                               r2.ctypes.data if r2 is not None else None,
                                               l2.ctypes.data if l2 is not None else None, r1.shape[1],
                                               m1.ctypes.data, m2.ctypes.data, ty.ctypes.data))
+        return m1, m2, ty
+
+    def map_packed(self, p1, l1, p2, l2, max_len):
+        """pemap_map_batch_packed: p1/p2 are (n, pemap_packed_stride(max_len)) uint8 matrices from pack_reads()."""
+        n = p1.shape[0]
+        m1 = np.zeros(n, dtype=np.uint32)
+        m2 = np.zeros(n, dtype=np.uint32)
+        ty = np.zeros(n, dtype=np.int32)
+        self._ck(self._L.pemap_map_batch_packed(self._h, n, p1.ctypes.data, l1.ctypes.data,
+                                                p2.ctypes.data if p2 is not None else None,
+                                                l2.ctypes.data if l2 is not None else None, max_len, m1.ctypes.data,
+                                                m2.ctypes.data, ty.ctypes.data))
         return m1, m2, ty
 
     def map_pointers(self, reads1: list, reads2: list | None = None):

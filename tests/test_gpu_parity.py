@@ -484,6 +484,60 @@ def test_peer_reduce_single_process(get_fixture):
         m.close()
 
 
+@pytest.mark.parametrize("name", ["pe150", "bis", "edge9"])
+def test_packed_reads_equal_ascii_rows(name, get_fixture):
+    """pemap_map_batch_packed (2-bit codes + N mask, 64 bytes per 150-bp read; the seed kernel cuts its k-mers out of the
+    packed words, the DP kernels read rows unpacked on the device) against pemap_map_batch_rows on the same reads:
+    candidates in order, loci, types, pileup records, insertions.  Reads with N (below and above the N filter), ragged
+    lengths inside one packed batch and the bisulfite read conversion are included."""
+    fx = get_fixture(name)
+    bis = int(getattr(fx, "bisulfite", False))
+    rng = np.random.default_rng(8)
+    for run in fx.runs:
+        kw = dict(min_align=run.min_align, pair_flag=int(run.paired), min_dist=run.min_dist, max_dist=run.max_dist,
+                  is_bisulfite=int(run.bisulfite))
+        n = min(20000, run.reads1.shape[0])
+        r1 = run.reads1[:n].copy()
+        r2 = run.reads2[:n].copy() if run.paired else None
+        L = r1.shape[1]
+        for r in (r1, r2):                                  # sprinkle N: a few per read in 2 % of the reads, many in 0.5 %
+            if r is not None:
+                rows = rng.choice(n, size=n // 50, replace=False)
+                for i in rows:
+                    r[i, rng.integers(0, L, size=int(rng.integers(1, 4)))] = ord("N")
+                for i in rng.choice(n, size=n // 200, replace=False):
+                    r[i, rng.integers(0, L, size=L // 8)] = ord("N")
+        lens1 = np.full(n, L, dtype=np.int32)
+        lens1[::7] = L - 3                                   # ragged: every seventh read loses its last three bases
+        lens1[5::11] = max(16, L // 2)
+        lens2 = lens1[::-1].copy() if run.paired else None
+        out = {}
+        for mode in ("rows", "packed"):
+            mapper = pb.PEMapper.from_genome(fx.genome, pb.default_params(is_bisulfite=bis))
+            mapper.set_params(**kw)
+            mapper.keep(pb.KEEP_CANDIDATES)
+            if mode == "rows":
+                b1, _ = pb.mapper.rows_from_reads(r1)
+                b2 = pb.mapper.rows_from_reads(r2)[0] if run.paired else None
+                g = mapper.map_rows(b1, lens1, b2, lens2)
+            else:
+                p1, _ = pb.mapper.pack_reads(r1, lens1, L)
+                p2 = pb.mapper.pack_reads(r2, lens2, L)[0] if run.paired else None
+                g = mapper.map_packed(p1, lens1, p2, lens2, L)
+            cands = [mapper.candidates(i, m) for i in range(0, n, 5) for m in range(2 if run.paired else 1)]
+            rec, ins = mapper.finish()
+            out[mode] = (g, cands, rec.tobytes(), sorted(ins))
+            mapper.close()
+        tag = "%s/%s" % (name, run.name)
+        for x, y in zip(out["rows"][0], out["packed"][0]):
+            assert np.array_equal(x, y), tag + ": per-read results"
+        for (s0, o0), (s1, o1) in zip(out["rows"][1], out["packed"][1]):
+            assert np.array_equal(s0, s1) and np.array_equal(o0, o1), tag + ": candidate lists"
+        assert out["rows"][2] == out["packed"][2], tag + ": pileup records"
+        assert out["rows"][3] == out["packed"][3], tag + ": insertions"
+        assert (out["rows"][0][0] != 0).sum() > 0.5 * n
+
+
 def test_cfg4_long_windows_match_oracle(oracle_built):
     """BASELINE configs[3]: reads of 100 / 150 / 250 bp against 1000-bp windows through pemap_sw_score_device.  The
     reference's 300 x 300 buffers cannot hold that shape, so the checker is the oracle's restatement of
@@ -518,6 +572,8 @@ def test_cfg4_long_windows_match_oracle(oracle_built):
                     r = np.concatenate([r[:L // 2], r[L // 2 + 2:], w[o + L:o + L + 2]])   # a 2-base deletion in the read
             else:
                 r = synth.ACGT[rng.integers(0, 4, size=L)]
+            if r.shape[0] < L:
+                r = np.concatenate([r, synth.ACGT[rng.integers(0, 4, size=L - r.shape[0])]])
             reads[i, :L] = r[:L]
         t = lambda a: torch.from_numpy(a).to(dev)
         d_reads, d_len, d_ws, d_wl = t(reads), t(np.full(n, L, np.int32)), t(ws), t(win_len)
