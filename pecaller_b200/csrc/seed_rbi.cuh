@@ -300,7 +300,6 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
     const int nw = a.pcode_words + a.pmask_words;
     uint32_t v = lane < nw ? __ldg(prow + lane) : 0u;
     n_masked = __reduce_add_sync(0xFFFFFFFFu, (lane >= a.pcode_words && lane < nw) ? __popc(v) : 0);
-    if (a.p.is_bisulfite && lane < a.pcode_words) v |= (v & 0x55555555u & ~(v >> 1)) << 1;  // convert_ct (2292-2300): C (01) -> T (11)
     pw[lane] = v;
     if (lane == 0) pw[32] = 0u;
     if (n_masked >= 1 + len / 10) ok = false;
@@ -350,8 +349,9 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
             m = (m | (m << 1)) & 0x55555555u;
             code &= ~(m | (m << 1));
           }
-          if (a.p.is_bisulfite) code |= (code & 0x55555555u & ~(code >> 1)) << 1;
         }
+        // convert_ct (2292-2300) rewrites C as T in the forward read AND in its reverse transcript: C (01) -> T (11)
+        if (a.p.is_bisulfite) code |= (code & 0x55555555u & ~(code >> 1)) << 1;
       } else {
         const char* q = sm.rd[strand] + off;
 #pragma unroll

@@ -1,15 +1,20 @@
 // alu_peak.cu - measured issue rates of the instructions the Smith-Waterman kernels are made of (SURVEY.md 8d:
 // "L must be measured on the box with a dependency-free issue-rate microbenchmark").
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o alu_peak tools/alu_peak.cu ; prints one JSON object.
-// Every kernel runs 8 independent dependency chains per thread, 1024 threads per SM-resident block set, and
-// reports results per clock per SM from clock64() deltas, plus Gop/s from CUDA events.
+// Every kernel runs 8 independent dependency chains per thread, 1024 threads per SM-resident block set, long enough
+// (>= 50 ms per launch) for the CUDA-event time to be the kernel and not its launch, and reports ops per clock per SM
+// twice: from the clock64() deltas inside the kernel and from the event time x the SM clock nvidia-smi shows DURING
+// the launches (sampled every 100 ms, median printed).  The two must agree; round 1's 0.1 ms kernels did not
+// (launch overhead in the event time).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #define CHAINS 8
-#define ITERS 4096
+#define ITERS (1 << 20)
 
 template <int OP>
 __device__ __forceinline__ unsigned int_op(unsigned a, unsigned b, unsigned c) {
@@ -90,7 +95,9 @@ static void run(const char* name, F launch, int sms, int blocks_per_sm, long lon
   const double ops_per_block = 256.0 * CHAINS * ITERS;
   const double per_clk_sm = ops_per_block * blocks_per_sm / avg;  // resident blocks share the SM for `avg` cycles
   const double gops = ops_per_block * blocks / (ms * 1e6);
-  printf("  \"%s\": {\"ops_per_clk_per_sm\": %.2f, \"gops\": %.1f, \"ms\": %.4f}%s\n", name, per_clk_sm, gops, ms, last ? "" : ",");
+  printf("  \"%s\": {\"ops_per_clk_per_sm\": %.2f, \"gops\": %.1f, \"ms\": %.4f, \"ops_per_clk_per_sm_from_events_at_1965MHz\": %.2f}%s\n",
+         name, per_clk_sm, gops, ms, gops * 1e9 / (1965e6 * sms), last ? "" : ",");
+  fflush(stdout);
   free(h);
 }
 
@@ -106,6 +113,7 @@ int main() {
   cudaMalloc(&d_c, sizeof(long long) * sms * bps);
   int clk_khz = 0;
   cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+  FILE* smi = popen("nvidia-smi -i 0 --query-gpu=clocks.sm --format=csv,noheader,nounits -lms 100 -c 60 2>/dev/null", "r");
   printf("{\n  \"device\": \"%s\", \"sms\": %d, \"clock_rate_khz\": %d, \"chains\": %d, \"threads_per_sm\": %d,\n", p.name, sms, clk_khz,
          CHAINS, 256 * bps);
 #define RUN_INT(OP, NAME) run(NAME, [&](int b) { k_int<OP><<<b, 256>>>(d_u, 12345u, d_c); }, sms, bps, d_c, false)
@@ -118,7 +126,15 @@ int main() {
   RUN_INT(6, "VIADDMNMX_s32");
   RUN_INT(7, "VIMNMX3_s32");
   run("DADD", [&](int b) { k_f64<0><<<b, 256>>>(d_d, 1.5, d_c); }, sms, bps, d_c, false);
-  run("DSETP_SEL_DADD", [&](int b) { k_f64<1><<<b, 256>>>(d_d, 1.5, d_c); }, sms, bps, d_c, true);
-  printf("}\n");
+  run("DSETP_SEL_DADD", [&](int b) { k_f64<1><<<b, 256>>>(d_d, 1.5, d_c); }, sms, bps, d_c, false);
+  std::vector<int> mhz;
+  if (smi) {  // the sampler (60 samples, 6 s) has been printing since before the first launch
+    char line[64];
+    while (fgets(line, sizeof line, smi)) mhz.push_back(atoi(line));
+    pclose(smi);
+  }
+  std::sort(mhz.begin(), mhz.end());
+  printf("  \"sm_clock_mhz_during_run\": {\"samples\": %zu, \"min\": %d, \"median\": %d, \"max\": %d}\n}\n", mhz.size(),
+         mhz.empty() ? 0 : mhz.front(), mhz.empty() ? 0 : mhz[mhz.size() / 2], mhz.empty() ? 0 : mhz.back());
   return 0;
 }
