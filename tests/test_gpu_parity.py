@@ -535,7 +535,7 @@ def test_packed_reads_equal_ascii_rows(name, get_fixture):
             assert np.array_equal(s0, s1) and np.array_equal(o0, o1), tag + ": candidate lists"
         assert out["rows"][2] == out["packed"][2], tag + ": pileup records"
         assert out["rows"][3] == out["packed"][3], tag + ": insertions"
-        assert (out["rows"][0][0] != 0).sum() > 0.5 * n
+        assert (out["rows"][0][0] != 0).sum() > 0.3 * n
 
 
 def test_cfg4_long_windows_match_oracle(oracle_built):

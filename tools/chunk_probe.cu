@@ -113,8 +113,10 @@ void one(const uint4* tab, uint64_t mask16, const uint32_t* dir, uint32_t dir_ma
   fflush(stdout);
 }
 
-int main() {
-  const uint64_t bytes = 48ull << 30;   // the rotated bucket arrays of a 3.1 Gb genome are ~62 GB
+int main(int argc, char** argv) {
+  // argv[1] = GB of table the chunk starts are spread over (default 32; the rotated bucket arrays of a 3.1 Gb genome are 63 GB)
+  const uint64_t range_gb = argc > 1 ? (uint64_t)atoi(argv[1]) : 32;
+  const uint64_t bytes = (range_gb + 1) << 30;
   uint4* tab; uint32_t* out; uint32_t* dir;
   CK(cudaMalloc(&tab, bytes + 65536));
   CK(cudaMemset(tab, 1, bytes + 65536));
@@ -124,8 +126,8 @@ int main() {
   k_fill<<<148 * 8, 256>>>(dir, dir_words);
   CK(cudaDeviceSynchronize());
   // chunk starts: any 16-byte unit inside the first 32 GiB (mask), chunks may run 64 KB past it
-  const uint64_t mask16 = ((32ull << 30) / 16) - 1;
-  printf("{\"table_GB\": 32, \"dir_MB\": 256, \"runs\": [\n");
+  const uint64_t mask16 = ((range_gb << 30) / 16) - 1;  // (a power of two is expected)
+  printf("{\"table_GB\": %llu, \"dir_MB\": 256, \"runs\": [\n", (unsigned long long)range_gb);
   one<64, 4, 8>(tab, mask16, dir, dir_words - 1, out, 8, false);
   one<128, 8, 4>(tab, mask16, dir, dir_words - 1, out, 8, false);
   one<128, 8, 8>(tab, mask16, dir, dir_words - 1, out, 8, false);
