@@ -168,6 +168,7 @@ struct pemap_ctx {
   bool want_drain = false;
 
   pemap_stats stats;
+  struct pemap_lanes* lanes_ = nullptr;
 };
 
 namespace {
@@ -204,6 +205,72 @@ int fail(pemap_ctx* h, int code, const std::string& msg) {
       return fail(h, e_ == cudaErrorMemoryAllocation ? PEMAP_ERR_NOMEM : PEMAP_ERR_CUDA,                  \
                   std::string(#call) + ": " + cudaGetErrorString(e_));                                    \
   } while (0)
+
+}  // namespace
+
+// The per-chunk working set exists twice ("lanes"): chunk c runs on lane c & 1, each lane on its own stream, so that the
+// seed stage of one chunk (bound by HBM) shares the SMs with the scoring and traceback kernels of the previous one
+// (bound by integer issue).  The context's plain fields are the CURRENT lane's; use_lane() swaps them.
+#define PM_LANE_FIELDS(X)                                                                                              \
+  X(stream) X(s_aux) X(ev_fork) X(ev_join) X(d_tasks) X(d_results) X(d_cursors) X(d_diag_winners) X(d_exact_winners)    \
+  X(d_oob_winners) X(d_ires) X(d_replay_reads) X(d_replay_tasks) X(d_sw_list) X(d_flagq) X(flagq_bytes) X(d_walk_meta)  \
+  X(d_pair_codes) X(pair_codes_bytes) X(d_cand_base) X(d_cand_n) X(d_winners) X(d_det_best) X(d_det_orient)             \
+  X(d_det_score) X(d_seed_scratch) X(d_dirs) X(d_pend) X(d_big_list) X(d_big_list2) X(d_big_scratch)
+
+struct pemap_lane {
+#define X(f) decltype(pemap_ctx::f) f{};
+  PM_LANE_FIELDS(X)
+#undef X
+};
+
+struct pemap_lanes {  // kept beside the context (pemap_ctx::lanes_)
+  pemap_lane saved[2];
+  int cur = 0, n = 1;
+  cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+};
+
+namespace {
+
+void use_lane(pemap_ctx* h, int k) {
+  pemap_lanes& L = *h->lanes_;
+  if (k == L.cur) return;
+#define X(f) L.saved[L.cur].f = h->f; h->f = L.saved[k].f;
+  PM_LANE_FIELDS(X)
+#undef X
+  L.cur = k;
+}
+
+// everything either lane has been given is done
+int sync_lanes(pemap_ctx* h) {
+  pemap_lanes& L = *h->lanes_;
+  CK(cudaStreamSynchronize(h->stream));
+  if (L.n > 1) CK(cudaStreamSynchronize(L.saved[L.cur ^ 1].stream));
+  return PEMAP_OK;
+}
+
+// the side lane starts after what the main stream holds so far (resets, parameter uploads)
+int fork_lanes(pemap_ctx* h) {
+  pemap_lanes& L = *h->lanes_;
+  if (L.n < 2) return PEMAP_OK;
+  use_lane(h, 0);
+  CK(cudaEventRecord(L.ev_main, h->stream));
+  CK(cudaStreamWaitEvent(L.saved[1].stream, L.ev_main, 0));
+  return PEMAP_OK;
+}
+
+// the main stream (the one pemap_stream hands out) continues after both lanes
+int join_lanes(pemap_ctx* h) {
+  pemap_lanes& L = *h->lanes_;
+  use_lane(h, 0);
+  if (L.n < 2) return PEMAP_OK;
+  CK(cudaEventRecord(L.ev_side, L.saved[1].stream));
+  CK(cudaStreamWaitEvent(h->stream, L.ev_side, 0));
+  return PEMAP_OK;
+}
+
+}  // namespace
+
+namespace {
 
 void fill_dev_params(pemap_ctx* h) {
   const pemap_params& p = h->params;
@@ -290,8 +357,51 @@ int open_device(pemap_ctx* h, int device) {
   return PEMAP_OK;
 }
 
+// the working set of one lane (see pemap_lanes): everything a chunk's kernels write between its H2D and its D2H
+int alloc_lane_scratch(pemap_ctx* h) {
+  const size_t n = (size_t)h->chunk;
+  CK(cudaMalloc(&h->d_tasks, (size_t)h->task_cap * sizeof(pm::Task)));
+  CK(cudaMalloc(&h->d_results, (size_t)h->task_cap * sizeof(pm::TaskResult)));
+  CK(cudaMalloc(&h->d_cursors, 128));
+  CK(cudaMalloc(&h->d_sw_list, (size_t)h->task_cap * 4));
+  CK(cudaMalloc(&h->d_ires, (size_t)h->task_cap * sizeof(pm::ITaskResult)));
+  CK(cudaMalloc(&h->d_replay_reads, n * 4));
+  CK(cudaMalloc(&h->d_replay_tasks, (size_t)h->task_cap * sizeof(pm::Winner)));
+  CK(cudaMalloc(&h->d_cand_base, 2 * n * 4));
+  CK(cudaMalloc(&h->d_cand_n, 2 * n * 4));
+  CK(cudaMemset(h->d_cand_n, 0, 2 * n * 4));
+  CK(cudaMemset(h->d_cand_base, 0, 2 * n * 4));
+  CK(cudaMalloc(&h->d_winners, 2 * n * sizeof(pm::Winner)));
+  CK(cudaMalloc(&h->d_diag_winners, 2 * n * sizeof(pm::Winner)));
+  CK(cudaMalloc(&h->d_exact_winners, 2 * n * sizeof(pm::Winner)));
+  CK(cudaMalloc(&h->d_oob_winners, 2 * n * sizeof(pm::Winner)));
+  CK(cudaMalloc(&h->d_det_best, 2 * n * 4));
+  CK(cudaMalloc(&h->d_det_orient, 2 * n * 4));
+  CK(cudaMalloc(&h->d_det_score, 2 * n * 8));
+  if (h->seed_legacy) {
+    CK(cudaMalloc(&h->d_seed_scratch, (size_t)h->seed_blocks * kSeedWarps * 2 * PM_MAX_SEG * PM_SEG_CAP * 4));
+  } else {  // second seed pass (strand lists that do not fit shared memory): one CTA per SM, per-warp lists in HBM
+    CK(cudaMalloc(&h->d_big_scratch, (size_t)h->big_grid * kRbiBigWarps * PM_RBI_BIG_BYTES));
+    CK(cudaMalloc(&h->d_big_list, 2 * n * 4));
+    CK(cudaMalloc(&h->d_big_list2, 2 * n * 4));
+  }
+  const size_t max_groups = (size_t)h->sw_blocks * (128 / 16);
+  // trace scratch: groups * G == sw_blocks * 128 lanes for every instantiation, PM_DP_MAX rows of one word per lane
+  CK(cudaMalloc(&h->d_dirs, (size_t)h->sw_blocks * 128 * PM_DP_MAX * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->d_pend, 2 * max_groups * PM_DP_MAX));
+  return PEMAP_OK;
+}
+
 int alloc_chunk_buffers(pemap_ctx* h) {
   int chunk = 1 << 19;  // reads (pairs) per pass of the kernel chain: larger chunks shorten the persistent kernels' tails
+  h->lanes_ = new pemap_lanes();
+  h->lanes_->n = 2;
+  if (const char* s = getenv("PEMAP_LANES")) h->lanes_->n = atoi(s) >= 2 ? 2 : 1;
+  {  // two lanes of 512 Ki pairs take ~2 x 16.5 GB; beside a human-sized genome's counters halve the chunk instead
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && h->lanes_->n > 1 && free_b < (44ull << 30)) chunk = 1 << 18;
+    cudaGetLastError();
+  }
   if (const char* s = getenv("PEMAP_CHUNK")) chunk = std::max(1024, atoi(s));
   h->chunk = chunk;
   h->stride_cap = PM_DP_MAX;
@@ -311,42 +421,30 @@ int alloc_chunk_buffers(pemap_ctx* h) {
     CK(cudaMalloc(&sl.d_type, n * 4));
   }
   h->task_cap = (uint32_t)std::min<size_t>(2 * n * PM_MAX_HITS, 0x7FFFFFFFull);
-  CK(cudaMalloc(&h->d_tasks, (size_t)h->task_cap * sizeof(pm::Task)));
-  CK(cudaMalloc(&h->d_results, (size_t)h->task_cap * sizeof(pm::TaskResult)));
-  CK(cudaMalloc(&h->d_cursors, 128));
-  CK(cudaMalloc(&h->d_sw_list, (size_t)h->task_cap * 4));
   if (const char* s = getenv("PEMAP_CERTIFY")) h->certify = atoi(s) != 0;
-  CK(cudaMalloc(&h->d_ires, (size_t)h->task_cap * sizeof(pm::ITaskResult)));
-  CK(cudaMalloc(&h->d_replay_reads, n * 4));
-  CK(cudaMalloc(&h->d_replay_tasks, (size_t)h->task_cap * sizeof(pm::Winner)));
   if (const char* s = getenv("PEMAP_EXACT")) h->exact = atoi(s) != 0;
   if (const char* s = getenv("PEMAP_TRACE32")) h->trace32 = atoi(s) != 0;
   if (const char* s = getenv("PEMAP_BAND_HALF")) h->band_half = std::min(PM_BAND_LANES / 2, std::max(0, atoi(s)));
-  CK(cudaMalloc(&h->d_cand_base, 2 * n * 4));
-  CK(cudaMalloc(&h->d_cand_n, 2 * n * 4));
-  CK(cudaMemset(h->d_cand_n, 0, 2 * n * 4));
-  CK(cudaMemset(h->d_cand_base, 0, 2 * n * 4));
-  CK(cudaMalloc(&h->d_winners, 2 * n * sizeof(pm::Winner)));
-  CK(cudaMalloc(&h->d_diag_winners, 2 * n * sizeof(pm::Winner)));
-  CK(cudaMalloc(&h->d_exact_winners, 2 * n * sizeof(pm::Winner)));
-  CK(cudaMalloc(&h->d_oob_winners, 2 * n * sizeof(pm::Winner)));
-  CK(cudaMalloc(&h->d_det_best, 2 * n * 4));
-  CK(cudaMalloc(&h->d_det_orient, 2 * n * 4));
-  CK(cudaMalloc(&h->d_det_score, 2 * n * 8));
   h->seed_blocks = h->sm_count * 8;
-  if (h->seed_legacy) {
-    CK(cudaMalloc(&h->d_seed_scratch, (size_t)h->seed_blocks * kSeedWarps * 2 * PM_MAX_SEG * PM_SEG_CAP * 4));
-  } else {  // second seed pass (strand lists that do not fit shared memory): one CTA per SM, per-warp lists in HBM
-    h->big_grid = 2 * h->sm_count;
-    CK(cudaMalloc(&h->d_big_scratch, (size_t)h->big_grid * kRbiBigWarps * PM_RBI_BIG_BYTES));
-    CK(cudaMalloc(&h->d_big_list, 2 * n * 4));
-    CK(cudaMalloc(&h->d_big_list2, 2 * n * 4));
-  }
+  h->big_grid = 2 * h->sm_count;
   h->sw_blocks = h->sm_count * 6;  // upper bound of CTAs per SM of the wavefront kernels (scratch is sized for it)
-  const size_t max_groups = (size_t)h->sw_blocks * (128 / 16);
-  // trace scratch: groups * G == sw_blocks * 128 lanes for every instantiation, PM_DP_MAX rows of one word per lane
-  CK(cudaMalloc(&h->d_dirs, (size_t)h->sw_blocks * 128 * PM_DP_MAX * sizeof(unsigned long long)));
-  CK(cudaMalloc(&h->d_pend, 2 * max_groups * PM_DP_MAX));
+  {
+    int rc = alloc_lane_scratch(h);  // lane 0: the context's own fields
+    if (rc) return rc;
+    pemap_lanes& L = *h->lanes_;
+    if (L.n > 1) {
+      use_lane(h, 1);
+      CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+      rc = alloc_lane_scratch(h);
+      use_lane(h, 0);
+      if (rc) return rc;
+      CK(cudaEventCreateWithFlags(&L.ev_main, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&L.ev_side, cudaEventDisableTiming));
+    }
+  }
   CK(cudaMalloc(&h->d_counters, sizeof(pm::SeedCounters)));
   CK(cudaMemset(h->d_counters, 0, sizeof(pm::SeedCounters)));
   if (const char* s = getenv("PEMAP_INS_MB")) h->ins_cap = (uint64_t)std::max(1, atoi(s)) << 20;
@@ -1159,7 +1257,10 @@ bool is_pinned(const void* p) {
 // Move what the traceback kernels appended so far to the host and rewind the device cursor (the reference mallocs
 // every insertion string, pemapper.c:1871-1904; here the append buffer is bounded and spills to host memory).
 int drain_insertions(pemap_ctx* h) {
-  CK(cudaStreamSynchronize(h->stream));
+  {
+    int rc = sync_lanes(h);
+    if (rc) return rc;
+  }
   unsigned long long used = 0;
   CK(cudaMemcpyAsync(&used, h->d_ins_cursor, 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -1193,11 +1294,11 @@ struct SlotGuard {
     for (auto& sl : h->slots) any = any || sl.pending;
     if (any) {
       cudaStreamSynchronize(h->s_h2d);
-      cudaStreamSynchronize(h->stream);
-      cudaStreamSynchronize(h->s_aux);
+      sync_lanes(h);
       cudaStreamSynchronize(h->s_d2h);
       for (auto& sl : h->slots) sl.pending = false;
     }
+    use_lane(h, 0);
   }
 };
 
@@ -1255,6 +1356,10 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
   }
   begin_batch(h, n);
   SlotGuard guard{h};
+  {
+    int rc = fork_lanes(h);
+    if (rc) return rc;
+  }
   const bool direct = rows1 && is_pinned(rows1) && is_pinned(len1) && (!paired || (is_pinned(rows2) && is_pinned(len2))) &&
                       is_pinned(m1) && is_pinned(m2) && is_pinned(mapping_type);
   const bool pipelined = h->keep == 0;  // the inspection modes read shared scratch after every chunk
@@ -1262,10 +1367,11 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
   for (int first = 0; first < n; first += h->chunk, chunk_no++) {
     const int cn = std::min(h->chunk, n - first);
     pemap_ctx::Slot& sl = h->slots[chunk_no & 1];
-    if (sl.pending) {  // the chunk that used this slot two iterations ago
+    if (sl.pending) {  // the chunk that used this slot (and this lane) two iterations ago
       int rc = finish_slot(h, sl, m1, m2, mapping_type);
       if (rc) return rc;
     }
+    use_lane(h, pipelined && h->lanes_->n > 1 ? (chunk_no & 1) : 0);
     if (h->want_drain) {  // the append buffer passed its high-water mark: spill it before more is appended
       int rc = drain_insertions(h);
       if (rc) return rc;
@@ -1366,7 +1472,7 @@ int map_host(pemap_ctx* h, int n, const char* rows1, const char* const* ptr1, co
       if (rc) return rc;
     }
   }
-  return PEMAP_OK;
+  return join_lanes(h);
 }
 
 }  // namespace
@@ -1635,26 +1741,70 @@ int pemap_map_batch_device(pemap_t* h, int n, const char* d_reads1, const int* d
     if (n > 0 && mm[0] == mm[1]) uniform_len = (int)mm[0];
     if (n > 0 && (int)mm[1] > max_len) return fail(h, PEMAP_ERR_ARG, "a read is longer than max_len");
   }
-  for (int first = 0; first < n; first += h->chunk) {
+  // chunks alternate between the two lanes; a lane's previous chunk is booked (stage times, insertion fill) before the
+  // lane is reused.  The inspection modes read a chunk's scratch right after it: they run one chunk at a time.
+  const bool two = h->lanes_->n > 1 && h->keep == 0;
+  {
+    int rc = fork_lanes(h);
+    if (rc) return rc;
+  }
+  struct Pending {
+    bool on = false;
+    int cn = 0;
+  } pend[2];
+  auto book = [&](int lane) -> int {
+    if (!pend[lane].on) return PEMAP_OK;
+    pend[lane].on = false;
+    int rc = account_chunk(h, pend[lane].cn, paired, h->slots[lane].ev);
+    if (rc) return rc;
+    return PEMAP_OK;
+  };
+  int chunk_no = 0;
+  for (int first = 0; first < n; first += h->chunk, chunk_no++) {
     const int cn = std::min(h->chunk, n - first);
-    int rc = run_chunk(h, cn, d_reads1 + (size_t)first * stride, d_len1 + first,
-                       paired ? d_reads2 + (size_t)first * stride : nullptr, paired ? d_len2 + first : nullptr, stride,
-                       max_len, uniform_len, d_m1 + first, d_m2 + first, d_mapping_type + first, h->slots[0].ev);
-    if (rc) return rc;
-    rc = account_chunk(h, cn, paired, h->slots[0].ev);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(h->h_ins_used, h->d_ins_cursor, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    rc = check_insertion_fill(h, h->h_ins_used[0]);
+    const int lane = two ? (chunk_no & 1) : 0;
+    int rc = book(lane);
     if (rc) return rc;
     if (h->want_drain) {
+      rc = book(lane ^ 1);
+      if (rc) return rc;
       rc = drain_insertions(h);
       if (rc) return rc;
     }
-    rc = retain_chunk(h, cn, first, paired);
+    use_lane(h, lane);
+    rc = run_chunk(h, cn, d_reads1 + (size_t)first * stride, d_len1 + first,
+                   paired ? d_reads2 + (size_t)first * stride : nullptr, paired ? d_len2 + first : nullptr, stride,
+                   max_len, uniform_len, d_m1 + first, d_m2 + first, d_mapping_type + first, h->slots[lane].ev);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->h_ins_used + lane, h->d_ins_cursor, 8, cudaMemcpyDeviceToHost, h->stream));
+    pend[lane].on = true;
+    pend[lane].cn = cn;
+    if (!two) {
+      rc = book(lane);
+      if (rc) return rc;
+      CK(cudaStreamSynchronize(h->stream));
+      rc = check_insertion_fill(h, h->h_ins_used[lane]);
+      if (rc) return rc;
+      rc = retain_chunk(h, cn, first, paired);
+      if (rc) return rc;
+    } else if (chunk_no >= 1) {  // the other lane's chunk was submitted one iteration ago: its fill level is (nearly) known
+      CK(cudaEventSynchronize(h->slots[lane ^ 1].ev[4]));
+      rc = check_insertion_fill(h, h->h_ins_used[lane ^ 1]);
+      if (rc) return rc;
+    }
+  }
+  for (int k = 0; k < 2; k++) {
+    int rc = book((chunk_no + k) & 1);
     if (rc) return rc;
   }
-  CK(cudaStreamSynchronize(h->stream));
+  {
+    int rc = join_lanes(h);
+    if (rc) return rc;
+    rc = sync_lanes(h);
+    if (rc) return rc;
+    rc = check_insertion_fill(h, std::max(h->h_ins_used[0], h->h_ins_used[1]));
+    if (rc) return rc;
+  }
   return PEMAP_OK;
 }
 
@@ -2066,6 +2216,25 @@ void pemap_destroy(pemap_t* h) {
   if (!h) return;
   if (h->stream) {
     cudaSetDevice(h->device);
+    if (h->lanes_) {
+      use_lane(h, 0);
+      sync_lanes(h);
+      pemap_lane& o = h->lanes_->saved[1];  // the side lane's working set (lane 0's is the context's own fields)
+      void* dv[] = {o.d_tasks, o.d_results, o.d_cursors, o.d_diag_winners, o.d_exact_winners, o.d_oob_winners, o.d_ires,
+                    o.d_replay_reads, o.d_replay_tasks, o.d_sw_list, o.d_flagq, o.d_walk_meta, o.d_pair_codes, o.d_cand_base,
+                    o.d_cand_n, o.d_winners, o.d_det_best, o.d_det_orient, o.d_det_score, o.d_seed_scratch, o.d_dirs, o.d_pend,
+                    o.d_big_list, o.d_big_list2, o.d_big_scratch};
+      for (void* p : dv)
+        if (p) cudaFree(p);
+      if (o.stream) cudaStreamDestroy(o.stream);
+      if (o.s_aux) cudaStreamDestroy(o.s_aux);
+      if (o.ev_fork) cudaEventDestroy(o.ev_fork);
+      if (o.ev_join) cudaEventDestroy(o.ev_join);
+      if (h->lanes_->ev_main) cudaEventDestroy(h->lanes_->ev_main);
+      if (h->lanes_->ev_side) cudaEventDestroy(h->lanes_->ev_side);
+      delete h->lanes_;
+      h->lanes_ = nullptr;
+    }
     cudaStreamSynchronize(h->stream);
 #ifdef PM_TIE_DEBUG
     {
