@@ -116,7 +116,6 @@ struct pemap_ctx {
   uint32_t* d_replay_reads = nullptr;
   pm::Winner* d_replay_tasks = nullptr;
   int band_half = PM_BAND_LANES / 2;  // PEMAP_BAND_HALF=0/1 narrows the traceback band (tests of the hand-over path)
-  int trace32 = 0;
   uint32_t* d_sw_list = nullptr;  // tasks left for the DP scoring kernel by k_diag_certify
   int certify = 1;                // PEMAP_CERTIFY=0: score every candidate with the DP (cross-check)
   void* d_flagq = nullptr;      // packed decision flags between k_trace_dp16 and k_trace_walk16
@@ -395,7 +394,7 @@ int alloc_lane_scratch(pemap_ctx* h) {
 int alloc_chunk_buffers(pemap_ctx* h) {
   int chunk = 1 << 19;  // reads (pairs) per pass of the kernel chain: larger chunks shorten the persistent kernels' tails
   h->lanes_ = new pemap_lanes();
-  h->lanes_->n = 2;
+  h->lanes_->n = 1;  // a second lane measured no gain (profiles/README_r02.md): opt-in
   if (const char* s = getenv("PEMAP_LANES")) h->lanes_->n = atoi(s) >= 2 ? 2 : 1;
   {  // two lanes of 512 Ki pairs take ~2 x 16.5 GB; beside a human-sized genome's counters halve the chunk instead
     size_t free_b = 0, total_b = 0;
@@ -423,7 +422,6 @@ int alloc_chunk_buffers(pemap_ctx* h) {
   h->task_cap = (uint32_t)std::min<size_t>(2 * n * PM_MAX_HITS, 0x7FFFFFFFull);
   if (const char* s = getenv("PEMAP_CERTIFY")) h->certify = atoi(s) != 0;
   if (const char* s = getenv("PEMAP_EXACT")) h->exact = atoi(s) != 0;
-  if (const char* s = getenv("PEMAP_TRACE32")) h->trace32 = atoi(s) != 0;
   if (const char* s = getenv("PEMAP_BAND_HALF")) h->band_half = std::min(PM_BAND_LANES / 2, std::max(0, atoi(s)));
   h->seed_blocks = h->sm_count * 8;
   h->big_grid = 2 * h->sm_count;
@@ -713,18 +711,6 @@ int ensure_flag_scratch(pemap_ctx* h, size_t bytes_per_pair, size_t code_bytes) 
 
 template <int G, int WD>
 int launch_trace_int(pemap_ctx* h, pm::TraceIntArgs& a) {
-  if (h->trace32) {  // one winner per sub-warp, 32-bit integers (PEMAP_TRACE32=1; kept as a cross-check)
-    const size_t dyn = pm::trace_band_bytes<G, WD>();
-    static int grids32[kMaxDev] = {};
-    int& grid32 = grids32[h->device % kMaxDev];
-    if (!grid32) {
-      cudaFuncSetAttribute(pm::k_trace_i32<G, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-      grid32 = one_wave_grid(h, pm::k_trace_i32<G, WD>, 128, dyn);
-    }
-    pm::k_trace_i32<G, WD><<<grid32, 128, dyn, h->stream>>>(a);
-    h->stats.launches++;
-    return PEMAP_OK;
-  }
   int rc = ensure_flag_scratch(h, pm::trace_flag_bytes_per_pair<G, WD>(), (size_t)pm::trace_code_bytes<G, WD>());
   if (rc) return rc;
   a.flagq = reinterpret_cast<uint2*>(h->d_flagq);

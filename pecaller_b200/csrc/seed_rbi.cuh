@@ -445,6 +445,8 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
       // tag is the segment's tag or one 2-bit field away from it
       // With the running min_match at F the first nseg - F + 2 segments decide whether the strand can matter at all (see
       // close_pair_exists): after a full-length hit on the forward strand the reverse strand is settled by two segments.
+      // (tried for every strand, i.e. also 8 of 10 segments at the initial min_match of 4: 269 against 201 ms per 8 M
+      // read-mates - the probe's hash build and the broken prefetch run cost more than two segments of reads)
       const int k_probe = nseg - min_match + 2 <= nseg / 2 ? nseg - min_match + 2 : 0;
       bool strand_dead = false;
       int cnt = 0;              // warp-uniform copy of sm.g.n_ent between segments

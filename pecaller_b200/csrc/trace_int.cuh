@@ -1,8 +1,7 @@
 // trace_int.cuh - integer traceback of the winners that are not pure diagonals (sm_100a).
 //
-// Two implementations: k_trace_i32 (one winner per sub-warp, 32-bit integers, flags inside the wavefront, lane 0 walks;
-// PEMAP_TRACE32=1, kept as a cross-check) described first, and the production pair k_trace_dp16 + k_trace_walk16
-// (two winners per lane, deferred band pass, cooperative walk) further down; they share the tie certification.
+// The walker and the tie certification come first, the kernel pair k_trace_dp16 + k_trace_walk16 (two winners per
+// lane, deferred band pass, cooperative walk) further down.
 //
 // Replaces smith_waterman_backtrack (pemapper.c:1752-1965) for winners with gaps.  The DP of the winning
 // (read, window) task is recomputed in exact integers (units of 1/36, sw_int16.cuh) with the same sub-warp
@@ -289,138 +288,6 @@ __device__ int walk_check_int(const Cell& cell, const TieCtx& t, int k, int i, i
   return PM_WALK_OK;
 }
 
-template <int G, int WD>
-__global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
-  static_assert(6 * WD <= 64, "decision bits of a lane's columns must fit one 64-bit word");
-  constexpr int GPB = 128 / G;
-  constexpr int ROWS = trace_rows<G, WD>();
-  extern __shared__ unsigned long long s_band_i[];  // [GPB][ROWS][PM_BAND_LANES]
-  __shared__ unsigned char s_win[GPB][ROWS];
-  __shared__ unsigned char s_q[GPB][ROWS];          // one-hot codes of the oriented read (columns <= G * WD <= ROWS)
-  const int tid = threadIdx.x, grp = tid / G, gl = tid % G;
-  const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((tid & 31) / G * G));
-  const uint32_t n_items = *a.n_items;
-  const uint32_t ggid = blockIdx.x * GPB + grp;
-  unsigned char* win = s_win[grp];
-  unsigned long long* band = s_band_i + (size_t)grp * ROWS * PM_BAND_LANES;
-  const int bis = a.p.is_bisulfite;
-  PileSink sink = a.sink;
-  sink.pend = a.sink.pend + (size_t)ggid * PM_DP_MAX;
-
-  for (;;) {
-    uint32_t first;
-    const uint32_t item = next_work_item_warp<G>(a.work, &first);
-    if (first >= n_items) break;
-    if (item >= n_items) continue;  // the warp's other sub-warp still has an item
-    const uint32_t task_id = a.winners[item].task;
-    const Task tk = a.tasks[task_id];
-    const TaskResult res = a.results[task_id];
-    const int orient = (int)(tk.rm >> 31);
-    const uint32_t rm = tk.rm & 0x7FFFFFFFu;
-    const int mm = ((rm & 1u) ? a.len[1] : a.len[0])[rm >> 1];
-    const char* read = ((rm & 1u) ? a.reads[1] : a.reads[0]) + (size_t)(rm >> 1) * a.stride;
-    const int nn = res.maxi < tk.blen ? res.maxi : tk.blen;  // rows below the winning cell are never consulted
-    const int dend = res.maxi - mm;
-
-    __syncwarp(gmask);
-    // one-hot base codes: two bases match iff their codes share a bit; 0 = outside ACGTN (the scoring kernel sent
-    // such reads to the fp64 path; their traceback goes there too)
-    bool bad = false;
-    for (int i = gl; i < nn; i += G) {
-      const char ch = a.genome[(size_t)tk.wstart + i];
-      unsigned c = ch == 'A' ? 1u : ch == 'C' ? (bis ? 10u : 2u) : ch == 'G' ? 4u : ch == 'T' ? 8u : (ch == 'N' || ch == 'n') ? 15u : 0u;
-      bad |= (c == 0u);
-      win[i] = (unsigned char)c;
-    }
-    unsigned q[WD];
-    int s0u[WD], s1u[WD], mu[WD];
-    const int jbase = gl * WD;
-#pragma unroll
-    for (int c = 0; c < WD; c++) {
-      const int j0 = jbase + c;
-      unsigned qc = 0;
-      if (j0 < mm) {
-        const char ch = oriented_char(read, mm, orient, j0);
-        qc = ch == 'A' ? 1u : ch == 'C' ? 2u : ch == 'G' ? 4u : ch == 'T' ? 8u : (ch == 'N' || ch == 'n') ? 15u : 0u;
-        bad |= (qc == 0u);
-      }
-      q[c] = qc;
-      s_q[grp][j0] = (unsigned char)qc;
-      const int b = -(72 + j0);  // S*[0][j] = -(go + (j-1) ge), j = j0 + 1 (2073-2081)
-      s0u[c] = b;
-      s1u[c] = b;
-      mu[c] = b;
-    }
-    bad = __any_sync(gmask, bad);
-    int out_s0 = 0, out_s2 = 0, out_m = 0;
-    __syncwarp(gmask);
-
-    const int steps = nn > 0 ? nn + G - 1 : 0;
-    for (int s = 0; s < steps; s++) {
-      int l_s0 = __shfl_up_sync(gmask, out_s0, 1, G);
-      int l_s2 = __shfl_up_sync(gmask, out_s2, 1, G);
-      int diag = __shfl_up_sync(gmask, out_m, 1, G);
-      if (gl == 0) {  // column 0 (2062-2081)
-        l_s0 = 0;
-        l_s2 = -72;
-        diag = 0;
-      }
-      const int i = s - gl + 1;
-      if (i >= 1 && i <= nn) {
-        const unsigned rc = win[i - 1];
-        unsigned long long dword = 0;
-#pragma unroll
-        for (int c = 0; c < WD; c++) {
-          const int s2 = max(l_s0 - 72, l_s2 - 1);
-          const int s1 = max(s0u[c] - 72, s1u[c] - 1);
-          const int s0 = diag + ((q[c] & rc) ? 36 : -12);
-          diag = mu[c];
-          const int m01 = max(s0, s1);
-          const int m = max(m01, s2);
-          const int opn = s0 - 72;
-          const unsigned ak = (s1 - 1 == opn || s2 - 1 == opn) ? 3u : (s2 > m01) ? 2u : (s1 > s0) ? 1u : 0u;
-          const unsigned bits = ak | ((s1 - 1 > opn) ? 4u : 0u) | ((s2 - 1 > opn) ? 8u : 0u) | ((s1 == s0) ? 16u : 0u) |
-                                ((s2 == m01) ? 32u : 0u);
-          dword |= (unsigned long long)bits << (6 * c);
-          s0u[c] = s0;
-          s1u[c] = s1;
-          mu[c] = m;
-          l_s0 = s0;
-          l_s2 = s2;
-        }
-        out_s0 = l_s0;
-        out_s2 = l_s2;
-        out_m = diag;
-        const int slot = gl - (band_center_lane<WD>(i, dend) - a.band_half);
-        if (slot >= 0 && slot <= 2 * a.band_half) band[(i - 1) * PM_BAND_LANES + slot] = dword;
-      }
-    }
-    __syncwarp(gmask);
-
-    if (gl == 0 && nn > 0) {
-      BandCell<WD, 6> cell;
-      cell.band = band;
-      cell.dend = dend;
-      cell.half = a.band_half;
-      TieCtx tc;
-      tc.win = win;
-      tc.qcode = s_q[grp];
-      tc.shift = 0;
-      const int r36 = (int)lrint(res.score * 36.0);
-      int rc = bad ? PM_WALK_TIE : walk_check_int(cell, tc, res.maxk, res.maxi, mm, r36);
-      atomicAdd(&a.counters->tb_cells_int, (unsigned long long)nn * (unsigned long long)mm);
-      if (rc == PM_WALK_OK) {
-        walk_path<true, 0>(cell, res.maxk, res.maxi, mm, read, mm, orient, tk.wstart, sink, s_q[grp], 0);
-      } else {
-        const uint32_t w = atomicAdd(a.exact_cursor, 1u);
-        a.exact_winners[w] = a.winners[item];
-        atomicAdd(&a.counters->exact_traced, 1ull);
-      }
-    }
-    __syncwarp(gmask);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Packed integer traceback: k_trace_dp16 + k_trace_walk16.
 //
@@ -430,8 +297,7 @@ __global__ void __launch_bounds__(128) k_trace_i32(TraceIntArgs a) {
 //     F0  S1 > S0                 F1  S2 > max(S0,S1)     F2  X1     F3  X2
 //     F4  S1 == S0, or X1 tie     F5  S2 == max(S0,S1), or X2 tie
 // (S1 >= S0 implies X1, so F4 without F2 is free to mean "S1 - ge == S0 - go"; likewise F5 without F3 for X2.  The
-// accessor turns them into bits 6 / 7; the A decision of such a cell stays usable, unlike with the A == 3 mark of
-// k_trace_i32.)
+// accessor turns them into bits 6 / 7; the A decision of such a cell stays usable.)
 //
 // Only the cells near the winners' end diagonal are ever consulted by the walk: lane l (columns WD*l+1 .. WD*l+WD)
 // is "in the band" for the nb = (half+1)*WD rows starting at r0(l) = WD*l - WD/2 + dmid + 1, and at any step of the
