@@ -387,6 +387,7 @@ def main():
     from pecaller_b200 import sharding
     reducer = sharding.SliceReducer(mapper) if world > 1 else None
     site_range = [None]
+    red = {"s": 0.0, "n": 0}   # wall time and count of the slice-wise counter sums inside the timed device leg
 
     def barrier():
         torch.cuda.synchronize()
@@ -399,7 +400,10 @@ def main():
                           d_m1.data_ptr(), d_m2.data_ptr(), d_ty.data_ptr())
         if world > 1 and (last or (i + 1) % a.reduce_every == 0):
             # slice-wise sum over NVLink peer memory: rank r ends up with the final counters of its 1/N of the genome
+            t_r = time.perf_counter()
             site_range[0] = reducer.reduce_scatter()
+            red["s"] += time.perf_counter() - t_r
+            red["n"] += 1
             mapper.reset_counts()
 
     fin = {"records": 0}
@@ -420,6 +424,7 @@ def main():
         step_device()
     mapper.reset_counts()
     mapper.reset_stats()
+    red["s"], red["n"] = 0.0, 0
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -542,6 +547,8 @@ def main():
                            "parallelism": ("reads sharded over %d GPUs, index replicated, pileup counters summed slice-wise over NVLink peer "
                                            "memory every %d steps (and at the end of the timed region), every GPU compacts its own "
                                            "1/%d of the genome" % (world, a.reduce_every, world)) if world > 1 else "1 GPU",
+                           "counter_sum_ms": round(1000.0 * red["s"] / max(red["n"], 1), 1) if world > 1 else None,
+                           "counter_sums_in_timed_region": red["n"],
                            "index_build_s": round(t_index, 2), "datagen_s": round(t_gen + t_genome, 2),
                            "hbm_used_gb": round((total_b - free_b) / 1e9, 1)},
                 "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": 2 * n * STRIDE + 2 * n * 4,

@@ -115,6 +115,14 @@ void pemap_default_params(pemap_params *p);
    call and copied to `device`.  Called once per GPU. */
 int pemap_init(pemap_t **h, const pemap_index *ix, const pemap_params *p, int device);
 
+/* pemap_init without the 16 GiB host table: ix->pos_index may be NULL and `next_idx_bytes(ctx, dst, bytes)` is called
+   (2^32+1)*4 / 64 MiB times, in order, to write the next `bytes` bytes of the inflated .idx stream into page-locked
+   staging of the library (return non-zero to abort); each chunk is copied to the GPU while the caller inflates the
+   next one.  The C host's gzread goes straight into `dst` (init_index_buffer, pemapper.c:2129-2149, chunked). */
+typedef int (*pemap_fill_cb)(void *ctx, void *dst, size_t bytes);
+int pemap_init_streamed(pemap_t **h, const pemap_index *ix, pemap_fill_cb next_idx_bytes, void *ctx,
+                        const pemap_params *p, int device);
+
 /* Same, but builds pos_index/mers on the device from the genome (what index_genome_whole.c:169-177, 248-299,
    334-351 computes), so no 16 GiB host table is needed.  contig_len are REAL lengths (.sdx value + 15). */
 int pemap_init_from_genome(pemap_t **h, const char *genome, const int64_t *contig_len, int no_contigs,

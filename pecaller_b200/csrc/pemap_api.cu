@@ -1508,12 +1508,17 @@ void pemap_default_params(pemap_params* p) {
 const char* pemap_last_error(pemap_t* h) { return h ? h->err.c_str() : "NULL handle"; }
 
 int pemap_init(pemap_t** out, const pemap_index* ix, const pemap_params* p, int device) {
+  return pemap_init_streamed(out, ix, nullptr, nullptr, p, device);
+}
+
+int pemap_init_streamed(pemap_t** out, const pemap_index* ix, pemap_fill_cb next_idx_bytes, void* cb_ctx, const pemap_params* p,
+                        int device) {
   if (!out) return PEMAP_ERR_ARG;
   pemap_ctx* h = new pemap_ctx();
   *out = h;
   int rc = check_params(h, p);
   if (rc) return rc;
-  if (!ix || !ix->pos_index || !ix->mers || !ix->genome || !ix->contig_starts)
+  if (!ix || (!ix->pos_index && !next_idx_bytes) || !ix->mers || !ix->genome || !ix->contig_starts)
     return fail(h, PEMAP_ERR_ARG, "index has NULL members");
   rc = check_contigs(h, ix->no_contigs);
   if (rc) return rc;
@@ -1525,7 +1530,36 @@ int pemap_init(pemap_t** out, const pemap_index* ix, const pemap_params* p, int 
   h->n_mers = ix->n_mers;
   const size_t idx_words = ((size_t)1 << 32) + 1;
   CK(cudaMalloc(&h->d_pos_index, idx_words * 4));
-  CK(cudaMemcpy(h->d_pos_index, ix->pos_index, idx_words * 4, cudaMemcpyHostToDevice));
+  if (next_idx_bytes) {
+    // init_index_buffer (2129-2149) without the 16 GiB host table: the caller inflates the .idx stream chunk by chunk
+    // straight into page-locked staging, every chunk is on its way to the GPU while the next one is inflated
+    const size_t chunk = (size_t)64 << 20, total = idx_words * 4;
+    char* stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2; k++) {
+      CK(cudaHostAlloc(&stage[k], chunk, cudaHostAllocDefault));
+      CK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+    }
+    int cb_rc = 0;
+    size_t at = 0;
+    for (int k = 0; at < total && !cb_rc; k ^= 1) {
+      const size_t nb = std::min(chunk, total - at);
+      CK(cudaEventSynchronize(done[k]));  // the copy that used this buffer two chunks ago
+      cb_rc = next_idx_bytes(cb_ctx, stage[k], nb);
+      if (cb_rc) break;
+      CK(cudaMemcpyAsync(reinterpret_cast<char*>(h->d_pos_index) + at, stage[k], nb, cudaMemcpyHostToDevice, h->s_h2d));
+      CK(cudaEventRecord(done[k], h->s_h2d));
+      at += nb;
+    }
+    CK(cudaStreamSynchronize(h->s_h2d));
+    for (int k = 0; k < 2; k++) {
+      cudaFreeHost(stage[k]);
+      cudaEventDestroy(done[k]);
+    }
+    if (cb_rc) return fail(h, PEMAP_ERR_ARG, "pemap_init_streamed: the .idx callback failed (short file?)");
+  } else {
+    CK(cudaMemcpy(h->d_pos_index, ix->pos_index, idx_words * 4, cudaMemcpyHostToDevice));
+  }
   CK(cudaMalloc(&h->d_mers, (size_t)(h->n_mers + 4) * 4));
   CK(cudaMemcpy(h->d_mers, ix->mers, (size_t)h->n_mers * 4, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_genome, h->genome_size + 64));
@@ -2006,7 +2040,13 @@ int reduce_slice(pemap_ctx* h, const pm::PeerPtrs& peers, uint64_t s0, uint64_t 
   if (s1 > s0 && peers.n > 0) {
     // word range [6 * s0, 6 * s1): s0 is a multiple of 2048; round the end up to 16 bytes (the array has 64 bytes of slack)
     const uint64_t first = 6 * s0, n_words = (6 * (s1 - s0) + 3) & ~3ull;
-    pm::k_reduce_slice<<<h->sm_count * 8, 256, 0, h->stream>>>(h->d_counts, peers, first, n_words);
+    const int grid = h->sm_count * 8;
+    switch (peers.n) {
+      case 1: pm::k_reduce_slice<1><<<grid, 256, 0, h->stream>>>(h->d_counts, peers, first, n_words); break;
+      case 3: pm::k_reduce_slice<3><<<grid, 256, 0, h->stream>>>(h->d_counts, peers, first, n_words); break;
+      case 7: pm::k_reduce_slice<7><<<grid, 256, 0, h->stream>>>(h->d_counts, peers, first, n_words); break;
+      default: pm::k_reduce_slice<0><<<grid, 256, 0, h->stream>>>(h->d_counts, peers, first, n_words); break;
+    }
     h->stats.launches++;
     CK(cudaGetLastError());
   }

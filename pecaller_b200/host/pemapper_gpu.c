@@ -205,6 +205,18 @@ static slot_t *slot_new(long cap, int paired) {
   return s;
 }
 
+/* pemap_fill_cb over a gzFile: the next `bytes` bytes of the inflated .idx */
+static int idx_chunk(void *ctx, void *dst, size_t bytes) {
+  size_t done = 0;
+  while (done < bytes) {
+    const unsigned want = (unsigned)((bytes - done) > (1u << 30) ? (1u << 30) : (bytes - done));
+    const int got = gzread((gzFile)ctx, (char *)dst + done, want);
+    if (got <= 0) return 1;
+    done += (size_t)got;
+  }
+  return 0;
+}
+
 /* ---- one submitting thread per GPU (replaces the reference's pool of map_everything threads, 677-702) ---- */
 typedef struct {
   pemap_t *h;
@@ -770,7 +782,27 @@ int main(int argc, char **argv) {
       if (rc) printf("\n pemap_init failed on GPU %d: %s \n", device + g, pemap_last_error(hs[g]));
     }
     free(lens);
-  } else { /* init_index_buffer 2129-2155 */
+  } else if (n_gpus == 1) { /* init_index_buffer 2129-2155, streamed: gzread inflates straight into the library's pinned staging */
+    snprintf(path, sizeof path, "%s.mdx", sdxbase);
+    FILE *mf = fopen(path, "rb");
+    if (!mf) die(" Could not read the .mdx file ");
+    fseek(mf, 0, SEEK_END);
+    const uint64_t n_mers = (uint64_t)ftell(mf) / 4;
+    fseek(mf, 0, SEEK_SET);
+    uint32_t *mers = malloc((n_mers + 1) * 4);
+    if (!mers || fread(mers, 4, n_mers, mf) != n_mers) die(" Could not read the .mdx file ");
+    fclose(mf);
+    snprintf(path, sizeof path, "%s.idx", sdxbase);
+    gf = gzopen(path, "r");
+    if (!gf) die(" Could Not Open the .idx file ");
+    gzbuffer(gf, 33554432);
+    printf("\n About to read kmers index \n\n");
+    pemap_index ix = {NULL, mers, n_mers, genome, genome_size, sdx.starts, sdx.n};
+    rc = pemap_init_streamed(&hs[0], &ix, idx_chunk, gf, &prm, device);
+    if (rc) printf("\n pemap_init failed on GPU %d: %s \n", device, pemap_last_error(hs[0]));
+    gzclose(gf);
+    free(mers);
+  } else { /* several GPUs: inflate once into the host table, every GPU gets a copy */
     const size_t words = ((size_t)1 << 32) + 1;
     uint32_t *pos_index = malloc(words * 4);
     if (!pos_index) die(" Can not allocate space for the position index ");

@@ -56,7 +56,7 @@ class Stats(C.Structure):
 
 SITE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)  # pemap_site_cb(ctx, records, n)
 
-EXPORTS = ["pemap_version", "pemap_default_params", "pemap_init", "pemap_init_from_genome", "pemap_set_params",
+EXPORTS = ["pemap_version", "pemap_default_params", "pemap_init", "pemap_init_streamed", "pemap_init_from_genome", "pemap_set_params",
            "pemap_map_batch", "pemap_map_batch_rows", "pemap_map_batch_device", "pemap_keep", "pemap_get_detail",
            "pemap_get_candidates", "pemap_finish", "pemap_finish_stream", "pemap_finish_stream_range", "pemap_get_insertions", "pemap_counts_ipc_handle",
            "pemap_reduce_scatter_ipc", "pemap_reduce_scatter_local", "pemap_host_alloc", "pemap_host_free", "pemap_sw_score_device", "pemap_packed_stride", "pemap_pack_read",
