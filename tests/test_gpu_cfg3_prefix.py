@@ -27,7 +27,7 @@ def _host_ram_gb():
     return 0.0
 
 
-def _parity(config, n, single, need_gb):
+def _parity(config, n, need_gb, also_single=0):
     import oracle_lib as ol
     if not ol.have_reference_lib():
         pytest.skip("oracle/_ref/libpemapper_ref.so was not built")
@@ -35,27 +35,27 @@ def _parity(config, n, single, need_gb):
         pytest.skip("the reference needs 32 B per genome base + the 16 GiB table on the host")
     if os.environ.get("PEMAP_SKIP_BIG_PARITY") == "1":
         pytest.skip("PEMAP_SKIP_BIG_PARITY=1")
-    env = dict(os.environ, PEMAP_PARITY_CONFIG=config, PEMAP_PARITY_SINGLE="1" if single else "0")
+    env = dict(os.environ, PEMAP_PARITY_CONFIG=config, PEMAP_PARITY_SINGLE="0", PEMAP_PARITY_ALSO_SINGLE=str(also_single))
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cfg3_parity.py"), str(n)], env=env, capture_output=True,
                        text=True, timeout=1500)
     assert r.stdout.strip(), r.stderr[-2000:]
     out = json.loads(r.stdout)
-    for k, v in out["identical"].items():
-        assert v, "%s: %s differs from the reference (%s)" % (config, k, json.dumps(out["cuda"])[:400])
+    for part in (out, out.get("single_end")):
+        if part:
+            for k, v in part["identical"].items():
+                assert v, "%s: %s differs from the reference (%s)" % (config, k, json.dumps(part["cuda"])[:400])
     return out
 
 
 def test_cfg3_prefix_equals_reference():
-    out = _parity("cfg3", int(os.environ.get("PEMAP_CFG3_TEST_PAIRS", 500_000)), False, 170)
+    out = _parity("cfg3", int(os.environ.get("PEMAP_CFG3_TEST_PAIRS", 300_000)), 170)
     assert out["cuda"]["type_counts"][0] > 0.99 * out["pairs"]
 
 
-def test_cfg5_repeats_single_end_equals_reference():
-    """200 k single-end reads on the high-repeat genome: ~15 % tie between repeat copies, where the reference's rounded
-    doubles decide between "unique" and "discarded" - the narrowed fp64 replay must reproduce every one."""
-    out = _parity("cfg5", int(os.environ.get("PEMAP_CFG5_TEST_READS", 200_000)), True, 40)
-    assert out["cuda"]["replayed_fp64_read_mates"] > 0.05 * out["pairs"]
-
-
-def test_cfg5_repeats_paired_equals_reference():
-    _parity("cfg5", int(os.environ.get("PEMAP_CFG5_TEST_PAIRS", 100_000)), False, 40)
+def test_cfg5_repeats_equal_reference():
+    """The high-repeat genome, 100 k pairs and 200 k single-end reads: ~15 % of the single-end reads tie between repeat
+    copies, where the reference's rounded doubles decide between "unique" and "discarded" - the narrowed fp64 replay
+    must reproduce every one."""
+    out = _parity("cfg5", int(os.environ.get("PEMAP_CFG5_TEST_PAIRS", 100_000)), 40,
+                  also_single=int(os.environ.get("PEMAP_CFG5_TEST_READS", 200_000)))
+    assert out["single_end"]["cuda"]["replayed_fp64_read_mates"] > 0.05 * out["single_end"]["pairs"]

@@ -13,8 +13,7 @@ run python tools/cfg5_check.py > $O/cfg5_check_r02.json 2> $O/cfg5_check.err
 run python tools/cfg4_sweep.py > $O/cfg4_sweep_r02.json 2> $O/cfg4_sweep.err
 run python tools/sw_sweep.py > $O/sw_sweep_r02.json 2> $O/sw_sweep.err
 run python tools/cfg3_parity.py 2000000 > $O/cfg3_parity_r02.json 2> $O/cfg3_parity.err
-PEMAP_PARITY_CONFIG=cfg5 PEMAP_PARITY_SINGLE=1 run python tools/cfg3_parity.py 200000 > $O/cfg5_parity_single_r02.json 2> $O/cfg5_parity_s.err
-PEMAP_PARITY_CONFIG=cfg5 run python tools/cfg3_parity.py 200000 > $O/cfg5_parity_paired_r02.json 2> $O/cfg5_parity_p.err
+PEMAP_PARITY_CONFIG=cfg5 PEMAP_PARITY_ALSO_SINGLE=400000 run python tools/cfg3_parity.py 200000 > $O/cfg5_parity_r02.json 2> $O/cfg5_parity.err
 run python tools/cli_e2e.py 10000000 > $O/cli_e2e_r02.json 2> $O/cli_e2e.err
 run python bench.py --steps 5 --warmup 3 > $O/bench_cfg3_r02.json 2> $O/bench_cfg3.err
 run python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref_cfg3_r02.json 2> $O/bench_ref_cfg3.err
