@@ -603,6 +603,7 @@ int build_rbi(pemap_ctx* h, uint32_t* code, const uint32_t* val, uint64_t n) {
     CKB(cudaMalloc(&h->d_rbi_data[g], bytes));
     CKB(cudaMemsetAsync(h->d_rbi_data[g], 0xFF, bytes, h->stream));
     if (ne) pm::k_rbi_fill<<<eblk, 256, 0, h->stream>>>(kk, vv, ne, bstart, h->d_rbi_dir[g], h->d_rbi_data[g]);
+    if (ne) pm::k_rbi_flag_buckets<<<eblk, 256, 0, h->stream>>>(kk, vv, ne, h->d_rbi_dir[g]);
     h->rbi_bytes += bytes + (size_t)nb24 * 4;
   }
   CKB(cudaStreamSynchronize(h->stream));
@@ -883,6 +884,8 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     ra.big_scratch = h->d_big_scratch;
     ra.fast_cap = PM_RBI_CAP;
     if (const char* s = getenv("PEMAP_RBI_CAP")) ra.fast_cap = std::min(PM_RBI_CAP, std::max(1, atoi(s)));
+    ra.shortcut = 1;
+    if (const char* s = getenv("PEMAP_SHORTCUT")) ra.shortcut = atoi(s) != 0;
     ra.p = sa.p;
     const int work = paired ? 2 * n : n;
     static int rbi_wave[kMaxDev] = {}, rbi_wave2[kMaxDev] = {};
@@ -1046,6 +1049,11 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     si.replay_tasks = h->d_replay_tasks;
     si.replay_task_cursor = h->d_cursors + 3;
     si.counters = h->d_counters;
+    si.reads[0] = d_r1;
+    si.reads[1] = d_r2;
+    si.stride = stride;
+    si.genome = h->d_genome;
+    si.border = h->d_border;
     si.p = sa.p;
     pm::k_select_int<<<(n + 127) / 128, 128, 0, h->stream>>>(si);
     // exact replay: fp64 scores of every candidate of the flagged reads, then the fp64 selection rules on them

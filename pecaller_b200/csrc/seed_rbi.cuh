@@ -66,7 +66,7 @@ __host__ __device__ __forceinline__ uint32_t rbi_units(uint32_t n) {  // blocks 
 
 struct RbiIndex {
   const uint4* data[4];     // bucket arrays of the four rotations
-  const uint32_t* dir[4];   // 2^24+1 offsets each, in 80-byte blocks
+  const uint32_t* dir[4];   // 2^24+1 offsets each, in 80-byte blocks; bit 31 = PM_RBI_DIR_FLAG of the bucket
 };
 
 // ------------------------------------------------------------------------------------------------ builder kernels
@@ -142,6 +142,15 @@ __global__ void __launch_bounds__(256) k_rbi_fill(const uint32_t* key, const uin
   blk[64 + (r & 15u)] = (unsigned char)(k & 255u);
 }
 
+// Bit 31 of a directory word: the bucket holds at least one crowded-k-mer marker.  The single-chain shortcut of the seed
+// kernel leaves most buckets of a strand unread; a marker in one of them would empty its segment's list (1602-1606), so
+// it only skips buckets whose flag is clear.  Set after k_rbi_fill (which reads the plain offsets).
+#define PM_RBI_DIR_FLAG 0x80000000u
+__global__ void __launch_bounds__(256) k_rbi_flag_buckets(const uint32_t* key, const uint32_t* val, uint64_t n, uint32_t* dir) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && val[i] == PM_RBI_MARK) atomicOr(&dir[key[i] >> 8], PM_RBI_DIR_FLAG);
+}
+
 // ------------------------------------------------------------------------------------------------ packed reads
 // Row of a packed read (pemap.h: pemap_pack_read): code words (base i at bits 31-2(i%16), 30-2(i%16) of word i/16; A 0,
 // C 1, G 2, T 3 as convert_seq_int codes them, N stored as 0), then N-mask words (bit i%32 of word i/32).
@@ -199,6 +208,7 @@ struct SeedRbiArgs {
   const uint32_t* work_n;
   unsigned char* big_scratch;  // BIG: per warp PM_RBI_BIG_BYTES
   int fast_cap;                // entries of a strand the first pass accepts (<= PM_RBI_CAP; PEMAP_RBI_CAP lowers it in tests)
+  int shortcut;                // single-chain shortcut on (PEMAP_SHORTCUT=0 switches it off: the on/off parity test)
   DevParams p;
 };
 
@@ -206,7 +216,7 @@ struct SeedRbiArgs {
 
 struct RbiWarpSmem {           // per warp, every path
   uint32_t b_off[2 * PM_RBI_MAXB];   // bucket start (16-byte units), both strands: [4 * (strand * nseg + segment) + rotation]
-  uint16_t b_n4[2 * PM_RBI_MAXB];    // its position quads (<= 256 * 99 / 4)
+  uint16_t b_n4[2 * PM_RBI_MAXB];    // its position quads (<= 256 * 99 / 4) in bits 0-14, the bucket's PM_RBI_DIR_FLAG in bit 15
   uint32_t kcode[2 * PM_MAX_SEG];
   uint32_t hit_pos[PM_MAX_HITS];
   uint16_t hit_off[PM_MAX_HITS];
@@ -373,9 +383,9 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
       const int g = b & 3;
       const uint32_t code = sm.kcode[b >> 2];
       const uint32_t bk = rbi_bucket(code, g);
-      const uint32_t d0 = __ldg(a.ix.dir[g] + bk), d1 = __ldg(a.ix.dir[g] + bk + 1);
+      const uint32_t w0 = __ldg(a.ix.dir[g] + bk), d0 = w0 & ~PM_RBI_DIR_FLAG, d1 = __ldg(a.ix.dir[g] + bk + 1) & ~PM_RBI_DIR_FLAG;
       sm.b_off[b] = d0;
-      sm.b_n4[b] = (uint16_t)(4u * (d1 - d0));  // quads of positions: four per block
+      sm.b_n4[b] = (uint16_t)((4u * (d1 - d0)) | ((w0 >> 31) << 15));  // quads of positions: four per block
     }
     __syncwarp();
     // lanes 8g..8g+7 read the bucket of rotation g
@@ -441,6 +451,223 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
         }
         return __any_sync(0xFFFFFFFFu, yes) != 0;
       };
+      // ---- single-chain shortcut (the model and its proof obligations: tools/seed_shortcut_model.py).
+      // A read that comes from this strand of a unique locus has one chain of hits on ONE diagonal d, and most of its
+      // segments find d through their exact k-mer, i.e. in rotation 0.  Read rotation 0 of every segment; let F0 be the
+      // best found count over those entries alone and k = nseg - F0 + 2.  Any anchor with found >= F0 has at most
+      // nseg - F0 of its segments missing, so two of its chain's members sit in the first k segments: read those k
+      // segments in full (and the segments rotation 0 left without an entry near d, to count d's own chain exactly).
+      // If, inside the first k segments, only entries exactly on d pair up across segments (within 2 (max_off - 1)),
+      // every anchor that reaches F0 lies on d; they share one dedup key (2269), the first of them has the largest
+      // count F >= F0 > min_match and resets the hit list (2251-2260).  The 200-cap return (2283) cannot fire before
+      // it: the anchors examined before it are entries of the first k segments, and tot + their number < max_hits is
+      // required; neither can the min_spots rule (2200-2207), segment 0's list being among them.  Buckets that stay
+      // unread must not hold a crowded-k-mer marker (PM_RBI_DIR_FLAG); a marker met in a bucket that IS read, an
+      // overflow, or any failed condition makes no claim and the strand runs through the full gather below.
+      auto try_single_chain = [&]() -> bool {
+        const unsigned FULLM = 0xFFFFFFFFu;
+        bool over = false;
+        auto seg_off = [&](const int s) { return (s < total_cuts) ? 16ll * s : (long long)(len - 16); };
+        auto prefetch_bucket = [&](const int s, const int g) {
+          const int bp = 4 * (strand * nseg + s) + g;
+          const char* p0 = reinterpret_cast<const char*>(a.ix.data[g] + 5ull * sm.b_off[bp]);
+          const uint32_t bytes = 20u * (sm.b_n4[bp] & 0x7FFFu);
+          const char* line = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)127) + 128 * l8;
+          for (; line < p0 + bytes; line += 8 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+        };
+        // lanes 8 * (lane >> 3) .. + 7 read bucket (sg, rg); entries carry their segment (they interleave)
+        auto gather_round = [&](const int sg, const int rg, const bool active) {
+          constexpr int SC_UNROLL = 2;  // (the buckets were prefetched into L2; registers are what is short here)
+          const int b = 4 * (strand * nseg + (active ? sg : 0)) + rg;
+          const uint32_t n4 = active ? (sm.b_n4[b] & 0x7FFFu) : 0u;
+          const uint4* base = a.ix.data[rg] + 5ull * sm.b_off[b];
+          const uint32_t etagx = ((sm.kcode[strand * nseg + (active ? sg : 0)] >> (8 * rg)) & 255u) * 0x01010101u;
+          const uint32_t keep = rg == 0 ? 0x80808080u : 0u;
+          const uint32_t nmax = __reduce_max_sync(FULLM, n4);
+          for (uint32_t q0 = 0; q0 < nmax; q0 += 8 * SC_UNROLL) {
+            uint4 P[SC_UNROLL];
+            uint32_t T[SC_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SC_UNROLL; u++) {
+              const uint32_t q = q0 + (uint32_t)(8 * u + l8);
+              T[u] = etagx ^ 0x0F0F0F0Fu;
+              if (q < n4) {
+                const uint4* blk = base + 5u * (q >> 2);
+                P[u] = rbi_ld16(blk + (q & 3u));
+                T[u] = rbi_ld4(reinterpret_cast<const uint32_t*>(blk + 4) + (q & 3u));
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < SC_UNROLL; u++) {
+              const uint32_t X = T[u] ^ etagx;
+              const uint32_t D = (X | (X >> 1)) & 0x55555555u;
+              const uint32_t Z = D & ((D | 0x80808080u) - 0x01010101u);
+              uint32_t hit = ((Z + 0x7F7F7F7Fu) & 0x80808080u) ^ 0x80808080u;
+              hit &= ((D + 0x7F7F7F7Fu) & 0x80808080u) | keep;
+              if (hit) {
+                const uint32_t at = atomicAdd(&sm.g.n_ent, (uint32_t)__popc(hit));
+                if (at + 4u <= (uint32_t)cap) {
+                  uint32_t w = at;
+                  if (hit & 0x80u) { st_pos[w] = P[u].x; st_seg[w++] = (uint8_t)sg; }
+                  if (hit & 0x8000u) { st_pos[w] = P[u].y; st_seg[w++] = (uint8_t)sg; }
+                  if (hit & 0x800000u) { st_pos[w] = P[u].z; st_seg[w++] = (uint8_t)sg; }
+                  if (hit & 0x80000000u) { st_pos[w] = P[u].w; st_seg[w++] = (uint8_t)sg; }
+                } else {
+                  over = true;
+                }
+              }
+            }
+          }
+        };
+        // entries [from, n): a marker -> -1; padding is squeezed out; -> the new n
+        auto screen = [&](const int from, int n) {
+          bool mark = false, pad = false;
+          for (int e = from + lane; e < n; e += 32) {
+            const uint32_t v = st_pos[e];
+            mark |= v == PM_RBI_MARK;
+            pad |= v == PM_RBI_EMPTY;
+          }
+          if (__any_sync(FULLM, mark)) return -1;
+          if (__any_sync(FULLM, pad)) {
+            int wr = from;
+            for (int e0 = from; e0 < n; e0 += 32) {
+              const int e = e0 + lane;
+              const uint32_t v = e < n ? st_pos[e] : PM_RBI_EMPTY;
+              const uint8_t sv = e < n ? st_seg[e] : (uint8_t)0;
+              const unsigned bal = __ballot_sync(FULLM, v != PM_RBI_EMPTY);
+              __syncwarp();
+              if (v != PM_RBI_EMPTY) {
+                const int to = wr + __popc(bal & ((1u << lane) - 1u));
+                st_pos[to] = v;
+                st_seg[to] = sv;
+              }
+              wr += __popc(bal);
+              __syncwarp();
+            }
+            n = wr;
+          }
+          return n;
+        };
+        if (lane == 0) sm.g.n_ent = 0;
+        __syncwarp();
+        // rotation 0 of every segment, four segments at a time
+        for (int s = rot; s < nseg; s += 4) prefetch_bucket(s, 0);
+        for (int s0 = 0; s0 < nseg; s0 += 4) gather_round(s0 + rot, 0, s0 + rot < nseg);
+        __syncwarp();
+        int n0 = (int)sm.g.n_ent;
+        if (__any_sync(FULLM, over) || n0 > cap) return false;
+        n0 = screen(0, n0);
+        if (n0 <= 0) return false;
+        if (lane == 0) sm.g.n_ent = (uint32_t)n0;  // (padding may have been squeezed out: the second part appends here)
+        build_hash(n0);
+        // best anchor over rotation 0 alone: largest found, then the lowest entry
+        uint32_t bestkey = 0;
+        for (int e = lane; e < n0; e += 32) {
+          const int s = st_seg[e];
+          const long long dg = (long long)st_pos[e] + 512ll - seg_off(s);
+          const uint32_t bin = (uint32_t)(dg >> 4);
+          uint32_t segs = 0;
+#pragma unroll
+          for (int db = 0; db < 3; db++) {
+            uint32_t q = st_head[rbi_hash(bin + (uint32_t)(db - 1), tab_mask)] & IMASK;
+            while (q != HNIL) {
+              const int sq = st_seg[q];
+              if (sq > s) {
+                const long long dd = (long long)st_pos[q] + 512ll - seg_off(sq) - dg;
+                if (dd > -(long long)mo && dd < (long long)mo) segs |= 1u << sq;
+              }
+              const NextT nx = st_next[q];
+              q = nx == NIL ? HNIL : (uint32_t)nx;
+            }
+          }
+          const uint32_t key = ((uint32_t)(1 + __popc(segs)) << 16) | (uint32_t)(0xFFFF - e);
+          bestkey = max(bestkey, key);
+        }
+        bestkey = __reduce_max_sync(FULLM, bestkey);
+        const int f0 = (int)(bestkey >> 16);
+        const int k = nseg - f0 + 2;
+        if (f0 <= min_match || k > nseg / 2) return false;
+        const int eb = 0xFFFF - (int)(bestkey & 0xFFFFu);
+        const long long d = (long long)st_pos[eb] - seg_off(st_seg[eb]);
+        // segments rotation 0 covers (an entry within max_off - 1 of d)
+        uint32_t cov = 0;
+        for (int e = lane; e < n0; e += 32) {
+          const long long dd = (long long)st_pos[e] - seg_off(st_seg[e]) - d;
+          if (dd > -(long long)mo && dd < (long long)mo) cov |= 1u << st_seg[e];
+        }
+        cov = __reduce_or_sync(FULLM, cov);
+        const uint32_t all = (nseg >= 32) ? 0xFFFFFFFFu : ((1u << nseg) - 1u);
+        const uint32_t fm = (((1u << k) - 1u) | ~cov) & all;   // segments to read in full
+        {  // unread buckets: rotations 1-3 of the other segments
+          bool flagged = false;
+          for (int i = lane; i < 4 * nseg; i += 32) {
+            const int s = i >> 2, g = i & 3;
+            if (g != 0 && !((fm >> s) & 1u) && (sm.b_n4[4 * (strand * nseg + s) + g] & 0x8000u)) flagged = true;
+          }
+          if (__any_sync(FULLM, flagged)) return false;
+        }
+        for (uint32_t m = fm; m; m &= m - 1u)
+          if (rot != 0) prefetch_bucket(__ffs((int)m) - 1, rot);
+        for (uint32_t m = fm; m; m &= m - 1u) gather_round(__ffs((int)m) - 1, rot, rot != 0);
+        __syncwarp();
+        int n1 = (int)sm.g.n_ent;
+        if (__any_sync(FULLM, over) || n1 > cap) return false;
+        n1 = screen(n0, n1);
+        if (n1 < 0) return false;
+        // cap rule: every anchor examined before the chain's first one is an entry of the first k segments
+        int n_first = 0;
+        for (int e = lane; e < n1; e += 32) n_first += (int)st_seg[e] < k;
+        n_first = __reduce_add_sync(FULLM, n_first);
+        if (tot + n_first >= a.p.max_hits) return false;
+        build_hash(n1);
+        // inside the first k segments only entries on d may pair up across segments
+        bool stray = false;
+        uint32_t on_d = 0, cov2 = 0;
+        for (int e = lane; e < n1; e += 32) {
+          const int s = st_seg[e];
+          const long long de = (long long)st_pos[e] - seg_off(s);
+          const long long dd = de - d;
+          if (dd == 0) on_d |= 1u << s;
+          if (dd > -(long long)mo && dd < (long long)mo) cov2 |= 1u << s;
+          if (s < k && dd != 0) {
+            const uint32_t bin = (uint32_t)((de + 512ll) >> 4);
+#pragma unroll
+            for (int db = -2; db <= 2; db++) {
+              uint32_t q = st_head[rbi_hash(bin + (uint32_t)db, tab_mask)] & IMASK;
+              while (q != HNIL) {
+                const int sq = st_seg[q];
+                if (sq != s && sq < k) {
+                  const long long x = (long long)st_pos[q] - seg_off(sq) - de;
+                  if (x > -2ll * mo + 1 && x < 2ll * mo - 1) stray = true;
+                }
+                const NextT nx = st_next[q];
+                q = nx == NIL ? HNIL : (uint32_t)nx;
+              }
+            }
+          }
+        }
+        if (__any_sync(FULLM, stray)) return false;
+        on_d = __reduce_or_sync(FULLM, on_d);
+        cov2 = __reduce_or_sync(FULLM, cov2);
+        const int s_first = __ffs((int)on_d) - 1;
+        const int f_max = 1 + __popc(cov2 & ~((2u << s_first) - 1u));
+        if (s_first < 0 || f_max < f0) return false;  // (cannot happen)
+        min_match = f_max;
+        tot = 1;
+        if (lane == 0) {
+          sm.hit_pos[0] = (uint32_t)(d + seg_off(s_first));
+          sm.hit_off[0] = (uint16_t)seg_off(s_first);
+          sm.hit_or[0] = (uint8_t)strand;
+        }
+        __syncwarp();
+        l_pos += (unsigned long long)n1;
+        return true;
+      };
+      if (!BIG && a.shortcut && nseg - min_match + 2 > nseg / 2 && nseg >= 6 && nseg <= 31) {
+        if (try_single_chain()) continue;
+        __syncwarp();
+      }
+
       // ---- gather (get_mers 2158-2165, loop 1594-1612 / 1619-1637): per segment, every entry of its four buckets whose
       // tag is the segment's tag or one 2-bit field away from it
       // With the running min_match at F the first nseg - F + 2 segments decide whether the strand can matter at all (see
@@ -462,7 +689,7 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
         if (sp >= nseg) return;
         const int bp = 4 * (strand * nseg + sp) + rot;
         const char* p0 = reinterpret_cast<const char*>(rdata + 5ull * sm.b_off[bp]);
-        const uint32_t bytes = 20u * sm.b_n4[bp];  // 80 bytes per block = 20 per quad
+        const uint32_t bytes = 20u * (sm.b_n4[bp] & 0x7FFFu);  // 80 bytes per block = 20 per quad
 #if PM_RBI_PREFETCH_MODE == 1   /* one bulk prefetch per bucket (TMA unit): the whole byte range at once */
         if (l8 == 0 && bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"(bytes) : "memory");
 #else                           /* one line-sized piece per lane and instruction */
@@ -480,7 +707,7 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
         if (k_probe == 0 || s + PM_RBI_PREFETCH < k_probe || s >= k_probe) prefetch_segment(s + PM_RBI_PREFETCH);
 #endif
         const int b = 4 * (strand * nseg + s) + rot;
-        const uint32_t n4 = sm.b_n4[b];
+        const uint32_t n4 = sm.b_n4[b] & 0x7FFFu;
         const uint4* base = rdata + 5ull * sm.b_off[b];  // 80-byte blocks
         const uint32_t etagx = ((sm.kcode[strand * nseg + s] >> (8 * rot)) & 255u) * 0x01010101u;
         const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, n4);
@@ -739,7 +966,7 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
 // CAP > 0: stores in shared memory; CAP = 0: in the per-warp global scratch.  Work items are all read-mates of the
 // chunk (work_list == nullptr) or the ones an earlier pass could not hold; the ones this pass cannot hold go to next_list.
 template <int WARPS, int CAP>
-__global__ void __launch_bounds__(WARPS * 32) k_seed_rbi(SeedRbiArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, (CAP == PM_RBI_CAP ? 3 : 1)) k_seed_rbi(SeedRbiArgs a) {
   extern __shared__ __align__(16) unsigned char rbi_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   RbiWarpSmem& sm = reinterpret_cast<RbiWarpSmem*>(rbi_smem)[warp];

@@ -498,8 +498,32 @@ struct SelectIntArgs {
   Winner* replay_tasks;       // every task of those reads
   uint32_t* replay_task_cursor;
   SeedCounters* counters;
+  const char* reads[2];       // for diag_score64
+  int stride;
+  const char* genome;
+  const double* border;
   DevParams p;
 };
+
+// The reference's double for a task whose integer result has a unique last-column maximum in state 0 (flags & 1 clear),
+// only ACGTN bases (flags & 2 clear) and, behind that cell, a state-0 diagonal on which S0 beats S1 and S2 by at least
+// 1/36 at every cell (flags & 4).  Rounding errors are ~1e-13, so the double DP takes the same maxima:
+// S0[i][j] = S0[i-1][j-1] + bump all the way (1713 / 1723), started from M[i0][0] = 0 (2062-2081) or, when the diagonal
+// leaves through row 0, from the border S[0][j0] (2073-2081), and the last-column scan (1717-1742) returns that cell.
+// The sum below is therefore the bit pattern k_sw_fp64 would produce, at mm additions instead of mm * nn cells.
+__device__ __forceinline__ double diag_score64(const Task& tk, int maxi, int mm, const char* read, const char* genome,
+                                               const double* border, const DevParams& p) {
+  const int orient = (int)(tk.rm >> 31);
+  const int j0 = maxi >= mm ? 0 : mm - maxi;   // the diagonal's cell before its first step: (i0, j0)
+  const int i0 = maxi - (mm - j0);
+  double s = j0 == 0 ? 0.0 : border[j0];
+  for (int j = j0 + 1; j <= mm; j++) {
+    const char rc = genome[(size_t)tk.wstart + (size_t)(i0 + (j - j0) - 1)];
+    const char q = seq_char(read, mm, orient, j - 1);
+    s = s + (bases_match(rc, q, p.is_bisulfite) ? p.match : p.mism);
+  }
+  return s;
+}
 
 // s >= good_score ?  returns 1 / 0, or -1 when the rational score is (numerically) on the threshold
 __device__ __forceinline__ int ge_good(int s36, double good36) {
@@ -628,6 +652,18 @@ __global__ void __launch_bounds__(128) k_select_int(SelectIntArgs a) {
   else if (n1 > 0 && n2 > 0)
     call = pair_rule_int(a.tasks + b1, a.ires + b1, n1, l1, a.tasks + b2, a.ires + b2, n2, l3, a.p, &keep1, &keep2, &amb);
   else call = T_NEITHER_MAP;
+  // a task of a replayed read whose double follows from its diagonal alone (diag_score64) is settled here
+  auto settle = [&](const uint32_t id, const uint32_t rmv) {
+    const ITaskResult ir = a.ires[id];
+    if ((ir.flags & 7) != 4) return false;
+    const int mm = a.len[rmv & 1][rmv >> 1];
+    TaskResult t64;
+    t64.score = diag_score64(a.tasks[id], (int)ir.maxi, mm, a.reads[rmv & 1] + (size_t)(rmv >> 1) * a.stride, a.genome, a.border, a.p);
+    t64.maxi = ir.maxi;
+    t64.maxk = ir.maxk;
+    a.results64[id] = t64;
+    return true;
+  };
   if (amb && narrow != -0x7FFFFFFF) {
     // single-end rule with a rational tie at the top: the exact selection (k_select) needs the reference's doubles of
     // the tied candidates only; every other candidate gets its rational score, which orders it exactly as its double
@@ -636,15 +672,20 @@ __global__ void __launch_bounds__(128) k_select_int(SelectIntArgs a) {
     a.replay_reads[slot] = (uint32_t)r;
     const int n = n1 > 0 ? n1 : n2;
     const uint32_t b = n1 > 0 ? b1 : b2, rmv = n1 > 0 ? 2u * r : 2u * r + 1u;
-    int tied = 0;
-    for (int q = 0; q < n; q++) tied += a.ires[b + q].score36 == narrow;
-    uint32_t at = atomicAdd(a.replay_task_cursor, (uint32_t)tied);
+    int queued = 0;
+    for (int q = 0; q < n; q++) {
+      const ITaskResult ir = a.ires[b + q];
+      queued += ir.score36 == narrow && (ir.flags & 7) != 4;
+    }
+    uint32_t at = queued ? atomicAdd(a.replay_task_cursor, (uint32_t)queued) : 0u;
     for (int q = 0; q < n; q++) {
       const ITaskResult ir = a.ires[b + q];
       if (ir.score36 == narrow) {
-        a.replay_tasks[at].task = b + q;
-        a.replay_tasks[at].rm = rmv;
-        at++;
+        if (!settle(b + q, rmv)) {
+          a.replay_tasks[at].task = b + q;
+          a.replay_tasks[at].rm = rmv;
+          at++;
+        }
       } else {
         TaskResult t64;
         t64.score = (double)ir.score36 / 36.0;
@@ -659,10 +700,14 @@ __global__ void __launch_bounds__(128) k_select_int(SelectIntArgs a) {
   if (amb) {  // hand the whole read (pair) to the exact path
     const uint32_t slot = atomicAdd(a.replay_read_cursor, 1u);
     a.replay_reads[slot] = (uint32_t)r;
-    const uint32_t tot = (uint32_t)(n1 + n2);
-    const uint32_t at = atomicAdd(a.replay_task_cursor, tot);
-    for (int q = 0; q < n1; q++) { a.replay_tasks[at + q].task = b1 + q; a.replay_tasks[at + q].rm = 2u * r; }
-    for (int q = 0; q < n2; q++) { a.replay_tasks[at + n1 + q].task = b2 + q; a.replay_tasks[at + n1 + q].rm = 2u * r + 1u; }
+    int queued = 0;
+    for (int q = 0; q < n1; q++) queued += (a.ires[b1 + q].flags & 7) != 4;
+    for (int q = 0; q < n2; q++) queued += (a.ires[b2 + q].flags & 7) != 4;
+    uint32_t at = queued ? atomicAdd(a.replay_task_cursor, (uint32_t)queued) : 0u;
+    for (int q = 0; q < n1; q++)
+      if (!settle(b1 + q, 2u * r)) { a.replay_tasks[at].task = b1 + q; a.replay_tasks[at].rm = 2u * r; at++; }
+    for (int q = 0; q < n2; q++)
+      if (!settle(b2 + q, 2u * r + 1u)) { a.replay_tasks[at].task = b2 + q; a.replay_tasks[at].rm = 2u * r + 1u; at++; }
     atomicAdd(&a.counters->replayed, (unsigned long long)((n1 > 0) + (n2 > 0)));
     return;
   }

@@ -253,8 +253,9 @@ def test_diagonal_certificate_changes_nothing(name, get_fixture, monkeypatch):
 def test_seed_index_layouts_agree(name, get_fixture, monkeypatch):
     """The seed stage reads a device-private rotated bucket index (seed_rbi.cuh); PEMAP_SEED=legacy runs the round-1
     kernel over pos_index / mers as the reference lays them out, and PEMAP_RBI_CAP=8 pushes nearly every read-mate
-    through the second (global-memory) pass of the new kernel.  Candidate lists in order, loci, types, pileup records
-    and insertions must be identical in all three."""
+    through the second (global-memory) pass of the new kernel; PEMAP_SHORTCUT=0 switches the single-chain shortcut off
+    (every strand then reads all four rotations of all its segments).  Candidate lists in order, loci, types, pileup
+    records and insertions must be identical in all four."""
     fx = get_fixture(name)
     bis = int(getattr(fx, "bisulfite", False))
     for run in fx.runs:
@@ -262,9 +263,10 @@ def test_seed_index_layouts_agree(name, get_fixture, monkeypatch):
                   is_bisulfite=int(run.bisulfite))
         n = min(20000, run.reads1.shape[0])
         out = {}
-        for mode in ("legacy", "rbi", "rbi-big"):
+        for mode in ("legacy", "rbi", "rbi-big", "rbi-full"):
             monkeypatch.setenv("PEMAP_SEED", "legacy" if mode == "legacy" else "rbi")
             monkeypatch.setenv("PEMAP_RBI_CAP", "8" if mode == "rbi-big" else "512")
+            monkeypatch.setenv("PEMAP_SHORTCUT", "0" if mode == "rbi-full" else "1")
             mapper = pb.PEMapper.from_genome(fx.genome, pb.default_params(is_bisulfite=bis))
             mapper.set_params(**kw)
             mapper.keep(pb.KEEP_CANDIDATES)
@@ -274,7 +276,7 @@ def test_seed_index_layouts_agree(name, get_fixture, monkeypatch):
             st = mapper.stats()
             out[mode] = (g, cands, rec.tobytes(), sorted(ins), st["candidates"], st["mer_positions"])
             mapper.close()
-        for mode in ("rbi", "rbi-big"):
+        for mode in ("rbi", "rbi-big", "rbi-full"):
             tag = "%s/%s %s vs legacy" % (name, run.name, mode)
             for x, y in zip(out["legacy"][0], out[mode][0]):
                 assert np.array_equal(x, y), tag + ": per-read results"
@@ -481,6 +483,36 @@ def test_peer_reduce_single_process(get_fixture):
     rec, _ = a.finish()
     assert rec.tobytes() == rec1.tobytes()
     for m in (a, b, one):
+        m.close()
+
+
+@pytest.mark.parametrize("ways", [3, 4, 8])
+def test_slice_sum_many_handles_one_gpu(ways, get_fixture, monkeypatch):
+    """The N-way slice sum (k_reduce_slice: the unrolled 3- and 7-peer forms and the generic loop) without needing N
+    GPUs: N handles on ONE device map N disjoint parts of the batch, every handle pulls its 1/N slice from the others
+    and compacts it; slices in rank order == everything mapped through one handle."""
+    monkeypatch.setenv("PEMAP_CHUNK", "4096")   # small per-handle scratch: up to nine handles share the device ...
+    monkeypatch.setenv("PEMAP_KEEP_INDEX", "0")  # ... and none keeps the 16 GiB file-format pos_index beside its bucket index
+    fx = get_fixture("pe150")
+    run = fx.runs[0]
+    n = 16000
+    kw = dict(min_align=run.min_align, pair_flag=1, min_dist=run.min_dist, max_dist=run.max_dist)
+    hs = [pb.PEMapper.from_genome(fx.genome, device=0) for _ in range(ways)]
+    one = pb.PEMapper.from_genome(fx.genome, device=0)
+    for m in hs + [one]:
+        m.set_params(**kw)
+    cuts = np.linspace(0, n, ways + 1).astype(int)
+    for r, m in enumerate(hs):
+        m.map_batch(run.reads1[cuts[r]:cuts[r + 1]], run.reads2[cuts[r]:cuts[r + 1]])
+    one.map_batch(run.reads1[:n], run.reads2[:n])
+    bounds = [pb.PEMapper.reduce_scatter_local(hs, r) for r in range(ways)]
+    assert bounds[0][0] == 0 and all(bounds[r][1] == bounds[r + 1][0] for r in range(ways - 1))
+    sl = []
+    for r, m in enumerate(hs):
+        m.finish_stream(lambda x: sl.append(x.copy()), site_range=bounds[r])
+    rec1, _ = one.finish()
+    assert np.concatenate(sl).tobytes() == rec1.tobytes()
+    for m in hs + [one]:
         m.close()
 
 
