@@ -7,6 +7,13 @@
 // VIMNMX3.S16x2 and VIMNMX.U16x2; values are stored biased by +1024 so that every half stays positive and the
 // constant subtractions can be plain 32-bit adds without borrows between halves.
 //
+// k_sw_i16 keeps every state in the frame T[i][j] = S[i][j] + i + j: the gap-extension steps S - 1 one column or one
+// row further then cost nothing (T2[i][j] = max(T0[i][j-1] - 71, T2[i][j-1]) is ONE VIADDMNMX with no separate
+// subtraction, likewise T1), the diagonal step becomes T0 = TM[i-1][j-1] + 2 + bump = (TM - 10) + 48 * match, and all
+// comparisons inside a cell are unchanged.  The three-input DPX instructions issue at half rate on sm_100a
+// (profiles/README_r02.md), so per pair of cells the loop is 2 x 2 (VIADDMNMX) + 8 single-rate slots instead of + 10.
+// Only the last-column scan compares cells of different rows: it subtracts the row index again.
+//
 // The reference compares IEEE doubles with strict '>' (1101, 1147, 1455, 1463, 1724-1741, 1805-1811), and
 // rationally equal scores need not be equal doubles.  Every comparison whose outcome
 // could depend on that is detected here (equal integers) and the read is replayed by the fp64 kernels; all
@@ -90,7 +97,7 @@ __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
   const uint32_t n_items = *a.n_items, n_pairs = (n_items + 1) >> 1;
   uint32_t* win = s_win[grp];
   uint32_t* last = s_last[PARK ? grp : 0];
-  constexpr uint32_t K1 = 0x00010001u, K12 = 0x000C000Cu, NEG72 = 0xFFB8FFB8u;
+  constexpr uint32_t K1 = 0x00010001u, K10 = 0x000A000Au, NEG71 = 0xFFB9FFB9u;
   constexpr uint32_t BIASP = (PM_IBIAS << 16) | PM_IBIAS;
 
   for (;;) {
@@ -129,11 +136,11 @@ __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
       if (j0 < mmA) { cA = read_code(seq_char(readA, mmA, orA, j0)); badA |= (cA == 0); }
       if (j0 < mmB) { cB = read_code(seq_char(readB, mmB, orB, j0)); badB |= (cB == 0); }
       q[c] = cA | (cB << 16);
-      // row 0: S*[0][j] = -(72 + j - 1) (2073-2081); mu holds max(S0,S1,S2) - 12
-      const uint32_t b = (uint32_t)(PM_IBIAS - 72 - (j0 + 1 - 1));
+      // row 0: S*[0][j] = -(72 + j - 1) (2073-2081), i.e. T = -71 in every column; mu holds max(T0,T1,T2) - 10
+      const uint32_t b = (uint32_t)(PM_IBIAS - 71);
       s0u[c] = b | (b << 16);
       s1u[c] = s0u[c];
-      mu[c] = s0u[c] - K12;
+      mu[c] = s0u[c] - K10;
       dvu[c] = 0xFFFFFFFFu;  // row 0 is never consulted by the walk (loop ends at i == 0)
     }
     badA = __any_sync(gmask, badA);
@@ -150,8 +157,9 @@ __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
       colA = ownA ? (mmA - 1) % WD : -1;
       colB = ownB ? (mmB - 1) % WD : -1;
     }
-    int bestA = PM_IBIAS - 72 - (mmA - 1), bkA = 0, biA = 0, tieA = 0, dqA = 0;  // S[0][0][mm] (1701-1703)
-    int bestB = PM_IBIAS - 72 - (mmB - 1), bkB = 0, biB = 0, tieB = 0, dqB = 0;
+    // the running maximum of the last column is kept as S + mm (+ bias): T minus the row index; S[0][0][mm] (1701-1703)
+    int bestA = PM_IBIAS - 71, bkA = 0, biA = 0, tieA = 0, dqA = 0;
+    int bestB = PM_IBIAS - 71, bkB = 0, biB = 0, tieB = 0, dqB = 0;
     uint32_t out_s0 = 0, out_s2 = 0, out_m = 0, out_dv = 0xFFFFFFFFu;
     __syncwarp(gmask);
 
@@ -161,21 +169,22 @@ __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
       uint32_t l_s2 = __shfl_up_sync(gmask, out_s2, 1, G);
       uint32_t diag = __shfl_up_sync(gmask, out_m, 1, G);
       uint32_t dvd = __shfl_up_sync(gmask, out_dv, 1, G);
-      if (gl == 0) {  // column 0: S0 = 0, S2 = -72, M(row above) - 12 = -12 (2062-2081)
-        l_s0 = BIASP;
-        l_s2 = BIASP - 0x00480048u;
-        diag = BIASP - K12;
+      const int i = s - gl + 1;
+      if (gl == 0) {  // column 0 of row i: S0 = 0, S2 = -72, M(row above) = 0 (2062-2081) -> T0 = i, T2 = i - 72, TM - 10 = i - 11
+        const uint32_t ik = BIASP + (uint32_t)i * K1;
+        l_s0 = ik;
+        l_s2 = ik - 0x00480048u;
+        diag = ik - 0x000B000Bu;
         dvd = 0xFFFFFFFFu;  // the walk stops at j == 0
       }
-      const int i = s - gl + 1;
       if (i >= 1 && i <= nn) {
         const uint32_t rc = win[i - 1];
 #pragma unroll
         for (int c = 0; c < WD; c++) {
-          const uint32_t s2 = __viaddmax_s16x2(l_s0, NEG72, l_s2 - K1);      // 1710 / 1720
-          const uint32_t s1 = __viaddmax_s16x2(s0u[c], NEG72, s1u[c] - K1);  // 1711 / 1721
+          const uint32_t s2 = __viaddmax_s16x2(l_s0, NEG71, l_s2);           // 1710 / 1720
+          const uint32_t s1 = __viaddmax_s16x2(s0u[c], NEG71, s1u[c]);       // 1711 / 1721
           const uint32_t m01 = __vminu2(q[c] & rc, K1);                      // 1 where the bases match
-          const uint32_t s0 = m01 * 48u + diag;                              // (M - 12) + 48 or + 0 (1713 / 1723)
+          const uint32_t s0 = m01 * 48u + diag;                              // (TM - 10) + 48 or + 0 (1713 / 1723)
           diag = mu[c];
           const uint32_t m12 = __vmaxs2(s1, s2);
           const uint32_t m = __vmaxs2(s0, m12);
@@ -186,17 +195,19 @@ __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
           } else if (CMM >= 0) {
             if (c == CMM && ownA) {
               if (i <= nnA)
-                track_best((int)(s0 & 0xFFFFu), (int)(s1 & 0xFFFFu), (int)(s2 & 0xFFFFu), (int)(dvd & 0xFFFFu), i, bestA, bkA,
-                           biA, tieA, dqA);
+                track_best((int)(s0 & 0xFFFFu) - i, (int)(s1 & 0xFFFFu) - i, (int)(s2 & 0xFFFFu) - i, (int)(dvd & 0xFFFFu), i,
+                           bestA, bkA, biA, tieA, dqA);
               if (i <= nnB)
-                track_best((int)(s0 >> 16), (int)(s1 >> 16), (int)(s2 >> 16), (int)(dvd >> 16), i, bestB, bkB, biB, tieB, dqB);
+                track_best((int)(s0 >> 16) - i, (int)(s1 >> 16) - i, (int)(s2 >> 16) - i, (int)(dvd >> 16), i, bestB, bkB, biB,
+                           tieB, dqB);
             }
           } else {
             if (c == colA && ownA && i <= nnA)
-              track_best((int)(s0 & 0xFFFFu), (int)(s1 & 0xFFFFu), (int)(s2 & 0xFFFFu), (int)(dvd & 0xFFFFu), i, bestA, bkA,
-                         biA, tieA, dqA);
+              track_best((int)(s0 & 0xFFFFu) - i, (int)(s1 & 0xFFFFu) - i, (int)(s2 & 0xFFFFu) - i, (int)(dvd & 0xFFFFu), i,
+                         bestA, bkA, biA, tieA, dqA);
             if (c == colB && ownB && i <= nnB)
-              track_best((int)(s0 >> 16), (int)(s1 >> 16), (int)(s2 >> 16), (int)(dvd >> 16), i, bestB, bkB, biB, tieB, dqB);
+              track_best((int)(s0 >> 16) - i, (int)(s1 >> 16) - i, (int)(s2 >> 16) - i, (int)(dvd >> 16), i, bestB, bkB, biB,
+                         tieB, dqB);
           }
           // both halves of m - m12 are >= 0, so the plain subtraction does not borrow across halves
           const uint32_t e = __vminu2(dvd, m - m12);
@@ -204,7 +215,7 @@ __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
           dvu[c] = e;
           s0u[c] = s0;
           s1u[c] = s1;
-          mu[c] = m - K12;
+          mu[c] = m - K10;
           l_s0 = s0;
           l_s2 = s2;
         }
@@ -228,14 +239,14 @@ __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
       }
       for (int r = gl; r < nn; r += G) {
         const uint32_t w0 = last[4 * r], w1 = last[4 * r + 1], w2 = last[4 * r + 2];
-        const uint32_t o = 3u * (uint32_t)(r + 1);
+        const uint32_t o = 3u * (uint32_t)(r + 1), ri = (uint32_t)(r + 1);  // parked values are T: take the row index off
         if (r < nnA) {
-          const uint32_t v0 = (w0 & 0xFFFFu) << 10, v1 = (w1 & 0xFFFFu) << 10, v2 = (w2 & 0xFFFFu) << 10;
+          const uint32_t v0 = ((w0 & 0xFFFFu) - ri) << 10, v1 = ((w1 & 0xFFFFu) - ri) << 10, v2 = ((w2 & 0xFFFFu) - ri) << 10;
           fA = max(fA, max(v0 | (1023u - o), max(v1 | (1022u - o), v2 | (1021u - o))));
           lA = max(lA, max(v0 | o, max(v1 | (o + 1u), v2 | (o + 2u))));
         }
         if (r < nnB) {
-          const uint32_t v0 = (w0 >> 16) << 10, v1 = (w1 >> 16) << 10, v2 = (w2 >> 16) << 10;
+          const uint32_t v0 = ((w0 >> 16) - ri) << 10, v1 = ((w1 >> 16) - ri) << 10, v2 = ((w2 >> 16) - ri) << 10;
           fB = max(fB, max(v0 | (1023u - o), max(v1 | (1022u - o), v2 | (1021u - o))));
           lB = max(lB, max(v0 | o, max(v1 | (o + 1u), v2 | (o + 2u))));
         }
@@ -255,7 +266,7 @@ __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
     }
     if (ownA) {
       ITaskResult r;
-      r.score36 = bestA - PM_IBIAS;
+      r.score36 = bestA - PM_IBIAS - mmA;
       r.maxi = (uint16_t)biA;
       r.maxk = (uint8_t)bkA;
       r.flags = (uint8_t)((tieA ? 1 : 0) | (badA ? 2 : 0) | ((bkA == 0 && biA > 0 && dqA >= 1) ? 4 : 0));
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(128, 6) k_sw_i16(SwIntArgs a) {
     }
     if (ownB && idB != idA) {
       ITaskResult r;
-      r.score36 = bestB - PM_IBIAS;
+      r.score36 = bestB - PM_IBIAS - mmB;
       r.maxi = (uint16_t)biB;
       r.maxk = (uint8_t)bkB;
       r.flags = (uint8_t)((tieB ? 1 : 0) | (badB ? 2 : 0) | ((bkB == 0 && biB > 0 && dqB >= 1) ? 4 : 0));

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""CPU model of the seed stage's "single-chain certificate" (seed_rbi.cuh, rbi_try_single_chain).
+"""CPU model of the seed stage's single-chain shortcut (seed_rbi.cuh, phases M_A / M_B of rbi_map_read_mate).
 
 Test infrastructure: the model restates find_matches (pemapper.c:2189-2288) and initial_map's two calls of it
 (1655-1659) over the full 49-k-mer segment lists (1594-1637), then runs the shortcut, which sees only
