@@ -508,7 +508,8 @@ def main():
         sw_gcups = per_step["sw_cells_dp"] / sw_s / 1e9
         ap_ = alu_peak() or {}
         pk16, pk32, pk64 = ap_.get("sw_s16x2_gcups_peak"), ap_.get("sw_s32_gcups_peak"), ap_.get("sw_fp64_gcups_peak")
-        src = "profiles/alu_peak.json (issue rates measured with tools/alu_peak.cu on a B200, SURVEY 8d: 10 ops per cell)"
+        src = ("profiles/alu_peak.json (issue rates measured with tools/alu_peak.cu on a B200; ceiling = the inner loop's issue "
+               "budget: per pair of packed cells 2 half-rate DPX + 8 single-rate ops)")
 
         def alu_roof(kernel, cells, secs, peak):
             g = cells / secs / 1e9

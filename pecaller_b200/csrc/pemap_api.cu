@@ -603,7 +603,6 @@ int build_rbi(pemap_ctx* h, uint32_t* code, const uint32_t* val, uint64_t n) {
     CKB(cudaMalloc(&h->d_rbi_data[g], bytes));
     CKB(cudaMemsetAsync(h->d_rbi_data[g], 0xFF, bytes, h->stream));
     if (ne) pm::k_rbi_fill<<<eblk, 256, 0, h->stream>>>(kk, vv, ne, bstart, h->d_rbi_dir[g], h->d_rbi_data[g]);
-    if (ne) pm::k_rbi_flag_buckets<<<eblk, 256, 0, h->stream>>>(kk, vv, ne, h->d_rbi_dir[g]);
     h->rbi_bytes += bytes + (size_t)nb24 * 4;
   }
   CKB(cudaStreamSynchronize(h->stream));
@@ -884,8 +883,6 @@ int run_chunk(pemap_ctx* h, int n, const char* d_r1, const int* d_l1, const char
     ra.big_scratch = h->d_big_scratch;
     ra.fast_cap = PM_RBI_CAP;
     if (const char* s = getenv("PEMAP_RBI_CAP")) ra.fast_cap = std::min(PM_RBI_CAP, std::max(1, atoi(s)));
-    ra.shortcut = 1;
-    if (const char* s = getenv("PEMAP_SHORTCUT")) ra.shortcut = atoi(s) != 0;
     ra.p = sa.p;
     const int work = paired ? 2 * n : n;
     static int rbi_wave[kMaxDev] = {}, rbi_wave2[kMaxDev] = {};

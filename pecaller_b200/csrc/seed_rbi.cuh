@@ -31,6 +31,18 @@
 #define PM_RBI_EMPTY 0xFFFFFFFFu
 #define PM_RBI_MARK 0xFFFFFFFEu
 #define PM_RBI_CAP 512                  // entries of one strand kept in shared memory (a 150-bp read on 3.1 Gb has ~360)
+#ifndef PM_RBI_PREFETCH
+#define PM_RBI_PREFETCH 1               // segments whose buckets are prefetched into L2 ahead of the one being read
+#endif
+#ifndef PM_RBI_PREFETCH_MODE
+#define PM_RBI_PREFETCH_MODE 0
+#endif
+#ifndef PM_RBI_PREFETCH_STRIDE
+#define PM_RBI_PREFETCH_STRIDE 128
+#endif
+#ifndef PM_RBI_EXPERIMENT
+#define PM_RBI_EXPERIMENT 0
+#endif
 #define PM_RBI_CAP2 2048                // second pass: strands of reads that sit in repeats
 #define PM_RBI_MAXB (4 * PM_MAX_SEG)    // buckets per strand
 #define PM_RBI_BIG_CAP 98304            // >= 19 segments * 49 * 99 positions: the slow path holds any strand
@@ -54,7 +66,7 @@ __host__ __device__ __forceinline__ uint32_t rbi_units(uint32_t n) {  // blocks 
 
 struct RbiIndex {
   const uint4* data[4];     // bucket arrays of the four rotations
-  const uint32_t* dir[4];   // 2^24+1 offsets each, in 80-byte blocks; bit 31 = PM_RBI_DIR_FLAG of the bucket
+  const uint32_t* dir[4];   // 2^24+1 offsets each, in 80-byte blocks
 };
 
 // ------------------------------------------------------------------------------------------------ builder kernels
@@ -130,15 +142,6 @@ __global__ void __launch_bounds__(256) k_rbi_fill(const uint32_t* key, const uin
   blk[64 + (r & 15u)] = (unsigned char)(k & 255u);
 }
 
-// Bit 31 of a directory word: the bucket holds at least one crowded-k-mer marker.  The single-chain shortcut of the seed
-// kernel leaves most buckets of a strand unread; a marker in one of them would empty its segment's list (1602-1606), so
-// it only skips buckets whose flag is clear.  Set after k_rbi_fill (which reads the plain offsets).
-#define PM_RBI_DIR_FLAG 0x80000000u
-__global__ void __launch_bounds__(256) k_rbi_flag_buckets(const uint32_t* key, const uint32_t* val, uint64_t n, uint32_t* dir) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && val[i] == PM_RBI_MARK) atomicOr(&dir[key[i] >> 8], PM_RBI_DIR_FLAG);
-}
-
 // ------------------------------------------------------------------------------------------------ packed reads
 // Row of a packed read (pemap.h: pemap_pack_read): code words (base i at bits 31-2(i%16), 30-2(i%16) of word i/16; A 0,
 // C 1, G 2, T 3 as convert_seq_int codes them, N stored as 0), then N-mask words (bit i%32 of word i/32).
@@ -196,7 +199,6 @@ struct SeedRbiArgs {
   const uint32_t* work_n;
   unsigned char* big_scratch;  // BIG: per warp PM_RBI_BIG_BYTES
   int fast_cap;                // entries of a strand the first pass accepts (<= PM_RBI_CAP; PEMAP_RBI_CAP lowers it in tests)
-  int shortcut;                // single-chain shortcut on (PEMAP_SHORTCUT=0 switches it off: the on/off parity test)
   DevParams p;
 };
 
@@ -204,7 +206,7 @@ struct SeedRbiArgs {
 
 struct RbiWarpSmem {           // per warp, every path
   uint32_t b_off[2 * PM_RBI_MAXB];   // bucket start (16-byte units), both strands: [4 * (strand * nseg + segment) + rotation]
-  uint16_t b_n4[2 * PM_RBI_MAXB];    // its position quads (<= 256 * 99 / 4) in bits 0-14, the bucket's PM_RBI_DIR_FLAG in bit 15
+  uint16_t b_n4[2 * PM_RBI_MAXB];    // its position quads (<= 256 * 99 / 4)
   uint32_t kcode[2 * PM_MAX_SEG];
   uint32_t hit_pos[PM_MAX_HITS];
   uint16_t hit_off[PM_MAX_HITS];
@@ -371,211 +373,29 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
       const int g = b & 3;
       const uint32_t code = sm.kcode[b >> 2];
       const uint32_t bk = rbi_bucket(code, g);
-      const uint32_t w0 = __ldg(a.ix.dir[g] + bk), d0 = w0 & ~PM_RBI_DIR_FLAG, d1 = __ldg(a.ix.dir[g] + bk + 1) & ~PM_RBI_DIR_FLAG;
+      const uint32_t d0 = __ldg(a.ix.dir[g] + bk), d1 = __ldg(a.ix.dir[g] + bk + 1);
       sm.b_off[b] = d0;
-      sm.b_n4[b] = (uint16_t)((4u * (d1 - d0)) | ((w0 >> 31) << 15));  // quads of positions: four per block
+      sm.b_n4[b] = (uint16_t)(4u * (d1 - d0));  // quads of positions: four per block
     }
     __syncwarp();
-    // lanes 8g..8g+7 form lane group g; in one gather step every group reads one bucket
+    // lanes 8g..8g+7 read the bucket of rotation g
     const int rot = lane >> 3, l8 = lane & 7;
-    const unsigned FULLM = 0xFFFFFFFFu;
-    uint8_t* const blist = reinterpret_cast<uint8_t*>(sm.g.pend);   // buckets of the current phase (<= 76 bytes)
-    uint32_t* const hist = sm.g.pend + 32;                          // entries per segment (both dead before the found pass)
-
-    // Per strand the buckets are read in PHASES, each followed by an evaluation of what has been gathered so far:
-    //   M_FULL   every bucket, then the reference's rules (find_matches 2189-2288).
-    //   M_PROBE  the running min_match F is high enough that the first k = nseg - F + 2 segments settle whether the strand
-    //            can matter at all: an anchor with found = F has F of the nseg segments agreeing within max_off - 1 of
-    //            its diagonal, so ANY nseg - F + 2 segments hold two of its members; without two entries of different
-    //            segments within 2 (max_off - 1) of each other among those segments the strand is dead.  Else -> M_REST.
-    //   M_A/M_B  single-chain shortcut (model and proof obligations: tools/seed_shortcut_model.py).  A read that comes
-    //            from this strand of a unique locus has one chain of hits on ONE diagonal d, and most of its segments find
-    //            d through their exact k-mer, i.e. in rotation 0.  M_A reads rotation 0 of every segment; F0 is the best
-    //            found count over those entries alone, k = nseg - F0 + 2.  M_B reads the other three rotations of the
-    //            first k segments and of the segments rotation 0 left without an entry near d.  Every anchor that reaches
-    //            F0 has two chain members in the first k segments; if only entries exactly on d pair up there, all such
-    //            anchors lie on d, share one dedup key (2269), and the first of them has the largest count
-    //            F >= F0 > min_match: it resets the hit list (2251-2260).  The 200-cap return (2283) cannot fire before
-    //            it (the anchors examined earlier are entries of the first k segments: tot + their number < max_hits is
-    //            required), nor the min_spots rule (2200-2207; segment 0 is among them).  Unread buckets must not hold a
-    //            crowded-k-mer marker (PM_RBI_DIR_FLAG).  Any failed condition -> M_REST: nothing is read twice.
-    //   M_REST   whatever has not been read yet, then the rules.
-    enum { M_FULL = 0, M_REST = 1, M_PROBE = 2, M_A = 3, M_B = 4 };
+    const uint4* const rdata = a.ix.data[rot];
+    const uint32_t keep_exact = rot == 0 ? 0x80808080u : 0u;  // the exact k-mer sits in all four buckets: rotation 0 takes it
 
     for (int strand = 0; strand < 2; strand++) {
       if (strand == 1 && tot >= a.p.max_hits) break;  // 1658
+      // ---- hash of the entries by diagonal / 16.  Shared-memory paths: a slot word holds the chain head (low bits, all
+      // ones = none) and the set of segments hashed into the slot (bit 13 + segment); BIG: the head index alone.
       constexpr uint32_t HNIL = IMASK;
-      auto seg_off = [&](const int s) -> int { return (s < total_cuts) ? 16 * s : len - 16; };
-      const int sb = 4 * strand * nseg;  // this strand's buckets in sm.b_off / sm.b_n4
-      const int k_probe = nseg - min_match + 2 <= nseg / 2 ? nseg - min_match + 2 : 0;
-      int mode = k_probe ? M_PROBE : (!BIG && a.shortcut && nseg >= 6) ? M_A : M_FULL;
-      int cnt = 0;                 // warp-uniform copy of sm.g.n_ent between phases
-      bool overflow = false;
-      uint32_t wiped = 0;          // segments emptied by a crowded-k-mer marker (1602-1606)
-      long long sc_d = 0;          // shortcut: the chain's diagonal, F0, k and the segments read in full
-      int sc_f0 = 0, sc_k = 0;
-      uint32_t sc_fm = 0;
-      bool settled = false;        // the strand is done without the rules: dead, wiped by min_spots, or claimed
-      bool relevant = false;       // some anchor reaches the running min_match
-      if (lane == 0) sm.g.n_ent = 0;
-      __syncwarp();
-
-      for (;;) {
-        // ---- the buckets of this phase: those the mode wants and no earlier phase has read (bit 14 of b_n4)
-        int nbk = 0;
-        for (int i0 = 0; i0 < nb; i0 += 32) {
-          const int i = i0 + lane;
-          bool need = false;
-          if (i < nb) {
-            const int s = i >> 2, g = i & 3;
-            const bool want = mode == M_A ? g == 0 : mode == M_B ? (g != 0 && ((sc_fm >> s) & 1u)) : mode == M_PROBE ? s < k_probe : true;
-            const uint32_t w = sm.b_n4[sb + i];
-            need = want && !(w & 0x4000u);
-            if (need) sm.b_n4[sb + i] = (uint16_t)(w | 0x4000u);
-          }
-          const unsigned bal = __ballot_sync(FULLM, need);
-          if (need) blist[nbk + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)i;
-          nbk += __popc(bal);
-        }
-        __syncwarp();
-        // ---- gather (get_mers 2158-2165, loop 1594-1612 / 1619-1637): every entry of a bucket whose tag is the segment's
-        // tag (rotation 0 only: the exact k-mer sits in all four buckets) or one 2-bit field away from it.  Group g takes
-        // bucket 4 u + g of the list in step u; in M_FULL that is rotation g of segment u.
-        // Bytes in flight, not bandwidth, bound the bucket reads (24 warps x 32 lanes x a few 16-byte registers keep
-        // HBM's queues too short for it to schedule well: 3.2 TB/s; the same reads issued 250 KB deep per SM reach
-        // 5.5-6 TB/s, tools/chunk_probe.cu).  So the buckets of the next step are pulled into L2 by prefetches, one
-        // 128-byte line per lane and instruction, which cost neither registers nor shared memory.
-        const int cnt0 = cnt;
-        const int nu = (nbk + 3) >> 2;
-        for (int u = -1; u < nu; u++) {
-          {
-            const int j = 4 * (u + 1) + rot;
-            if (j < nbk) {
-              const int sl = blist[j], g = sl & 3;
-              const uint4* dp = g == 0 ? a.ix.data[0] : g == 1 ? a.ix.data[1] : g == 2 ? a.ix.data[2] : a.ix.data[3];
-              const char* p0 = reinterpret_cast<const char*>(dp + 5ull * sm.b_off[sb + sl]);
-              const uint32_t bytes = 20u * (sm.b_n4[sb + sl] & 0x1FFFu);  // 80 bytes per block = 20 per quad
-              const char* line = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)127) + 128 * l8;
-              for (; line < p0 + bytes; line += 8 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
-            }
-          }
-          if (u < 0) continue;
-          const int j = 4 * u + rot;
-          const bool active = j < nbk;
-          const int sl = active ? (int)blist[j] : 0;
-          const int sg = sl >> 2, rg = sl & 3;
-          const uint32_t n4 = active ? (sm.b_n4[sb + sl] & 0x1FFFu) : 0u;
-          const uint4* dp = rg == 0 ? a.ix.data[0] : rg == 1 ? a.ix.data[1] : rg == 2 ? a.ix.data[2] : a.ix.data[3];
-          const uint4* base = dp + 5ull * sm.b_off[sb + sl];  // 80-byte blocks
-          const uint32_t etagx = ((sm.kcode[strand * nseg + sg] >> (8 * rg)) & 255u) * 0x01010101u;
-          const uint32_t keep_exact = rg == 0 ? 0x80808080u : 0u;
-          const uint32_t nmax = __reduce_max_sync(FULLM, n4);
-          for (uint32_t q0 = 0; q0 < nmax; q0 += 8 * PM_RBI_UNROLL) {
-            uint4 P[PM_RBI_UNROLL];
-            uint32_t T[PM_RBI_UNROLL];
-#pragma unroll
-            for (int v = 0; v < PM_RBI_UNROLL; v++) {
-              const uint32_t q = q0 + (uint32_t)(8 * v + l8);
-              T[v] = etagx ^ 0x0F0F0F0Fu;  // two fields away: never qualifies (P[v] is then never looked at)
-              if (q < n4) {
-                const uint4* blk = base + 5u * (q >> 2);  // quad q: positions at 16 * (q & 3), its four tags at 64 + 4 * (q & 3)
-                P[v] = rbi_ld16(blk + (q & 3u));
-                T[v] = rbi_ld4(reinterpret_cast<const uint32_t*>(blk + 4) + (q & 3u));
-              }
-            }
-#pragma unroll
-            for (int v = 0; v < PM_RBI_UNROLL; v++) {
-              // per tag byte: fields that differ from the exact tag; a byte qualifies when at most one field differs
-              const uint32_t X = T[v] ^ etagx;
-              const uint32_t D = (X | (X >> 1)) & 0x55555555u;
-              const uint32_t Z = D & ((D | 0x80808080u) - 0x01010101u);             // byte == 0 <=> <= 1 field differs
-              uint32_t hit = ((Z + 0x7F7F7F7Fu) & 0x80808080u) ^ 0x80808080u;       // bit 7 of byte k: tag k qualifies
-              hit &= ((D + 0x7F7F7F7Fu) & 0x80808080u) | keep_exact;                 // ... and it is not the exact tag (rot > 0)
-              if (hit) {  // ~19 % of the quads: the lane reserves its slots in the strand's list and fills them, no loop
-                const uint32_t at = atomicAdd(&sm.g.n_ent, (uint32_t)__popc(hit));
-                if (at + 4u <= (uint32_t)cap) {
-                  uint32_t w = at;
-                  if (hit & 0x80u) { st_pos[w] = P[v].x; st_seg[w++] = (uint8_t)sg; }
-                  if (hit & 0x8000u) { st_pos[w] = P[v].y; st_seg[w++] = (uint8_t)sg; }
-                  if (hit & 0x800000u) { st_pos[w] = P[v].z; st_seg[w++] = (uint8_t)sg; }
-                  if (hit & 0x80000000u) { st_pos[w] = P[v].w; st_seg[w] = (uint8_t)sg; }
-                } else {
-                  overflow = true;
-                }
-              }
-            }
-          }
-        }
-        __syncwarp();
-        cnt = (int)sm.g.n_ent;
-        if (cnt > cap) cnt = cap;
-        if (__any_sync(FULLM, overflow)) {
-          if (!BIG) return false;  // the next pass has larger stores; the BIG stores hold 19 * 49 * 99 entries
-        }
-        // ---- markers of crowded k-mers and the padding of a bucket's last quad came along as positions: a marker empties
-        // its segment's list (1602-1606), padding is dropped (only tags next to 0xFF ever pick it up)
-        {
-          bool pad = false;
-          uint32_t wnew = 0;
-          for (int e = cnt0 + lane; e < cnt; e += 32) {
-            const uint32_t v = st_pos[e];
-            if (v == PM_RBI_MARK) wnew |= 1u << st_seg[e];
-            pad |= v == PM_RBI_EMPTY;
-          }
-          wiped |= __reduce_or_sync(FULLM, wnew);
-          if (wiped != 0 || __any_sync(FULLM, pad)) {  // in-place compaction, 32 entries at a time
-            int wr = 0;
-            for (int e0 = 0; e0 < cnt; e0 += 32) {
-              const int e = e0 + lane;
-              const uint32_t v = e < cnt ? st_pos[e] : PM_RBI_EMPTY;
-              const uint8_t sv = e < cnt ? st_seg[e] : (uint8_t)0;
-              const bool keep = v != PM_RBI_EMPTY && v != PM_RBI_MARK && !((wiped >> sv) & 1u);
-              const unsigned bal = __ballot_sync(FULLM, keep);
-              __syncwarp();
-              if (keep) {
-                const int to = wr + __popc(bal & ((1u << lane) - 1u));
-                st_pos[to] = v;
-                st_seg[to] = sv;
-              }
-              wr += __popc(bal);
-              __syncwarp();
-            }
-            cnt = wr;
-            if (lane == 0) sm.g.n_ent = (uint32_t)cnt;
-            __syncwarp();
-          }
-        }
-        // ---- entries per segment: min_spots of 2200-2207 (over the segments read in full)
-        uint32_t min_spots = 0;
-        if (mode <= M_PROBE) {
-          hist[lane] = 0;
-          __syncwarp();
-          for (int e = lane; e < cnt; e += 32) atomicAdd(&hist[st_seg[e]], 1u);
-          __syncwarp();
-          min_spots = __reduce_min_sync(FULLM, lane < (mode == M_PROBE ? k_probe : nseg) ? hist[lane] : 0xFFFFFFFFu);
-        }
-        if (mode <= M_REST && min_spots > (uint32_t)a.p.max_hits) {  // every list longer than max_hits -> no hits at all
-          tot = 0;                                                      // (also wipes the other strand's)
-          settled = true;
-          break;
-        }
-        if (mode == M_PROBE && min_spots > (uint32_t)a.p.max_hits) {  // that rule may still fire: no verdict from the probe
-          mode = M_REST;
-          continue;
-        }
-        if (mode >= M_A && wiped != 0) {
-          mode = M_REST;
-          continue;
-        }
-
-        // ---- hash of the entries by diagonal / 16.  Shared-memory paths: a slot word holds the chain head (low bits, all
-        // ones = none) and the set of segments hashed into the slot (bit 13 + segment); BIG: the head index alone.
+      auto build_hash = [&](const int n_entries) {
         for (uint32_t i = 4u * lane; i <= tab_mask; i += 128)
           *reinterpret_cast<uint4*>(st_head + i) = make_uint4(HNIL, HNIL, HNIL, HNIL);
         __syncwarp();
-        for (int e = lane; e < cnt; e += 32) {
+        for (int e = lane; e < n_entries; e += 32) {
           const int s = st_seg[e];
-          const uint32_t bin = (uint32_t)(((unsigned long long)st_pos[e] + 512ull - (uint32_t)seg_off(s)) >> 4);
+          const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
+          const uint32_t bin = (uint32_t)(((unsigned long long)st_pos[e] + 512ull - off) >> 4);
           uint32_t* hp = &st_head[rbi_hash(bin, tab_mask)];
           uint32_t old;
           if (BIG) {
@@ -592,170 +412,250 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
           st_next[e] = old == HNIL ? NIL : (NextT)old;
         }
         __syncwarp();
-
-        if (mode == M_PROBE || mode == M_B) {
-          // ---- is there a pair of entries of two different segments (M_B: of the first k) whose diagonals lie within
-          // 2 (max_off - 1) of each other (M_B: entries exactly on d excepted) ?
-          const int lim = mode == M_B ? sc_k : nseg;
-          bool pair = false;
-          uint32_t on_d = 0, cov2 = 0;
-          int n_first = 0;
-          for (int e = lane; e < cnt; e += 32) {
-            const int s = st_seg[e];
-            const long long de = (long long)st_pos[e] - (long long)seg_off(s);
-            if (mode == M_B) {
-              const long long dd = de - sc_d;
-              n_first += s < lim;
-              if (dd > -(long long)mo && dd < (long long)mo) cov2 |= 1u << s;
-              if (dd == 0) {
-                on_d |= 1u << s;
-                continue;
-              }
-            }
-            if (s >= lim) continue;
-            const uint32_t bin = (uint32_t)((de + 512ll) >> 4);
-#pragma unroll 1
-            for (int db = -2; db <= 2; db++) {
-              uint32_t q = st_head[rbi_hash(bin + (uint32_t)db, tab_mask)] & IMASK;
-              while (q != HNIL) {
-                const int sq = st_seg[q];
-                if (sq != s && sq < lim) {
-                  const long long x = (long long)st_pos[q] - (long long)seg_off(sq) - de;
-                  if (x > -2ll * mo + 1 && x < 2ll * mo - 1) pair = true;
-                }
-                const NextT nx = st_next[q];
-                q = nx == NIL ? HNIL : (uint32_t)nx;
-              }
-            }
-          }
-          pair = __any_sync(FULLM, pair) != 0;
-          if (mode == M_PROBE) {
-            if (!pair) {  // no anchor of this strand reaches min_match: the strand leaves the hit list as it is
-              settled = true;
-              break;
-            }
-            mode = M_REST;
-            continue;
-          }
-          on_d = __reduce_or_sync(FULLM, on_d);
-          cov2 = __reduce_or_sync(FULLM, cov2);
-          n_first = __reduce_add_sync(FULLM, n_first);
-          const int s_first = __ffs((int)on_d) - 1;
-          const int f_max = s_first < 0 ? 0 : 1 + __popc(cov2 & ~((2u << s_first) - 1u));
-          if (pair || tot + n_first >= a.p.max_hits || f_max < sc_f0) {
-            mode = M_REST;
-            continue;
-          }
-          min_match = f_max;  // 2251-2260: the chain's first anchor resets the hit list
-          tot = 1;
-          if (lane == 0) {
-            sm.hit_pos[0] = (uint32_t)(sc_d + (long long)seg_off(s_first));
-            sm.hit_off[0] = (uint16_t)seg_off(s_first);
-            sm.hit_or[0] = (uint8_t)strand;
-          }
-          __syncwarp();
-          settled = true;
-          break;
-        }
-
-        // ---- found count of every entry as an anchor (2230-2249): later segments with a position whose diagonal is
-        // within max_off - 1 of the anchor's.  The segments present in the three slots around the anchor bound it from
-        // above; only anchors whose bound reaches min_match (the read's true locus, rarely a chance cluster) walk the chains.
-        relevant = false;
-        {
-          int np = 0;  // anchors waiting in sm.pend (warp-uniform): they are walked 32 at a time, all lanes busy
-          for (int e0 = 0; e0 < cnt; e0 += 32) {
-            const int e = e0 + lane;
-            bool pass = false;
-            if (e < cnt) {
-              const int s = st_seg[e];
-              if (1 + max_depth - s >= min_match) {  // an anchor of segment s reaches at most 1 + max_depth - s
-                pass = true;
-                if (!BIG) {
-                  const uint32_t bin = (uint32_t)(((unsigned long long)st_pos[e] + 512ull - (uint32_t)seg_off(s)) >> 4);
-                  const uint32_t hw = st_head[rbi_hash(bin - 1u, tab_mask)] | st_head[rbi_hash(bin, tab_mask)] |
-                                      st_head[rbi_hash(bin + 1u, tab_mask)];
-                  pass = 1 + __popc((hw >> 13) & ~((2u << s) - 1u)) >= min_match;
-                }
-              }
-              if (!pass) st_found[e] = 0;
-            }
-            const unsigned bal = __ballot_sync(FULLM, pass);
-            if (pass) sm.g.pend[np + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)e;
-            np += __popc(bal);
-            __syncwarp();
-            const bool last = e0 + 32 >= cnt;
-            while (np >= 32 || (last && np > 0)) {
-              if (lane < np) {
-                const uint32_t ea = sm.g.pend[lane];
-                const int s = st_seg[ea];
-                const long long dg = (long long)st_pos[ea] + 512ll - (long long)seg_off(s);
-                const uint32_t bin = (uint32_t)(dg >> 4);
-                uint32_t segs = 0;
+      };
+      // Is there a pair of entries of two different segments whose diagonals lie within 2 * (max_off - 1) of each other?
+      // An anchor with `found` = F has F of the nseg segments agreeing within max_off - 1 of its diagonal, so at most
+      // nseg - F segments are outside the chain and ANY nseg - F + 2 segments hold two of its members: without such a
+      // pair among the first nseg - F + 2 segments no anchor of the strand reaches F.
+      auto close_pair_exists = [&](const int n_entries) {
+        bool yes = false;
+        for (int e = lane; e < n_entries; e += 32) {
+          const int s = st_seg[e];
+          const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
+          const long long dg = (long long)st_pos[e] + 512ll - (long long)off;
+          const uint32_t bin = (uint32_t)(dg >> 4);
 #pragma unroll
-                for (int db = 0; db < 3; db++) {
-                  uint32_t q = st_head[rbi_hash(bin + (uint32_t)(db - 1), tab_mask)] & IMASK;
-                  while (q != HNIL) {
-                    const int sq = st_seg[q];
-                    if (sq > s) {
-                      const long long d = (long long)st_pos[q] + 512ll - (long long)seg_off(sq) - dg;
-                      if (d > -(long long)mo && d < (long long)mo) segs |= 1u << sq;  // 2244
-                    }
-                    const NextT nx = st_next[q];
-                    q = nx == NIL ? HNIL : (uint32_t)nx;
-                  }
-                }
-                const int fnd = 1 + __popc(segs);
-                st_found[ea] = (uint8_t)fnd;
-                relevant |= fnd >= min_match;
+          for (int db = -2; db <= 2; db++) {
+            uint32_t q = st_head[rbi_hash(bin + (uint32_t)db, tab_mask)] & IMASK;
+            while (q != HNIL) {
+              const int sq = st_seg[q];
+              if (sq != s) {
+                const uint32_t offq = (sq < total_cuts) ? 16u * (uint32_t)sq : (uint32_t)(len - 16);
+                const long long d = (long long)st_pos[q] + 512ll - (long long)offq - dg;
+                if (d > -2ll * mo + 1 && d < 2ll * mo - 1) yes = true;
               }
-              const uint32_t keepv = (lane + 32 < np) ? sm.g.pend[32 + lane] : 0u;
-              __syncwarp();
-              if (lane + 32 < np) sm.g.pend[lane] = keepv;
-              np = np > 32 ? np - 32 : 0;
-              __syncwarp();
+              const NextT nx = st_next[q];
+              q = nx == NIL ? HNIL : (uint32_t)nx;
+            }
+          }
+        }
+        return __any_sync(0xFFFFFFFFu, yes) != 0;
+      };
+      // ---- gather (get_mers 2158-2165, loop 1594-1612 / 1619-1637): per segment, every entry of its four buckets whose
+      // tag is the segment's tag or one 2-bit field away from it
+      // With the running min_match at F the first nseg - F + 2 segments decide whether the strand can matter at all (see
+      // close_pair_exists): after a full-length hit on the forward strand the reverse strand is settled by two segments.
+      // (tried for every strand, i.e. also 8 of 10 segments at the initial min_match of 4: 269 against 201 ms per 8 M
+      // read-mates - the probe's hash build and the broken prefetch run cost more than two segments of reads)
+      const int k_probe = nseg - min_match + 2 <= nseg / 2 ? nseg - min_match + 2 : 0;
+      bool strand_dead = false;
+      int cnt = 0;              // warp-uniform copy of sm.g.n_ent between segments
+      uint32_t min_spots = 10000;
+      bool overflow = false;
+      if (lane == 0) sm.g.n_ent = 0;
+      __syncwarp();
+      // Bytes in flight, not bandwidth, bound the bucket reads (24 warps x 32 lanes x a few 16-byte registers keep
+      // HBM's queues too short for it to schedule well: 3.2 TB/s; the same reads issued 250 KB deep per SM reach
+      // 5.5-6 TB/s, tools/chunk_probe.cu).  So the buckets of the segments ahead are pulled into L2 by prefetches, one
+      // 128-byte line per lane and instruction, which cost neither registers nor shared memory.
+      auto prefetch_segment = [&](const int sp) {
+        if (sp >= nseg) return;
+        const int bp = 4 * (strand * nseg + sp) + rot;
+        const char* p0 = reinterpret_cast<const char*>(rdata + 5ull * sm.b_off[bp]);
+        const uint32_t bytes = 20u * sm.b_n4[bp];  // 80 bytes per block = 20 per quad
+#if PM_RBI_PREFETCH_MODE == 1   /* one bulk prefetch per bucket (TMA unit): the whole byte range at once */
+        if (l8 == 0 && bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p0), "r"(bytes) : "memory");
+#else                           /* one line-sized piece per lane and instruction */
+        const char* line = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p0) & ~(uintptr_t)(PM_RBI_PREFETCH_STRIDE - 1)) +
+                           PM_RBI_PREFETCH_STRIDE * l8;
+        for (; line < p0 + bytes; line += 8 * PM_RBI_PREFETCH_STRIDE) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+#endif
+      };
+#if PM_RBI_PREFETCH > 0
+      for (int sp = 0; sp < PM_RBI_PREFETCH; sp++)
+        if (k_probe == 0 || sp < k_probe) prefetch_segment(sp);
+#endif
+      for (int s = 0; s < nseg; s++) {
+#if PM_RBI_PREFETCH > 0
+        if (k_probe == 0 || s + PM_RBI_PREFETCH < k_probe || s >= k_probe) prefetch_segment(s + PM_RBI_PREFETCH);
+#endif
+        const int b = 4 * (strand * nseg + s) + rot;
+        const uint32_t n4 = sm.b_n4[b];
+        const uint4* base = rdata + 5ull * sm.b_off[b];  // 80-byte blocks
+        const uint32_t etagx = ((sm.kcode[strand * nseg + s] >> (8 * rot)) & 255u) * 0x01010101u;
+        const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, n4);
+        const int cnt0 = cnt;
+        for (uint32_t q0 = 0; q0 < nmax; q0 += 8 * PM_RBI_UNROLL) {
+          uint4 P[PM_RBI_UNROLL];
+          uint32_t T[PM_RBI_UNROLL];
+#pragma unroll
+          for (int u = 0; u < PM_RBI_UNROLL; u++) {
+            const uint32_t q = q0 + (uint32_t)(8 * u + l8);
+            T[u] = etagx ^ 0x0F0F0F0Fu;  // two fields away: never qualifies (P[u] is then never looked at)
+            if (q < n4) {
+#if PM_RBI_EXPERIMENT == 2   /* timing experiment: no bucket loads, pseudo-random tags and positions */
+              uint32_t x = (q + sm.b_off[b]) * 0x9E3779B1u;
+              x ^= x >> 15;
+              x *= 0x85EBCA77u;
+              T[u] = x ^ (x >> 13);
+              P[u] = make_uint4(x & 0x7FFFFFFFu, (x * 3u) & 0x7FFFFFFFu, (x * 5u) & 0x7FFFFFFFu, (x * 7u) & 0x7FFFFFFFu);
+#else
+              const uint4* blk = base + 5u * (q >> 2);  // quad q: positions at 16 * (q & 3), its four tags at 64 + 4 * (q & 3)
+              P[u] = rbi_ld16(blk + (q & 3u));
+              T[u] = rbi_ld4(reinterpret_cast<const uint32_t*>(blk + 4) + (q & 3u));
+#endif
+            }
+          }
+#if PM_RBI_EXPERIMENT == 1   /* timing experiment: the bucket loads alone */
+          {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int u = 0; u < PM_RBI_UNROLL; u++)
+              if (q0 + (uint32_t)(8 * u + l8) < n4) acc ^= P[u].x ^ P[u].y ^ P[u].z ^ P[u].w ^ T[u];
+            if (acc == 0x12345678u) overflow = true;
+            continue;
+          }
+#endif
+#pragma unroll
+          for (int u = 0; u < PM_RBI_UNROLL; u++) {
+            // per tag byte: fields that differ from the exact tag; a byte qualifies when at most one field differs
+            const uint32_t X = T[u] ^ etagx;
+            const uint32_t D = (X | (X >> 1)) & 0x55555555u;
+            const uint32_t Z = D & ((D | 0x80808080u) - 0x01010101u);             // byte == 0 <=> <= 1 field differs
+            uint32_t hit = ((Z + 0x7F7F7F7Fu) & 0x80808080u) ^ 0x80808080u;       // bit 7 of byte k: tag k qualifies
+            hit &= ((D + 0x7F7F7F7Fu) & 0x80808080u) | keep_exact;                 // ... and it is not the exact tag (rot > 0)
+            if (hit) {  // ~19 % of the quads: the lane reserves its slots in the strand's list and fills them, no loop
+              const uint32_t at = atomicAdd(&sm.g.n_ent, (uint32_t)__popc(hit));
+              if (at + 4u <= (uint32_t)cap) {
+                if (hit & 0x80u) st_pos[at] = P[u].x;
+                if (hit & 0x8000u) st_pos[at + ((hit >> 7) & 1u)] = P[u].y;
+                if (hit & 0x800000u) st_pos[at + (uint32_t)__popc(hit & 0x8080u)] = P[u].z;
+                if (hit & 0x80000000u) st_pos[at + (uint32_t)__popc(hit & 0x808080u)] = P[u].w;
+              } else {
+                overflow = true;
+              }
             }
           }
         }
         __syncwarp();
-        if (mode != M_A) break;  // M_FULL / M_REST: on to the rules
-
-        // ---- M_A: the best anchor over rotation 0 alone (largest found, then the lowest entry), the segments it covers
-        {
-          uint32_t bestkey = 0;
-          for (int e = lane; e < cnt; e += 32) bestkey = max(bestkey, ((uint32_t)st_found[e] << 16) | (uint32_t)(0xFFFF - e));
-          bestkey = __reduce_max_sync(FULLM, bestkey);
-          const int f0 = (int)(bestkey >> 16);
-          const int k = nseg - f0 + 2;
-          mode = M_REST;
-          if (f0 <= min_match || k > nseg / 2) continue;
-          const int eb = 0xFFFF - (int)(bestkey & 0xFFFFu);
-          const long long d = (long long)st_pos[eb] - (long long)seg_off(st_seg[eb]);
-          uint32_t cov = 0;
-          bool rival = false;  // a second diagonal whose chain is as long (a repeat): M_B would only find that out later
-          for (int e = lane; e < cnt; e += 32) {
-            const long long dd = (long long)st_pos[e] - (long long)seg_off(st_seg[e]) - d;
-            if (dd > -(long long)mo && dd < (long long)mo) cov |= 1u << st_seg[e];
-            rival |= dd != 0 && (int)st_found[e] >= f0;
+        cnt = (int)sm.g.n_ent;
+        if (cnt > cap) cnt = cap;  // (overflow is reported below; keep the reads in range)
+        // markers of crowded k-mers and the padding of a bucket's last quad came along as positions: a marker empties
+        // the segment's list (1602-1606), padding is dropped (only tags next to 0xFF ever pick it up)
+        bool crowded = false, padded = false;
+        for (int e = cnt0 + lane; e < cnt; e += 32) {
+          const uint32_t v = st_pos[e];
+          crowded |= v == PM_RBI_MARK;
+          padded |= v == PM_RBI_EMPTY;
+          st_seg[e] = (uint8_t)s;
+        }
+        if (__any_sync(0xFFFFFFFFu, crowded)) cnt = cnt0;
+        else if (__any_sync(0xFFFFFFFFu, padded)) {  // stable in-place compaction, 32 entries at a time
+          int wr = cnt0;
+          for (int e0 = cnt0; e0 < cnt; e0 += 32) {
+            const int e = e0 + lane;
+            const uint32_t v = e < cnt ? st_pos[e] : PM_RBI_EMPTY;
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, v != PM_RBI_EMPTY);
+            __syncwarp();
+            if (v != PM_RBI_EMPTY) st_pos[wr + __popc(bal & ((1u << lane) - 1u))] = v;
+            wr += __popc(bal);
+            __syncwarp();
           }
-          cov = __reduce_or_sync(FULLM, cov);
-          if (__any_sync(FULLM, rival)) continue;
-          const uint32_t fm = (((1u << k) - 1u) | ~cov) & ((1u << nseg) - 1u);  // segments to read in full
-          bool flagged = false;  // a bucket that would stay unread may hold a marker
-          for (int i = lane; i < nb; i += 32)
-            if ((i & 3) != 0 && !((fm >> (i >> 2)) & 1u) && (sm.b_n4[sb + i] & 0x8000u)) flagged = true;
-          if (__any_sync(FULLM, flagged)) continue;
-          sc_d = d;
-          sc_f0 = f0;
-          sc_k = k;
-          sc_fm = fm;
-          mode = M_B;
+          cnt = wr;
+        }
+        __syncwarp();
+        if (lane == 0) sm.g.n_ent = (uint32_t)cnt;
+        __syncwarp();
+        min_spots = min(min_spots, (uint32_t)(cnt - cnt0));
+        if (s + 1 == k_probe && min_spots <= (uint32_t)a.p.max_hits && !__any_sync(0xFFFFFFFFu, overflow)) {
+          // (min_spots <= max_hits: the rule of 2200-2207 cannot fire whatever the other segments hold)
+          build_hash(cnt);
+          if (!close_pair_exists(cnt)) {
+            strand_dead = true;
+            break;
+          }
         }
       }
-      l_pos += (unsigned long long)cnt;
-      if (settled) continue;
-      if (!__any_sync(FULLM, relevant)) continue;  // the usual fate of the strand the read does not come from
+      if (strand_dead) {  // no anchor of this strand reaches min_match: the strand leaves the hit list as it is
+        l_pos += (unsigned long long)cnt;
+        continue;
+      }
+      if (__any_sync(0xFFFFFFFFu, overflow)) {
+        if (!BIG) return false;  // the BIG stores hold 19 * 49 * 99 entries
+      }
       const int N = cnt;
+      l_pos += (unsigned long long)N;
+      __syncwarp();
+      // ---- 2200-2207: every segment list longer than max_hits -> no hits at all (also wipes the other strand's)
+      if (min_spots > (uint32_t)a.p.max_hits) {
+        tot = 0;
+        continue;
+      }
+
+      build_hash(N);
+      // ---- found count of every entry as an anchor (2230-2249): later segments with a position whose diagonal is
+      // within max_off - 1 of the anchor's.  The segments present in the three slots around the anchor bound it from
+      // above; only anchors whose bound reaches min_match (the read's true locus, rarely a chance cluster) walk the chains.
+      bool relevant = false;  // some anchor reaches the running min_match
+      auto exact_found = [&](const uint32_t e) {
+        const int s = st_seg[e];
+        const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
+        const long long dg = (long long)st_pos[e] + 512ll - (long long)off;
+        const uint32_t bin = (uint32_t)(dg >> 4);
+        uint32_t segs = 0;
+#pragma unroll
+        for (int db = 0; db < 3; db++) {
+          const uint32_t hw = st_head[rbi_hash(bin + (uint32_t)(db - 1), tab_mask)];
+          uint32_t q = hw & IMASK;
+          while (q != HNIL) {
+            const int sq = st_seg[q];
+            if (sq > s) {
+              const uint32_t offq = (sq < total_cuts) ? 16u * (uint32_t)sq : (uint32_t)(len - 16);
+              const long long d = (long long)st_pos[q] + 512ll - (long long)offq - dg;
+              if (d > -(long long)mo && d < (long long)mo) segs |= 1u << sq;  // 2244
+            }
+            const NextT nx = st_next[q];
+            q = nx == NIL ? HNIL : (uint32_t)nx;
+          }
+        }
+        const int fnd = 1 + __popc(segs);
+        st_found[e] = (uint8_t)fnd;
+        relevant |= fnd >= min_match;
+      };
+      int np = 0;  // anchors waiting in sm.pend (warp-uniform): they are walked 32 at a time, all lanes busy
+      for (int e0 = 0; e0 < N; e0 += 32) {
+        const int e = e0 + lane;
+        bool pass = false;
+        if (e < N) {
+          const int s = st_seg[e];
+          if (1 + max_depth - s >= min_match) {  // an anchor of segment s reaches at most 1 + max_depth - s
+            pass = true;
+            if (!BIG) {
+              const uint32_t off = (s < total_cuts) ? 16u * (uint32_t)s : (uint32_t)(len - 16);
+              const uint32_t bin = (uint32_t)(((unsigned long long)st_pos[e] + 512ull - off) >> 4);
+              const uint32_t hw = st_head[rbi_hash(bin - 1u, tab_mask)] | st_head[rbi_hash(bin, tab_mask)] |
+                                  st_head[rbi_hash(bin + 1u, tab_mask)];
+              pass = 1 + __popc((hw >> 13) & ~((2u << s) - 1u)) >= min_match;
+            }
+          }
+          if (!pass) st_found[e] = 0;
+        }
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
+        if (pass) sm.g.pend[np + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)e;
+        np += __popc(bal);
+        __syncwarp();
+        if (np >= 32) {
+          exact_found(sm.g.pend[lane]);
+          const uint32_t keep = lane < np - 32 ? sm.g.pend[32 + lane] : 0u;
+          __syncwarp();
+          if (lane < np - 32) sm.g.pend[lane] = keep;
+          np -= 32;
+          __syncwarp();
+        }
+      }
+      if (lane < np) exact_found(sm.g.pend[lane]);
+      __syncwarp();
+      if (!__any_sync(0xFFFFFFFFu, relevant)) continue;  // the usual fate of the strand the read does not come from
 
       // ---- the reference's sequential rules over the anchors that can still matter, in its order: segment, position
       bool done = false;
@@ -839,7 +739,7 @@ __device__ __forceinline__ bool rbi_map_read_mate(const SeedRbiArgs& a, RbiWarpS
 // CAP > 0: stores in shared memory; CAP = 0: in the per-warp global scratch.  Work items are all read-mates of the
 // chunk (work_list == nullptr) or the ones an earlier pass could not hold; the ones this pass cannot hold go to next_list.
 template <int WARPS, int CAP>
-__global__ void __launch_bounds__(WARPS * 32, (CAP == PM_RBI_CAP ? 3 : 1)) k_seed_rbi(SeedRbiArgs a) {
+__global__ void __launch_bounds__(WARPS * 32) k_seed_rbi(SeedRbiArgs a) {
   extern __shared__ __align__(16) unsigned char rbi_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   RbiWarpSmem& sm = reinterpret_cast<RbiWarpSmem*>(rbi_smem)[warp];

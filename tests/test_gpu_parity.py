@@ -253,9 +253,8 @@ def test_diagonal_certificate_changes_nothing(name, get_fixture, monkeypatch):
 def test_seed_index_layouts_agree(name, get_fixture, monkeypatch):
     """The seed stage reads a device-private rotated bucket index (seed_rbi.cuh); PEMAP_SEED=legacy runs the round-1
     kernel over pos_index / mers as the reference lays them out, and PEMAP_RBI_CAP=8 pushes nearly every read-mate
-    through the second (global-memory) pass of the new kernel; PEMAP_SHORTCUT=0 switches the single-chain shortcut off
-    (every strand then reads all four rotations of all its segments).  Candidate lists in order, loci, types, pileup
-    records and insertions must be identical in all four."""
+    through the second (global-memory) pass of the new kernel.  Candidate lists in order, loci, types, pileup records
+    and insertions must be identical in all three."""
     fx = get_fixture(name)
     bis = int(getattr(fx, "bisulfite", False))
     for run in fx.runs:
@@ -263,10 +262,9 @@ def test_seed_index_layouts_agree(name, get_fixture, monkeypatch):
                   is_bisulfite=int(run.bisulfite))
         n = min(20000, run.reads1.shape[0])
         out = {}
-        for mode in ("legacy", "rbi", "rbi-big", "rbi-full"):
+        for mode in ("legacy", "rbi", "rbi-big"):
             monkeypatch.setenv("PEMAP_SEED", "legacy" if mode == "legacy" else "rbi")
             monkeypatch.setenv("PEMAP_RBI_CAP", "8" if mode == "rbi-big" else "512")
-            monkeypatch.setenv("PEMAP_SHORTCUT", "0" if mode == "rbi-full" else "1")
             mapper = pb.PEMapper.from_genome(fx.genome, pb.default_params(is_bisulfite=bis))
             mapper.set_params(**kw)
             mapper.keep(pb.KEEP_CANDIDATES)
@@ -276,7 +274,7 @@ def test_seed_index_layouts_agree(name, get_fixture, monkeypatch):
             st = mapper.stats()
             out[mode] = (g, cands, rec.tobytes(), sorted(ins), st["candidates"], st["mer_positions"])
             mapper.close()
-        for mode in ("rbi", "rbi-big", "rbi-full"):
+        for mode in ("rbi", "rbi-big"):
             tag = "%s/%s %s vs legacy" % (name, run.name, mode)
             for x, y in zip(out["legacy"][0], out[mode][0]):
                 assert np.array_equal(x, y), tag + ": per-read results"
