@@ -19,11 +19,12 @@ run python bench.py --steps 5 --warmup 3 > $O/bench_cfg3_r02.json 2> $O/bench_cf
 run python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref_cfg3_r02.json 2> $O/bench_ref_cfg3.err
 run python bench.py --config cfg2 --steps 5 --warmup 3 > $O/bench_cfg2_r02.json 2> $O/bench_cfg2.err
 # ncu: launch list of every kernel of ours over four passes of 1 M pairs on cfg3 (the last pass is the warm one), then
-# --set full of the dominant kernels, one launch each
+# --set full of the dominant kernels, one launch each (one lane = two chunks of 524288 pairs per pass: k_seed_rbi matches three
+# launches per chunk, the DP regex four; the warm pass starts at chunk 6)
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 900 --csv --log-file $O/launches_r02.csv \
     python tools/cfg3_check.py 1048576 > $O/ncu_launches.log 2>&1
-ncu --set full --import-source on --clock-control none --kernel-name regex:k_seed_rbi --launch-skip 36 --launch-count 1 \
+ncu --set full --import-source on --clock-control none --kernel-name regex:k_seed_rbi --launch-skip 18 --launch-count 1 \
     -o $O/ncu_seed_rbi_r02 python tools/cfg3_check.py 1048576 > $O/ncu_seed.log 2>&1
-ncu --set full --clock-control none --kernel-name regex:"k_sw_i16|k_trace_dp16|k_trace_walk16|k_diag_certify" --launch-skip 48 --launch-count 4 \
+ncu --set full --clock-control none --kernel-name regex:"k_sw_i16|k_trace_dp16|k_trace_walk16|k_diag_certify" --launch-skip 24 --launch-count 4 \
     -o $O/ncu_dp_r02 python tools/cfg3_check.py 1048576 > $O/ncu_dp.log 2>&1
 ls -la $O/*r02* >&2
